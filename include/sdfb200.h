@@ -1,0 +1,100 @@
+/*
+ * sdfb200.h -- C-ABI of libsdfb200.so: the B200-native replacement for the
+ * mesh-generation hot path of fogleman/sdf.
+ *
+ * The reference is pure Python; the "FFI" a maintainer would bind is therefore a
+ * ctypes stub (INTEGRATION.md shows it).  Each entry point names the reference
+ * interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions: every function returns 0 on success or a negative SDFB200_E_*
+ * code; sdfb200_last_error() returns a thread-local message for the last
+ * failure on the calling thread.  No C++ exception crosses this boundary.
+ * Pointers may be host or device pointers (detected with
+ * cudaPointerGetAttributes); host buffers are staged through device memory
+ * inside the call.  `stream` is a cudaStream_t (NULL = default stream); calls
+ * are re-entrant per (program, stream).
+ */
+#ifndef SDFB200_H
+#define SDFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFB200_ABI_VERSION 1
+
+#define SDFB200_OK 0
+#define SDFB200_E_INVALID (-1)   /* bad argument / malformed program            */
+#define SDFB200_E_CUDA (-2)      /* CUDA runtime error (message has the detail)  */
+#define SDFB200_E_CAPACITY (-3)  /* tri_out too small; *n_tri = required count   */
+#define SDFB200_E_NOGPU (-4)     /* no CUDA device: there is NO CPU fallback     */
+
+/* precision modes of sdfb200_generate */
+#define SDFB200_PREC_F32 0    /* float32 evaluation only                                      */
+#define SDFB200_PREC_MIXED 1  /* float32, then float64 re-evaluation of samples with |d| < tau */
+#define SDFB200_PREC_F64 2    /* float64 evaluation of every sample (reference arithmetic)    */
+
+typedef struct sdfb200_prog sdfb200_prog;
+
+int sdfb200_abi_version(void);
+const char* sdfb200_last_error(void);
+int sdfb200_device_count(int* count);
+
+/*
+ * Replaces: construction of the closure tree by the @sdf3/@op3 factories
+ * (sdf/d3.py:48-63) -- the lowered program of sdf_b200/ir.py.
+ *   code[n_code]     instruction words  op | a << 8 | const_index << 16
+ *   consts[n_consts] float64 constants (converted once to float32 for the f32 path)
+ */
+int sdfb200_program_create(const uint32_t* code, int n_code, const double* consts, int n_consts,
+                           sdfb200_prog** out);
+void sdfb200_program_free(sdfb200_prog* prog);
+
+/*
+ * Replaces: SDF3.__call__(p) (sdf/d3.py:24-25) on a point block.
+ *   xyz: n x 3 points (AoS, the reference's P[N,3] layout of core.py:20-26), d_out: n distances.
+ * f32: 12 B/point read + 4 B/point written, streamed through shared memory by
+ * bulk async copies.  f64: the reference's float64 arithmetic.
+ */
+int sdfb200_eval_f32(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream);
+int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n, double* d_out, int device, void* stream);
+
+/*
+ * Replaces: the batch loop of core.generate (sdf/core.py:114-141), i.e. per batch
+ * _skip (core.py:28-43), _cartesian_product + sdf(P) (core.py:51-52),
+ * _marching_cubes (core.py:16-18) and the world mapping (core.py:58-60).
+ *
+ *   xs/ys/zs     the float64 sample axes exactly as np.arange produced them (core.py:110-112)
+ *   batch_size   cubes per batch side (core.py:14)
+ *   sparse       core.py:47
+ *   precision    SDFB200_PREC_*
+ *   tau          PREC_MIXED: samples with |d_f32| < tau are re-evaluated in float64 (sign safety)
+ *   zb_begin/end this call's range of Z batch layers (multi-GPU slab split); 0, -1 = all
+ *   tri_out      9 float32 per triangle (3 world-space vertices, verts[faces] order), caller-owned,
+ *                host or device; NULL = count only
+ *   n_tri        triangles produced (or required, with SDFB200_E_CAPACITY)
+ *   stats[6]     skipped, empty, nonempty batches (core.py:135-141), samples evaluated in f32,
+ *                samples re-evaluated in f64, active cubes
+ *   timings_ms[4] optional: skip pre-pass, fused eval+MC kernel, whole device section, D2H
+ */
+int sdfb200_generate(sdfb200_prog* prog,
+                     const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
+                     int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
+                     float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
+                     double timings_ms[4], int device, void* stream);
+
+/*
+ * Replaces: nothing in the reference (diagnostic / load balancing): the skip
+ * flags of every batch (1 = skipped), X-major / Z-fastest batch order of
+ * core.py:119.  flags: host pointer, nbx*nby*nbz bytes.
+ */
+int sdfb200_skip_flags(sdfb200_prog* prog,
+                       const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
+                       int batch_size, uint8_t* flags, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFB200_H */

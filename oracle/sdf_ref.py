@@ -1,0 +1,490 @@
+"""ORACLE (test infrastructure, not product code).
+
+CPU restatement, in numpy float64, of the reference's mesh-generation hot path:
+
+  * node formulas            /root/reference/sdf/d3.py:92-502, sdf/dn.py:7-114
+  * grid / batching / skip   sdf/core.py:20-60, 84-150
+  * bounds estimation        sdf/core.py:62-82
+  * marching cubes           sdf/core.py:16-18 -> oracle/mc_lewiner.c (C restatement of
+                             skimage's Lewiner MC; PARITY UNPINNED, see that file)
+
+It walks the product's IR tree (sdf_b200.ir.Node) so that one model definition
+drives both the CUDA path and this checker.  The numpy expressions follow the
+reference's operation order so that, in float64, results are bit-identical to
+the reference closures wherever numpy itself is deterministic (pinned by
+tests/golden/*.npz, which were produced by importing the real reference with a
+stub ``skimage`` module: tests/golden/make_golden.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+import ctypes
+import itertools
+import os
+import subprocess
+
+import numpy as np
+
+from sdf_b200.ir import node_of
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+_min = np.minimum
+_max = np.maximum
+
+
+def _length(a):
+    return np.linalg.norm(a, axis=1)
+
+
+def _dot(a, b):
+    return np.sum(a * b, axis=1)
+
+
+def _vec(*arrs):
+    return np.stack(arrs, axis=-1)
+
+
+# --------------------------------------------------------------------------
+# node evaluation.  Every function takes the constants (float64 list) and the
+# (N,3) point block and returns what the reference closure returns.
+
+def _p_sphere(c, p):                       # d3.py:92-96
+    return _length(p - np.array(c[0:3])) - c[3]
+
+
+def _p_plane(c, p):                        # d3.py:98-103
+    return np.dot(np.array(c[3:6]) - p, np.array(c[0:3]))
+
+
+def _p_box(c, p):                          # d3.py:131-133 (c[3:6] is size / 2)
+    q = np.abs(p - np.array(c[0:3])) - np.array(c[3:6])
+    return _length(_max(q, 0)) + _min(np.amax(q, axis=1), 0)
+
+
+def _p_rounded_box(c, p):                  # d3.py:139-141
+    q = np.abs(p) - np.array(c[0:3]) + c[3]
+    return _length(_max(q, 0)) + _min(np.amax(q, axis=1), 0) - c[3]
+
+
+def _p_wireframe_box(c, p):                # d3.py:147-154
+    half, t = np.array(c[0:3]), c[3]
+
+    def g(a, b, cc):
+        return _length(_max(_vec(a, b, cc), 0)) + _min(_max(a, _max(b, cc)), 0)
+    p = np.abs(p) - half - t / 2
+    q = np.abs(p + t / 2) - t / 2
+    px, py, pz = p[:, 0], p[:, 1], p[:, 2]
+    qx, qy, qz = q[:, 0], q[:, 1], q[:, 2]
+    return _min(_min(g(px, qy, qz), g(qx, py, qz)), g(qx, qy, pz))
+
+
+def _p_torus(c, p):                        # d3.py:159-164
+    a = _length(p[:, [0, 1]]) - c[0]
+    return _length(_vec(a, p[:, 2])) - c[1]
+
+
+def _p_capsule(c, p):                      # d3.py:171-175
+    a, b = np.array(c[0:3]), np.array(c[3:6])
+    pa = p - a
+    ba = b - a
+    h = np.clip(np.dot(pa, ba) / np.dot(ba, ba), 0, 1).reshape((-1, 1))
+    return _length(pa - np.multiply(ba, h)) - c[6]
+
+
+def _p_cylinder(c, p):                     # d3.py:180-181
+    return _length(p[:, [0, 1]]) - c[0]
+
+
+def _p_capped_cylinder(c, p):              # d3.py:188-203
+    a, b, radius = np.array(c[0:3]), np.array(c[3:6]), c[6]
+    ba = b - a
+    pa = p - a
+    baba = np.dot(ba, ba)
+    paba = np.dot(pa, ba).reshape((-1, 1))
+    x = _length(pa * baba - ba * paba) - radius * baba
+    y = np.abs(paba - baba * 0.5) - baba * 0.5
+    x = x.reshape((-1, 1))
+    y = y.reshape((-1, 1))
+    x2 = x * x
+    y2 = y * y * baba
+    d = np.where(_max(x, y) < 0, -_min(x2, y2), np.where(x > 0, x2, 0) + np.where(y > 0, y2, 0))
+    return np.sign(d) * np.sqrt(np.abs(d)) / baba
+
+
+def _p_rounded_cylinder(c, p):             # d3.py:208-214
+    ra, rb, h = c
+    d = _vec(_length(p[:, [0, 1]]) - ra + rb, np.abs(p[:, 2]) - h / 2 + rb)
+    return _min(_max(d[:, 0], d[:, 1]), 0) + _length(_max(d, 0)) - rb
+
+
+def _p_capped_cone(c, p):                  # d3.py:221-236
+    a, b, ra, rb = np.array(c[0:3]), np.array(c[3:6]), c[6], c[7]
+    rba = rb - ra
+    baba = np.dot(b - a, b - a)
+    papa = _dot(p - a, p - a)
+    paba = np.dot(p - a, b - a) / baba
+    x = np.sqrt(papa - paba * paba * baba)
+    cax = _max(0, x - np.where(paba < 0.5, ra, rb))
+    cay = np.abs(paba - 0.5) - 0.5
+    k = rba * rba + baba
+    f = np.clip((rba * (x - ra) + paba * baba) / k, 0, 1)
+    cbx = x - ra - f * rba
+    cby = paba - f
+    s = np.where(np.logical_and(cbx < 0, cay < 0), -1, 1)
+    return s * np.sqrt(_min(cax * cax + cay * cay * baba, cbx * cbx + cby * cby * baba))
+
+
+def _p_rounded_cone(c, p):                 # d3.py:241-249
+    r1, r2, h = c
+    q = _vec(_length(p[:, [0, 1]]), p[:, 2])
+    b = (r1 - r2) / h
+    a = np.sqrt(1 - b * b)
+    k = np.dot(q, _vec(-b, a))
+    c1 = _length(q) - r1
+    c2 = _length(q - _vec(0, h)) - r2
+    c3 = np.dot(q, _vec(a, b)) - r1
+    return np.where(k < 0, c1, np.where(k > a * h, c2, c3))
+
+
+def _p_ellipsoid(c, p):                    # d3.py:255-258
+    size = np.array(c[0:3])
+    k0 = _length(p / size)
+    k1 = _length(p / (size * size))
+    return k0 * (k0 - 1) / k1
+
+
+def _p_pyramid(c, p):                      # d3.py:263-281
+    h = c[0]
+    a = np.abs(p[:, [0, 1]]) - 0.5
+    w = a[:, 1] > a[:, 0]
+    a[w] = a[:, [1, 0]][w]
+    px = a[:, 0]
+    py = p[:, 2]
+    pz = a[:, 1]
+    m2 = h * h + 0.25
+    qx = pz
+    qy = h * py - 0.5 * px
+    qz = h * px + 0.5 * py
+    s = _max(-qx, 0)
+    t = np.clip((qy - 0.5 * pz) / (m2 + 0.25), 0, 1)
+    a = m2 * (qx + s) ** 2 + qy * qy
+    b = m2 * (qx + 0.5 * t) ** 2 + (qy - m2 * t) ** 2
+    d2 = np.where(_min(qy, -qx * m2 - qy * 0.5) > 0, 0, _min(a, b))
+    return np.sqrt((d2 + qz * qz) / m2) * np.sign(_max(qz, -py))
+
+
+def _p_tetrahedron(c, p):                  # d3.py:288-292
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    return (_max(np.abs(x + y) - z, np.abs(x - y) + z) - c[0]) / np.sqrt(3)
+
+
+def _p_octahedron(c, p):                   # d3.py:297-298 (c[1] = tan(radians(30)))
+    return (np.sum(np.abs(p), axis=1) - c[0]) * c[1]
+
+
+def _p_dodecahedron(c, p):                 # d3.py:303-310
+    r, x, y, z = c
+    p = np.abs(p / r)
+    a = np.dot(p, (x, y, z))
+    b = np.dot(p, (z, x, y))
+    cc = np.dot(p, (y, z, x))
+    return (_max(_max(a, b), cc) - x) * r
+
+
+def _p_icosahedron(c, p):                  # d3.py:318-324 (c[0] already scaled by 0.85065...)
+    r, x, y, z, w = c
+    p = np.abs(p / r)
+    a = np.dot(p, (x, y, z))
+    b = np.dot(p, (z, x, y))
+    cc = np.dot(p, (y, z, x))
+    d = np.dot(p, (w, w, w)) - x
+    return _max(_max(_max(a, b), cc) - x, d) * r
+
+
+_PRIMS = {
+    'SPHERE': _p_sphere, 'PLANE': _p_plane, 'BOX': _p_box, 'ROUNDED_BOX': _p_rounded_box,
+    'WIREFRAME_BOX': _p_wireframe_box, 'TORUS': _p_torus, 'CAPSULE': _p_capsule,
+    'CYLINDER': _p_cylinder, 'CAPPED_CYLINDER': _p_capped_cylinder,
+    'ROUNDED_CYLINDER': _p_rounded_cylinder, 'CAPPED_CONE': _p_capped_cone,
+    'ROUNDED_CONE': _p_rounded_cone, 'ELLIPSOID': _p_ellipsoid, 'PYRAMID': _p_pyramid,
+    'TETRAHEDRON': _p_tetrahedron, 'OCTAHEDRON': _p_octahedron,
+    'DODECAHEDRON': _p_dodecahedron, 'ICOSAHEDRON': _p_icosahedron,
+}
+
+
+def _fold(name, K, d1, d2):
+    if name == 'union':                     # dn.py:13-18
+        if K is None:
+            return _min(d1, d2)
+        h = np.clip(0.5 + 0.5 * (d2 - d1) / K, 0, 1)
+        m = d2 + (d1 - d2) * h
+        return m - K * h * (1 - h)
+    if name == 'difference':                # dn.py:28-33
+        if K is None:
+            return _max(d1, -d2)
+        h = np.clip(0.5 - 0.5 * (d2 + d1) / K, 0, 1)
+        m = d1 + (-d2 - d1) * h
+        return m + K * h * (1 - h)
+    if name == 'intersection':              # dn.py:43-48
+        if K is None:
+            return _max(d1, d2)
+        h = np.clip(0.5 - 0.5 * (d2 - d1) / K, 0, 1)
+        m = d2 + (d1 - d2) * h
+        return m + K * h * (1 - h)
+    raise KeyError(name)
+
+
+def evaluate(obj, p):
+    """sdf(p): (N,3) float64 -> (N,1) float64, like SDF3.__call__ (d3.py:24-25)."""
+    p = np.asarray(p)
+    n = node_of(obj)
+    kind, c = n.kind, n.consts
+    if kind == 'opaque':
+        return obj.f(p).reshape((-1, 1))
+    if kind == 'prim':
+        return _PRIMS[n.op](c, p).reshape((-1, 1))
+    child = n.children[0] if n.children else None
+    if kind == 'transform':
+        if n.op == 'TRANSLATE':             # d3.py:331-332
+            return evaluate(child, p - np.array(c))
+        if n.op == 'ROTATE':                # d3.py:358-359
+            return evaluate(child, np.dot(p, np.array(c).reshape(3, 3)))
+        if n.op in ('TWIST', 'BEND'):       # d3.py:409-418, 423-432
+            x, y, z = p[:, 0], p[:, 1], p[:, 2]
+            arg = c[0] * (z if n.op == 'TWIST' else x)
+            cs, sn = np.cos(arg), np.sin(arg)
+            return evaluate(child, _vec(cs * x - sn * y, sn * x + cs * y, z))
+        raise KeyError(n.op)
+    if kind == 'scale':                     # d3.py:343-344
+        s = (c[0], c[1], c[2])
+        return evaluate(child, p / s) * c[3]
+    if kind == 'elongate':                  # d3.py:398-404
+        q = np.abs(p) - np.array(c)
+        x = q[:, 0].reshape((-1, 1))
+        y = q[:, 1].reshape((-1, 1))
+        z = q[:, 2].reshape((-1, 1))
+        w = _min(_max(x, _max(y, z)), 0)
+        return evaluate(child, _max(q, 0)) + w
+    if kind == 'circular':                  # d3.py:381-391
+        da, offset = c
+        shifted = lambda q: evaluate(child, q - np.array((1, 0, 0)) * offset)
+        x, y, z = p[:, 0], p[:, 1], p[:, 2]
+        d = np.hypot(x, y)
+        a = np.arctan2(y, x) % da
+        d1 = shifted(_vec(np.cos(a - da) * d, np.sin(a - da) * d, z))
+        d2 = shifted(_vec(np.cos(a) * d, np.sin(a) * d, z))
+        return _min(d1, d2)
+    if kind == 'value':
+        d = evaluate(child, p)
+        if n.op == 'NEGATE':                # dn.py:63-64
+            return -d
+        if n.op == 'ADDC':                  # dn.py:68-69, 73-74 (c = -r / +r)
+            return d + c[0]
+        if n.op == 'SHELL':                 # dn.py:78-79
+            return np.abs(d) - c[0] / 2
+        raise KeyError(n.op)
+    if kind == 'fold':
+        d1 = evaluate(n.children[0], p)
+        for b in n.children[1:]:
+            d2 = evaluate(b, p)
+            K = n.extra or getattr(b, '_k', None)
+            d1 = _fold(n.op, K, d1, d2)
+        return d1
+    if kind == 'blend':                     # dn.py:53-59
+        d1 = evaluate(n.children[0], p)
+        for b in n.children[1:]:
+            d2 = evaluate(b, p)
+            K = n.extra or getattr(b, '_k', None)
+            d1 = K * d2 + (1 - K) * d1
+        return d1
+    if kind == 'repeat':                    # dn.py:101-113
+        spacing, count, has_count, neighbours = n.extra
+        dim = p.shape[-1]
+        spacing = np.array(spacing[:dim])
+        q = np.divide(p, spacing, out=np.zeros_like(p), where=spacing != 0)
+        if has_count:
+            cnt = np.array(count[:dim])
+            index = np.clip(np.round(q), -cnt, cnt)
+        else:
+            index = np.round(q)
+        A = [evaluate(child, p - spacing * (index + np.array(nb[:dim]))) for nb in neighbours]
+        a = A[0]
+        for b in A[1:]:
+            a = _min(a, b)
+        return a
+    raise KeyError(kind)
+
+
+# --------------------------------------------------------------------------
+# marching cubes through the C oracle
+
+_lib = None
+
+
+def mc_lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_HERE, 'libmc_oracle.so')
+        src = os.path.join(_HERE, 'mc_lewiner.c')
+        if (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(['make', '-s', '-C', _HERE])
+        _lib = ctypes.CDLL(so)
+        _lib.mc_lewiner_f32.restype = ctypes.c_long
+        _lib.mc_lewiner_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_double, ctypes.c_void_p, ctypes.c_long,
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_long)]
+        _lib.mc_select_tiling.restype = ctypes.c_int
+        _lib.mc_select_tiling.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+class MCValueError(ValueError):
+    pass
+
+
+class MCRuntimeError(RuntimeError):
+    pass
+
+
+def marching_cubes_soup(volume, level=0.0, return_active=False):
+    """Stand-in for core._marching_cubes (core.py:16-18): (3T,3) float32 soup in
+    array-axis (voxel index) coordinates; raises like skimage does."""
+    vol = np.ascontiguousarray(volume, np.float32)
+    if vol.ndim != 3:
+        raise MCValueError('Input volume should be a 3D numpy array.')
+    lib = mc_lib()
+    status = ctypes.c_int(0)
+    active = ctypes.c_long(0)
+    n0, n1, n2 = vol.shape
+    cap = max(1, (n0 - 1) * (n1 - 1) * (n2 - 1)) * 12
+    out = np.empty((min(cap, 1 << 24), 9), np.float32)
+    n = lib.mc_lewiner_f32(vol.ctypes.data, n0, n1, n2, float(level), out.ctypes.data,
+                           out.shape[0], ctypes.byref(status), ctypes.byref(active))
+    if n < 0:
+        out = np.empty((cap, 9), np.float32)
+        n = lib.mc_lewiner_f32(vol.ctypes.data, n0, n1, n2, float(level), out.ctypes.data,
+                               out.shape[0], ctypes.byref(status), ctypes.byref(active))
+    if status.value == 1:
+        raise MCValueError('Surface level must be within volume data range / array at least 2x2x2.')
+    if status.value == 2:
+        raise MCRuntimeError('No surface found at the given iso value.')
+    soup = out[:n].reshape(-1, 3).copy()
+    return (soup, active.value) if return_active else soup
+
+
+# --------------------------------------------------------------------------
+# engine (core.py)
+
+def cartesian_product(*arrays):             # core.py:20-26
+    grids = np.meshgrid(*arrays, indexing='ij')
+    return np.stack([g.reshape(-1) for g in grids], axis=-1)
+
+
+def skip(sdf, job):                         # core.py:28-43
+    X, Y, Z = job
+    x0, x1 = X[0], X[-1]
+    y0, y1 = Y[0], Y[-1]
+    z0, z1 = Z[0], Z[-1]
+    x = (x0 + x1) / 2
+    y = (y0 + y1) / 2
+    z = (z0 + z1) / 2
+    r = abs(evaluate(sdf, np.array([(x, y, z)])).reshape(-1)[0])
+    d = np.linalg.norm(np.array((x - x0, y - y0, z - z0)))
+    if r <= d:
+        return False
+    corners = np.array(list(itertools.product((x0, x1), (y0, y1), (z0, z1))))
+    values = evaluate(sdf, corners).reshape(-1)
+    return bool(np.all(values > 0) if values[0] > 0 else np.all(values < 0))
+
+
+def worker(sdf, job, sparse=True):          # core.py:45-60
+    X, Y, Z = job
+    if sparse and skip(sdf, job):
+        return None
+    P = cartesian_product(X, Y, Z)
+    volume = evaluate(sdf, P).reshape((len(X), len(Y), len(Z)))
+    try:
+        points = marching_cubes_soup(volume)
+    except Exception:
+        return []
+    scale = np.array([X[1] - X[0], Y[1] - Y[0], Z[1] - Z[0]])
+    offset = np.array([X[0], Y[0], Z[0]])
+    return points * scale + offset
+
+
+def estimate_bounds(sdf):                   # core.py:62-82
+    s = 16
+    x0 = y0 = z0 = -1e9
+    x1 = y1 = z1 = 1e9
+    prev = None
+    for _ in range(32):
+        X = np.linspace(x0, x1, s)
+        Y = np.linspace(y0, y1, s)
+        Z = np.linspace(z0, z1, s)
+        d = np.array([X[1] - X[0], Y[1] - Y[0], Z[1] - Z[0]])
+        threshold = np.linalg.norm(d) / 2
+        if threshold == prev:
+            break
+        prev = threshold
+        P = cartesian_product(X, Y, Z)
+        volume = evaluate(sdf, P).reshape((len(X), len(Y), len(Z)))
+        where = np.argwhere(np.abs(volume) <= threshold)
+        x1, y1, z1 = (x0, y0, z0) + where.max(axis=0) * d + d / 2
+        x0, y0, z0 = (x0, y0, z0) + where.min(axis=0) * d - d / 2
+    return ((x0, y0, z0), (x1, y1, z1))
+
+
+def lattice(bounds, step=None, samples=2 ** 22):   # core.py:94-112
+    (x0, y0, z0), (x1, y1, z1) = bounds
+    if step is None and samples is not None:
+        volume = (x1 - x0) * (y1 - y0) * (z1 - z0)
+        step = (volume / samples) ** (1 / 3)
+    try:
+        dx, dy, dz = step
+    except TypeError:
+        dx = dy = dz = step
+    return np.arange(x0, x1, dx), np.arange(y0, y1, dy), np.arange(z0, z1, dz)
+
+
+def batches_of(X, Y, Z, batch_size=32):     # core.py:114-119
+    s = batch_size
+    Xs = [X[i:i + s + 1] for i in range(0, len(X), s)]
+    Ys = [Y[i:i + s + 1] for i in range(0, len(Y), s)]
+    Zs = [Z[i:i + s + 1] for i in range(0, len(Z), s)]
+    return list(itertools.product(Xs, Ys, Zs))
+
+
+def generate(sdf, step=None, bounds=None, samples=2 ** 22, batch_size=32, sparse=True,
+             batch_subset=None):
+    """core.generate (core.py:84-150) without the thread pool / printing.
+
+    Returns (points (3T,3) float64, stats dict).  ``batch_subset`` (iterable of
+    batch indices) restricts the work for bounded-time baselines.
+    """
+    if bounds is None:
+        bounds = estimate_bounds(sdf)
+    X, Y, Z = lattice(bounds, step, samples)
+    batches = batches_of(X, Y, Z, batch_size)
+    if batch_subset is not None:
+        batches = [batches[i] for i in batch_subset]
+    pts = []
+    skipped = empty = nonempty = 0
+    evaluated = 0
+    for job in batches:
+        res = worker(sdf, job, sparse)
+        if res is None:
+            skipped += 1
+            continue
+        evaluated += len(job[0]) * len(job[1]) * len(job[2])
+        if len(res) == 0:
+            empty += 1
+        else:
+            nonempty += 1
+            pts.append(res)
+    points = np.concatenate(pts) if pts else np.zeros((0, 3))
+    stats = dict(skipped=skipped, empty=empty, nonempty=nonempty, batches=len(batches),
+                 samples=sum(len(a) * len(b) * len(c) for a, b, c in batches),
+                 evaluated=evaluated, triangles=len(points) // 3,
+                 dims=(len(X), len(Y), len(Z)))
+    return points, stats

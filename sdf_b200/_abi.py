@@ -1,0 +1,128 @@
+"""ctypes binding of libsdfb200.so (include/sdfb200.h).
+
+This is the whole boundary between the Python host code and the CUDA path; it
+is exactly the stub a maintainer of the reference would add.
+There is no CPU fallback: a missing library or a missing GPU raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsdfb200.so')
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOGPU = 0, -1, -2, -3, -4
+PREC = {'f32': 0, 'mixed': 1, 'f64': 2}
+
+EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
+           'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32',
+           'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags']
+
+
+class SdfB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('libsdfb200 error %d: %s' % (code, message))
+        self.code = code
+
+
+class CapacityError(SdfB200Error):
+    def __init__(self, code, message, needed):
+        super().__init__(code, message)
+        self.needed = needed
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(sdf_b200 has no CPU fallback)' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    L.sdfb200_abi_version.restype = i32
+    L.sdfb200_last_error.restype = ctypes.c_char_p
+    L.sdfb200_device_count.argtypes = [ctypes.POINTER(i32)]
+    L.sdfb200_program_create.argtypes = [vp, i32, vp, i32, ctypes.POINTER(vp)]
+    L.sdfb200_program_free.argtypes = [vp]
+    L.sdfb200_program_free.restype = None
+    L.sdfb200_eval_f32.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.sdfb200_eval_f64.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.sdfb200_generate.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
+                                   vp, i64, ctypes.POINTER(i64), vp, vp, i32, vp]
+    L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        msg = lib().sdfb200_last_error().decode('utf-8', 'replace')
+        raise SdfB200Error(rc, msg)
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    _check(lib().sdfb200_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def _ptr(obj):
+    """Address of a numpy array or a torch tensor (host or device)."""
+    if obj is None:
+        return None
+    if isinstance(obj, np.ndarray):
+        return obj.ctypes.data
+    return obj.data_ptr()
+
+
+class ProgramHandle:
+    """Owns one sdfb200_prog (freed on garbage collection)."""
+
+    def __init__(self, program):
+        self._h = ctypes.c_void_p()
+        self.program = program
+        code = np.ascontiguousarray(program.code, np.uint32)
+        consts = np.ascontiguousarray(program.consts, np.float64)
+        _check(lib().sdfb200_program_create(code.ctypes.data, len(code),
+                                            consts.ctypes.data if len(consts) else None, len(consts),
+                                            ctypes.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _lib is not None:
+            _lib.sdfb200_program_free(h)
+
+    def eval_f32(self, xyz, out, n, device=0, stream=None):
+        _check(lib().sdfb200_eval_f32(self._h, _ptr(xyz), n, _ptr(out), device, stream))
+
+    def eval_f64(self, xyz, out, n, device=0, stream=None):
+        _check(lib().sdfb200_eval_f64(self._h, _ptr(xyz), n, _ptr(out), device, stream))
+
+    def skip_flags(self, X, Y, Z, batch_size, device=0, stream=None):
+        nb = [(len(a) + batch_size - 1) // batch_size for a in (X, Y, Z)]
+        flags = np.zeros(nb[0] * nb[1] * nb[2], np.uint8)
+        _check(lib().sdfb200_skip_flags(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y),
+                                        Z.ctypes.data, len(Z), batch_size, flags.ctypes.data, device, stream))
+        return flags.reshape(nb)
+
+    def generate(self, X, Y, Z, batch_size, sparse, precision, tau, tri_out, capacity,
+                 zb=(0, -1), device=0, stream=None):
+        """Returns (n_tri, stats[6], timings_ms[4]); raises CapacityError with .needed."""
+        n_tri = ctypes.c_int64(0)
+        stats = np.zeros(6, np.int64)
+        timings = np.zeros(4, np.float64)
+        rc = lib().sdfb200_generate(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y),
+                                    Z.ctypes.data, len(Z), int(batch_size), int(bool(sparse)),
+                                    PREC[precision], float(tau), int(zb[0]), int(zb[1]), _ptr(tri_out), int(capacity),
+                                    ctypes.byref(n_tri), stats.ctypes.data, timings.ctypes.data,
+                                    device, stream)
+        if rc == E_CAPACITY:
+            raise CapacityError(rc, lib().sdfb200_last_error().decode(), n_tri.value)
+        _check(rc)
+        return n_tri.value, stats, timings

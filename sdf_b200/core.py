@@ -1,0 +1,277 @@
+"""Mesh-generation engine (host side) -- the drop-in for the reference's sdf/core.py.
+
+``generate`` keeps the reference signature (core.py:84-88) and its verbose
+output (core.py:105-108, 124-126, 145-148).  What used to be a ThreadPool of
+numpy/skimage workers (core.py:131-141) is one call through the C-ABI
+(``sdfb200_generate``): skip pre-pass, fused SDF evaluation, marching cubes and
+world mapping all run on the GPU.  ``workers`` is accepted and ignored.
+
+Lattice construction stays on the host in float64 with ``np.arange`` so the
+sample coordinates are bit-identical to the reference's (core.py:110-112).
+"""
+import multiprocessing
+import os
+import time
+
+import numpy as np
+
+from . import _abi, progress, stl
+from .ir import lower
+
+WORKERS = multiprocessing.cpu_count()
+SAMPLES = 2 ** 22
+BATCH_SIZE = 32
+
+TAU_ULPS = 64.0          # PREC_MIXED guard band, in float32 ulps of the largest magnitude in play
+
+_handles = {}            # (code bytes, consts bytes) -> ProgramHandle
+_capacity_hint = {}      # (program key, lattice dims, batch, sparse) -> triangles needed last time
+
+
+def default_device():
+    for var in ('SDFB200_DEVICE', 'LOCAL_RANK'):
+        v = os.environ.get(var)
+        if v is not None:
+            return int(v)
+    return 0
+
+
+def program_handle(sdf):
+    """Lower ``sdf`` (every call: ``.k()`` may have changed) and return a cached handle."""
+    prog = lower(sdf)
+    key = (prog.code.tobytes(), prog.consts.tobytes())
+    h = _handles.get(key)
+    if h is None:
+        if len(_handles) > 64:
+            _handles.clear()
+        h = _abi.ProgramHandle(prog)
+        _handles[key] = h
+    return h, key
+
+
+def evaluate(sdf, p, device=None):
+    """``sdf(p)``: float64 points in, float64 distances out (d3.py:24-25), on the GPU.
+
+    numpy in -> numpy out (staged through device memory inside the C-ABI call);
+    a CUDA torch tensor in -> a CUDA tensor of the same dtype out (float32 uses
+    the streamed float32 evaluator).
+    """
+    h, _ = program_handle(sdf)
+    if isinstance(p, np.ndarray) or not hasattr(p, 'data_ptr'):
+        pts = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(pts), np.float64)
+        h.eval_f64(pts, out, len(pts), device=default_device() if device is None else device)
+        return out
+    import torch
+    pts = p.contiguous().reshape(-1, 3)
+    dev = pts.device.index if pts.is_cuda else (default_device() if device is None else device)
+    stream = torch.cuda.current_stream(dev).cuda_stream if pts.is_cuda else None
+    out = torch.empty(len(pts), dtype=pts.dtype, device=pts.device)
+    if pts.dtype == torch.float32:
+        h.eval_f32(pts, out, len(pts), device=dev, stream=stream)
+    elif pts.dtype == torch.float64:
+        h.eval_f64(pts, out, len(pts), device=dev, stream=stream)
+    else:
+        raise TypeError('points must be float32 or float64')
+    return out
+
+
+def _cartesian_product(*arrays):
+    grids = np.meshgrid(*arrays, indexing='ij')
+    return np.stack([g.reshape(-1) for g in grids], axis=-1)
+
+
+def _estimate_bounds(sdf):
+    """core.py:62-82: shrink a 16^3 probe lattice from +-1e9 around |d| <= half a cell diagonal."""
+    s = 16
+    lo = np.full(3, -1e9)
+    hi = np.full(3, 1e9)
+    prev = None
+    for _ in range(32):
+        axes = [np.linspace(lo[k], hi[k], s) for k in range(3)]
+        d = np.array([a[1] - a[0] for a in axes])
+        threshold = np.linalg.norm(d) / 2
+        if threshold == prev:
+            break
+        prev = threshold
+        P = _cartesian_product(*axes)
+        volume = sdf(P).reshape((s, s, s))
+        where = np.argwhere(np.abs(volume) <= threshold)
+        x1, y1, z1 = (lo[0], lo[1], lo[2]) + where.max(axis=0) * d + d / 2
+        x0, y0, z0 = (lo[0], lo[1], lo[2]) + where.min(axis=0) * d - d / 2
+        lo = np.array([x0, y0, z0])
+        hi = np.array([x1, y1, z1])
+    return ((lo[0], lo[1], lo[2]), (hi[0], hi[1], hi[2]))
+
+
+def make_lattice(sdf, step=None, bounds=None, samples=SAMPLES):
+    """Bounds, step and the three float64 axes exactly as core.py:94-112 builds them."""
+    if bounds is None:
+        bounds = _estimate_bounds(sdf)
+    (x0, y0, z0), (x1, y1, z1) = bounds
+    if step is None and samples is not None:
+        volume = (x1 - x0) * (y1 - y0) * (z1 - z0)
+        step = (volume / samples) ** (1 / 3)
+    try:
+        dx, dy, dz = step
+    except TypeError:
+        dx = dy = dz = step
+    X = np.arange(x0, x1, dx)
+    Y = np.arange(y0, y1, dy)
+    Z = np.arange(z0, z1, dz)
+    return ((x0, y0, z0), (x1, y1, z1)), (dx, dy, dz), (X, Y, Z)
+
+
+def batch_counts(X, Y, Z, batch_size):
+    """Number of batches per axis and total sample count incl. shared planes (core.py:114-122)."""
+    def lens(n):
+        return [min(batch_size + 1, n - i) for i in range(0, n, batch_size)]
+    lx, ly, lz = lens(len(X)), lens(len(Y)), lens(len(Z))
+    num_samples = sum(lx) * sum(ly) * sum(lz)
+    return (len(lx), len(ly), len(lz)), num_samples
+
+
+def mixed_tau(program, X, Y, Z):
+    """Guard band of PREC_MIXED: TAU_ULPS float32 ulps of the largest coordinate / constant."""
+    mag = 1.0
+    for a in (X, Y, Z):
+        if len(a):
+            mag = max(mag, abs(float(a[0])), abs(float(a[-1])))
+    mag = max(mag, min(program.scale_hint, 1e6))
+    return TAU_ULPS * float(np.finfo(np.float32).eps) * mag
+
+
+def default_capacity(X, Y, Z):
+    nx, ny, nz = len(X), len(Y), len(Z)
+    return int(max(1 << 16, 8 * (nx * ny + ny * nz + nx * nz)))
+
+
+def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='mixed',
+                zb=(0, -1), device=None, out=None, stream=None):
+    """One C-ABI generate call (with the retry on capacity overflow).
+
+    ``out``: None -> a fresh host ndarray is returned; or a caller-owned torch CUDA tensor /
+    numpy array of shape (capacity, 9) float32.  Returns (triangles (T,9) view, info dict).
+    """
+    h, key = program_handle(sdf)
+    X = np.ascontiguousarray(X, np.float64)
+    Y = np.ascontiguousarray(Y, np.float64)
+    Z = np.ascontiguousarray(Z, np.float64)
+    tau = mixed_tau(h.program, X, Y, Z)
+    dev = default_device() if device is None else device
+    hint_key = (key, len(X), len(Y), len(Z), batch_size, bool(sparse), tuple(zb))
+    own = out is None
+    cap = _capacity_hint.get(hint_key, default_capacity(X, Y, Z)) if own else int(out.shape[0])
+    while True:
+        if own:
+            out = np.empty((cap, 9), np.float32)
+        try:
+            n_tri, stats, timings = h.generate(X, Y, Z, batch_size, sparse, precision, tau, out, cap,
+                                               zb=zb, device=dev, stream=stream)
+            break
+        except _abi.CapacityError as e:
+            if not own:
+                raise
+            cap = int(e.needed * 1.05) + 1024
+    _capacity_hint[hint_key] = int(n_tri * 1.05) + 1024
+    info = dict(triangles=n_tri, skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
+                evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]),
+                prepass_ms=float(timings[0]), fused_ms=float(timings[1]), device_ms=float(timings[2]),
+                d2h_ms=float(timings[3]), tau=tau, precision=precision)
+    return out[:n_tri], info
+
+
+def generate(
+        sdf,
+        step=None, bounds=None, samples=SAMPLES,
+        workers=WORKERS, batch_size=BATCH_SIZE,
+        verbose=True, sparse=True, *,
+        precision='mixed', device=None, return_info=False):
+    """Mesh ``sdf`` (core.py:84-150).
+
+    Returns the triangle soup as an ``(3*T, 3)`` float32 ndarray of world-space
+    vertices, three consecutive rows per triangle -- ``len(points)``,
+    ``points[:3]`` and ``write_binary_stl(path, points)`` behave as with the
+    reference's list of float64 rows (README "generate").  Batch order is not
+    preserved (triangles are emitted by whichever SM finishes first).
+    """
+    start = time.time()
+    bounds, (dx, dy, dz), (X, Y, Z) = make_lattice(sdf, step, bounds, samples)
+    (x0, y0, z0), (x1, y1, z1) = bounds
+
+    if verbose:
+        print('min %g, %g, %g' % (x0, y0, z0))
+        print('max %g, %g, %g' % (x1, y1, z1))
+        print('step %g, %g, %g' % (dx, dy, dz))
+
+    (nbx, nby, nbz), num_samples = batch_counts(X, Y, Z, batch_size)
+    num_batches = nbx * nby * nbz
+    if verbose:
+        print('%d samples in %d batches with %d workers' % (num_samples, num_batches, workers))
+
+    bar = progress.Bar(num_batches, enabled=verbose)
+    tris, info = run_batches(sdf, X, Y, Z, batch_size, sparse, precision, device=device)
+    bar.done()
+    points = tris.reshape(-1, 3)
+
+    if verbose:
+        print('%d skipped, %d empty, %d nonempty' % (info['skipped'], info['empty'], info['nonempty']))
+        seconds = time.time() - start
+        print('%d triangles in %g seconds' % (len(points) // 3, seconds))
+
+    if return_info:
+        info.update(batches=num_batches, samples=num_samples, dims=(len(X), len(Y), len(Z)))
+        return points, info
+    return points
+
+
+def save(path, *args, **kwargs):
+    """core.py:152-158."""
+    points = generate(*args, **kwargs)
+    if path.lower().endswith('.stl'):
+        stl.write_binary_stl(path, points)
+    else:
+        mesh = _mesh(points)
+        mesh.write(path)
+
+
+def _mesh(points):
+    """core.py:160-164 (needs the optional ``meshio`` package, as in the reference)."""
+    import meshio
+    points, cells = np.unique(points, axis=0, return_inverse=True)
+    cells = [('triangle', cells.reshape((-1, 3)))]
+    return meshio.Mesh(points, cells)
+
+
+def sample_slice(sdf, w=1024, h=1024, x=None, y=None, z=None, bounds=None):
+    """core.py:202-232: evaluate one axis-aligned w x h slice (on the GPU, float64)."""
+    if bounds is None:
+        bounds = _estimate_bounds(sdf)
+    (x0, y0, z0), (x1, y1, z1) = bounds
+    if x is not None:
+        axes, names = (np.array([x]), np.linspace(y0, y1, w), np.linspace(z0, z1, h)), 'ZY'
+        extent = (axes[2][0], axes[2][-1], axes[1][0], axes[1][-1])
+    elif y is not None:
+        axes, names = (np.linspace(x0, x1, w), np.array([y]), np.linspace(z0, z1, h)), 'ZX'
+        extent = (axes[2][0], axes[2][-1], axes[0][0], axes[0][-1])
+    elif z is not None:
+        axes, names = (np.linspace(x0, x1, w), np.linspace(y0, y1, h), np.array([z])), 'YX'
+        extent = (axes[1][0], axes[1][-1], axes[0][0], axes[0][-1])
+    else:
+        raise Exception('x, y, or z position must be specified')
+    P = _cartesian_product(*axes)
+    return sdf(P).reshape((w, h)), extent, names
+
+
+def show_slice(*args, **kwargs):
+    """core.py:234-244 (needs matplotlib, as in the reference)."""
+    import matplotlib.pyplot as plt
+    show_abs = kwargs.pop('abs', False)
+    a, extent, axes = sample_slice(*args, **kwargs)
+    if show_abs:
+        a = np.abs(a)
+    im = plt.imshow(a, extent=extent, origin='lower')
+    plt.xlabel(axes[0])
+    plt.ylabel(axes[1])
+    plt.colorbar(im)
+    plt.show()
