@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+import models
+from util_cmp import compare_soups, mesh_topology
+
+pytestmark = pytest.mark.gpu
+
+SMALL = [('sphere', 64), ('csg', 96), ('gearlike', 128), ('blobby', 128), ('knurling', 160)]
+
+
+@pytest.fixture(scope='module')
+def sdf():
+    import sdf_b200
+    from sdf_b200 import _abi
+    assert _abi.device_count() >= 1, 'no CUDA device: the product path has no CPU fallback'
+    return sdf_b200
+
+
+@pytest.fixture(scope='module')
+def ref():
+    from oracle import sdf_ref
+    return sdf_ref
+
+
+@pytest.fixture(scope='module')
+def corpus(sdf):
+    return models.build(sdf)
+
+
+def test_eval_f64_matches_reference_goldens(sdf, corpus, golden_dir):
+    """SDF3.__call__ on the GPU (float64) against vectors produced by the REAL reference."""
+    g = np.load(golden_dir + '/node_eval.npz')
+    P = g['points']
+    worst = {}
+    for name, f in corpus.items():
+        d = f(P).reshape(-1)
+        r = g['d_' + name]
+        ok = np.isfinite(r)
+        scale = np.maximum(1.0, np.abs(r[ok]))
+        err = np.max(np.abs(d[ok] - r[ok]) / scale) if ok.any() else 0.0
+        worst[name] = err
+        assert np.array_equal(np.isnan(d), np.isnan(r)), name
+    bad = {k: v for k, v in worst.items() if v > 5e-13}
+    assert not bad, bad
+
+
+def test_eval_f32_stream_matches_oracle(sdf, ref, corpus):
+    """The streamed float32 evaluator (TMA-staged float3 points) against the float64 oracle."""
+    import torch
+    P64 = models.random_points(1 << 16, seed=99)
+    P32 = P64.astype(np.float32)
+    Pd = torch.from_numpy(P32).cuda()
+    for name, f in corpus.items():
+        d = f(Pd).cpu().numpy().reshape(-1)
+        r = ref.evaluate(f, P32.astype(np.float64)).reshape(-1)
+        ok = np.isfinite(r) & np.isfinite(d)
+        assert ok.mean() > 0.99, name
+        # tolerance: 256 float32 ulps of max(1, |p|, |d|); the trees amplify input rounding
+        tol = 256 * np.finfo(np.float32).eps * np.maximum(1.0, np.maximum(np.abs(r[ok]), 3.0))
+        err = np.abs(d[ok] - r[ok])
+        assert np.all(err <= tol), (name, float(err.max()), float(tol.min()))
+
+
+def test_eval_ragged_sizes(sdf, ref):
+    """Empty, tiny and non-multiple-of-tile point blocks; host and device buffers."""
+    import torch
+    f = models.cfg_csg(sdf)
+    for n in (0, 1, 3, 1023, 1024, 1025, 4099):
+        P = models.random_points(max(n, 8), seed=n)[:n]
+        d = f(P)
+        assert d.shape == (n, 1)
+        if n:
+            r = ref.evaluate(f, P)
+            assert np.max(np.abs(d - r)) < 1e-12
+            dd = f(torch.from_numpy(P.astype(np.float32)).cuda()).cpu().numpy()
+            assert np.max(np.abs(dd.reshape(-1) - r.reshape(-1))) < 1e-4
+
+
+@pytest.mark.parametrize('name,n', SMALL)
+@pytest.mark.parametrize('precision', ['f64', 'mixed'])
+def test_generate_matches_oracle(sdf, ref, golden_dir, name, n, precision):
+    """Whole hot path: batch classification == reference goldens, triangles == oracle."""
+    f = models.CONFIGS[name](sdf)
+    _, L = models.CONFIG_GRIDS[name]
+    bounds, step = ((-L, -L, -L), (L, L, L)), 2.0 * L / n
+    pts, info = sdf.generate(f, step=step, bounds=bounds, verbose=False, precision=precision, return_info=True)
+    gold = np.load(golden_dir + '/engine.npz')['cls_%s_%d' % (name, n)]
+    assert (info['skipped'], info['empty'], info['nonempty']) == tuple(gold[:3])
+    assert info['active_cubes'] == gold[3]
+    assert info['dims'] == tuple(gold[4:7])
+    rpts, rstats = ref.generate(f, step=step, bounds=bounds)
+    rep = compare_soups(pts, rpts)
+    assert rep['count_equal'], rep                       # identical triangle count
+    assert rep['max_vertex_dist'] <= 1e-5, rep           # north_star tolerance
+    if precision == 'f64':
+        # same float64 arithmetic up to libm/FMA differences: expect (almost) every triangle bit-equal
+        assert rep['exact_triangles'] >= 0.999 * rep['n_ref'], rep
+    topo = mesh_topology(pts)
+    assert topo['boundary'] == 0 and topo['nonmanifold'] == 0 and topo['repeated_directed'] == 0, topo
+
+
+def test_generate_auto_bounds_matches_reference_goldens(sdf, golden_dir):
+    """samples=N^3 with _estimate_bounds on the GPU evaluator: bounds, step, lattice and batch
+    classification equal the real reference's."""
+    g = np.load(golden_dir + '/engine.npz')
+    from sdf_b200 import core
+    for name in ('sphere', 'csg', 'gearlike', 'blobby', 'knurling'):
+        f = models.CONFIGS[name](sdf)
+        b = core._estimate_bounds(f)
+        assert np.array_equal(np.array(b), g['bounds_' + name]), (name, b, g['bounds_' + name])
+    for name, n in (('sphere', 64), ('csg', 256)):
+        f = models.CONFIGS[name](sdf)
+        pts, info = sdf.generate(f, samples=n ** 3, verbose=False, return_info=True)
+        gold = g['auto_' + name]
+        assert (info['skipped'], info['empty'], info['nonempty'], info['active_cubes']) == tuple(gold[:4]), (name, info)
+        assert info['dims'] == tuple(gold[4:7])
+
+
+def test_skip_flags_match_reference(sdf, golden_dir):
+    g = np.load(golden_dir + '/engine.npz')
+    from sdf_b200 import core
+    for name, n in SMALL:
+        f = models.CONFIGS[name](sdf)
+        _, L = models.CONFIG_GRIDS[name]
+        _, _, (X, Y, Z) = core.make_lattice(f, 2.0 * L / n, ((-L, -L, -L), (L, L, L)))
+        h, _ = core.program_handle(f)
+        flags = h.skip_flags(X, Y, Z, 32).reshape(-1)
+        assert np.array_equal(flags, g['flags_%s_%d' % (name, n)]), name
+
+
+def test_sparse_off_and_batch_size_invariance(sdf, ref):
+    """sparse=False evaluates every batch; the triangle multiset does not depend on batch_size."""
+    f = models.cfg_csg(sdf)
+    bounds, step = ((-1, -1, -1), (1, 1, 1)), 2.0 / 80
+    base, info = sdf.generate(f, step=step, bounds=bounds, verbose=False, sparse=False, precision='f64', return_info=True)
+    assert info['skipped'] == 0
+    for bs in (8, 16, 24, 40, 64, 80):
+        pts, inf = sdf.generate(f, step=step, bounds=bounds, verbose=False, sparse=False, batch_size=bs,
+                                precision='f64', return_info=True)
+        rep = compare_soups(pts, base)
+        # voxel coordinates are batch-local float32, so world positions may differ by an ulp
+        assert rep['count_equal'] and rep['max_vertex_dist'] < 1e-6, (bs, rep)
+    rpts, rstats = ref.generate(f, step=step, bounds=bounds, sparse=False, batch_size=40)
+    pts, inf = sdf.generate(f, step=step, bounds=bounds, verbose=False, sparse=False, batch_size=40,
+                            precision='f64', return_info=True)
+    assert (inf['skipped'], inf['empty'], inf['nonempty']) == (rstats['skipped'], rstats['empty'], rstats['nonempty'])
+    assert compare_soups(pts, rpts)['count_equal']
+
+
+def test_edge_cases(sdf, ref):
+    """Ragged lattices (tail batches of 1..3 planes), single-batch grids, empty results, capacity retry."""
+    f = models.cfg_sphere(sdf)
+    for n in (33, 34, 65, 66, 31):
+        L = 1.25
+        step = 2 * L / n
+        pts, info = sdf.generate(f, step=step, bounds=((-L, -L, -L), (L, L, L)), verbose=False, precision='f64',
+                                 return_info=True)
+        rpts, rstats = ref.generate(f, step=step, bounds=((-L, -L, -L), (L, L, L)))
+        assert (info['skipped'], info['empty'], info['nonempty']) == (rstats['skipped'], rstats['empty'], rstats['nonempty']), n
+        assert compare_soups(pts, rpts)['count_equal'], n
+    # no surface inside the bounds: every batch skipped or empty, zero triangles
+    pts, info = sdf.generate(f, step=0.05, bounds=((2, 2, 2), (3, 3, 3)), verbose=False, return_info=True)
+    assert len(pts) == 0 and info['nonempty'] == 0
+    # capacity overflow is reported, never truncated
+    from sdf_b200 import core, _abi
+    _, _, (X, Y, Z) = core.make_lattice(f, 2.5 / 64, ((-1.25,) * 3, (1.25,) * 3))
+    h, _ = core.program_handle(f)
+    small = np.empty((10, 9), np.float32)
+    with pytest.raises(_abi.CapacityError) as ei:
+        h.generate(X, Y, Z, 32, True, 'f64', 0.0, small, 10)
+    assert ei.value.needed > 10
+    n_tri, stats, _ = h.generate(X, Y, Z, 32, True, 'f64', 0.0, None, 0)      # count only
+    assert n_tri == ei.value.needed
+
+
+def test_opaque_closure_is_callable_but_not_meshable(sdf):
+    @sdf.sdf3
+    def my_sphere(r):
+        def f(p):
+            return np.linalg.norm(p, axis=1) - r
+        return f
+    s = my_sphere(1.0)
+    assert abs(float(s(np.array([[2.0, 0, 0]]))[0, 0]) - 1.0) < 1e-15
+    with pytest.raises(sdf.NotLowerableError):
+        (s | sdf.sphere(0.5)).generate(verbose=False)
