@@ -456,11 +456,12 @@ def batches_of(X, Y, Z, batch_size=32):     # core.py:114-119
 
 
 def generate(sdf, step=None, bounds=None, samples=2 ** 22, batch_size=32, sparse=True,
-             batch_subset=None):
-    """core.generate (core.py:84-150) without the thread pool / printing.
+             batch_subset=None, workers=1):
+    """core.generate (core.py:84-150) without the printing.
 
     Returns (points (3T,3) float64, stats dict).  ``batch_subset`` (iterable of
-    batch indices) restricts the work for bounded-time baselines.
+    batch indices) restricts the work for bounded-time baselines; ``workers`` > 1
+    uses a ThreadPool over batches exactly like the reference (core.py:131-133).
     """
     if bounds is None:
         bounds = estimate_bounds(sdf)
@@ -471,8 +472,13 @@ def generate(sdf, step=None, bounds=None, samples=2 ** 22, batch_size=32, sparse
     pts = []
     skipped = empty = nonempty = 0
     evaluated = 0
-    for job in batches:
-        res = worker(sdf, job, sparse)
+    if workers > 1:
+        from multiprocessing.pool import ThreadPool
+        with ThreadPool(workers) as pool:
+            results = list(pool.imap(lambda job: worker(sdf, job, sparse), batches))
+    else:
+        results = (worker(sdf, job, sparse) for job in batches)
+    for job, res in zip(batches, results):
         if res is None:
             skipped += 1
             continue

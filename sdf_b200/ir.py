@@ -167,7 +167,9 @@ class _Lowerer:
         assert len(consts) == NCONST[name], (name, len(consts))
         ci = len(self.consts)
         self.consts.extend(float(c) for c in consts)
-        assert 0 <= a < 256
+        if not (0 <= a < 256 and ci < 65536):
+            raise NotLowerableError('tree too deep / too many constants for the instruction encoding '
+                                    '(operand %d, constant index %d)' % (a, ci))
         self.code.append(OPCODE[name] | (a << 8) | (ci << 16))
 
     def push(self):

@@ -1,0 +1,227 @@
+"""CPU suite, part 3: host logic (IR lowering, lattice, batching, slab partition, STL sink) and the
+C-ABI library surface.  No compute call is made here (there is no GPU in this container)."""
+import ctypes
+import io
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import models
+import sdf_b200
+from sdf_b200 import _abi, core, ir, multi, stl
+from oracle import sdf_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ IR / lowering
+
+def test_every_corpus_model_lowers():
+    for name, f in models.build(sdf_b200).items():
+        prog = ir.lower(f)
+        assert 1 <= len(prog.code) <= ir.MAX_CODE, name
+        assert prog.vdepth <= ir.MAX_VSTACK and prog.pslots <= ir.MAX_PSLOTS
+        for w in prog.code:
+            op, ci = int(w) & 0xff, int(w) >> 16
+            assert op in ir.OPNAME
+            assert ci + ir.NCONST[ir.OPNAME[op]] <= len(prog.consts)
+        assert prog.disassemble()
+
+
+def test_config_programs_are_small():
+    sizes = {k: len(ir.lower(f(sdf_b200)).code) for k, f in models.CONFIGS.items()}
+    assert sizes['sphere'] == 1 and sizes['knurling'] < 64, sizes
+
+
+def test_k_selection_rule():
+    """dn.py:12: K = k or getattr(b, '_k', None) -- op-level k wins, else the RIGHT operand's .k();
+    the left operand's _k is never read; k=0 is falsy; .k() set after the fold is still honoured."""
+    s, b = sdf_b200.sphere(1), sdf_b200.box(1)
+
+    def ops(f):
+        return [ir.OPNAME[int(w) & 0xff] for w in ir.lower(f).code]
+    assert 'UNION' in ops(s | b) and 'UNION_K' not in ops(s | b)
+    assert 'UNION_K' in ops(s | sdf_b200.box(1).k(0.2))
+    assert 'UNION_K' not in ops(sdf_b200.sphere(1).k(0.2) | b)            # left operand's k ignored
+    assert 'DIFFERENCE_K' in ops(sdf_b200.difference(s, b, k=0.3))
+    assert 'UNION' in ops(sdf_b200.union(s, b, k=0))                      # k=0 is falsy
+    late = sdf_b200.box(1)
+    f = s & late
+    late.k(0.25)
+    prog = ir.lower(f)
+    assert 'INTERSECTION_K' in ops(f) and 0.25 in prog.consts
+
+
+def test_point_save_restore_only_when_needed():
+    names = lambda f: [ir.OPNAME[int(w) & 0xff] for w in ir.lower(f).code]
+    assert 'SAVEP' not in names(sdf_b200.sphere(1) | sdf_b200.box(1))                # no child moves P
+    n = names(sdf_b200.sphere(1).translate((1, 0, 0)) | sdf_b200.box(1))
+    assert n.count('SAVEP') == 1 and n.count('LOADP') == 1
+    n = names(sdf_b200.sphere(1) | sdf_b200.box(1).translate((1, 0, 0)))             # only the LAST child moves P
+    assert 'SAVEP' not in n
+
+
+def test_method_chaining_and_registry():
+    f = sdf_b200.sphere(1).translate((1, 2, 3)).rotate(0.5).scale(2).shell(0.1)
+    assert isinstance(f, sdf_b200.d3.SDF3)
+    assert set(['translate', 'rotate', 'orient', 'union', 'shell', 'circular_array', 'twist']) <= set(sdf_b200.d3._ops)
+    with pytest.raises(AttributeError):
+        sdf_b200.sphere(1).no_such_op
+    assert getattr(sdf_b200.sphere(1), '_k', None) is None
+
+
+def test_reference_quirks_are_kept():
+    a = sdf_b200.sphere(1)
+    assert sdf_b200.rotate_to(a, (0, 0, 1), (0, 0, 2)) is a               # dot == 1 -> identity (d3.py:366-367)
+    assert sdf_b200.slab(z0=0)._node.kind == 'fold'                        # slab returns the inner intersection
+    b = sdf_b200.box(a=(0, 0, 0), b=(1, 2, 3))
+    assert b._node.consts == [0.5, 1.0, 1.5, 0.5, 1.0, 1.5]
+
+
+def test_opaque_closure_cannot_be_lowered():
+    @sdf_b200.sdf3
+    def blob(r):
+        def f(p):
+            return np.linalg.norm(p, axis=1) - r
+        return f
+    s = blob(2.0)
+    assert float(s(np.array([[3.0, 0, 0]]))[0, 0]) == 1.0                  # still callable in numpy
+    with pytest.raises(ir.NotLowerableError):
+        ir.lower(s | sdf_b200.sphere(1))
+
+
+def test_program_size_limit():
+    f = sdf_b200.sphere(0.1)
+    for i in range(300):
+        f = f | sdf_b200.sphere(0.1).translate((i, 0, 0))
+    with pytest.raises(ir.NotLowerableError):
+        ir.lower(f)
+
+
+# ------------------------------------------------------------------ lattice / batching
+
+def test_lattice_matches_reference_construction():
+    f = sdf_b200.sphere(1)
+    b, step, (X, Y, Z) = core.make_lattice(f, bounds=((-1.25,) * 3, (1.25,) * 3), step=2.5 / 64)
+    assert len(X) == len(Y) == len(Z) == 64 and X[0] == -1.25
+    Xr, Yr, Zr = sdf_ref.lattice(((-1.25,) * 3, (1.25,) * 3), step=2.5 / 64)
+    assert np.array_equal(X, Xr)
+    # samples -> isotropic step (core.py:96-98)
+    _, (dx, dy, dz), _ = core.make_lattice(f, bounds=((0, 0, 0), (1, 2, 4)), samples=8 ** 3)
+    assert dx == dy == dz == (8.0 / 512) ** (1 / 3)
+
+
+@pytest.mark.parametrize('n,bs', [(64, 32), (65, 32), (33, 32), (100, 32), (96, 40), (5, 8)])
+def test_batch_counts_match_reference_slicing(n, bs):
+    X = np.arange(n, dtype=np.float64)
+    (nbx, nby, nbz), samples = core.batch_counts(X, X, X, bs)
+    ref = sdf_ref.batches_of(X, X, X, bs)
+    assert nbx * nby * nbz == len(ref)
+    assert samples == sum(len(a) * len(b) * len(c) for a, b, c in ref)
+
+
+def test_partition_layers_properties():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n, world = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+        a = rng.integers(0, 50, n) * (rng.random(n) < 0.6)
+        parts = multi.partition_layers(a, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        assert all(b <= e for b, e in parts)
+    parts = multi.partition_layers([10] * 16, 8)
+    assert parts == [(2 * i, 2 * i + 2) for i in range(8)]
+    sums = [sum([0, 0, 5, 10, 10, 5, 0, 0][b:e]) for b, e in multi.partition_layers([0, 0, 5, 10, 10, 5, 0, 0], 2)]
+    assert sums == [15, 15]
+
+
+def test_tau_scales_with_magnitude():
+    p = ir.lower(sdf_b200.sphere(1))
+    X = np.linspace(-1, 1, 8)
+    t1 = core.mixed_tau(p, X, X, X)
+    t2 = core.mixed_tau(p, X * 100, X, X)
+    assert 0 < t1 < 1e-4 and abs(t2 / t1 - 100) < 1e-9
+
+
+# ------------------------------------------------------------------ sinks
+
+def test_binary_stl_layout(tmp_path):
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1]], np.float64)
+    path = tmp_path / 'a.stl'
+    stl.write_binary_stl(str(path), pts)
+    raw = path.read_bytes()
+    assert len(raw) == 80 + 4 + 2 * 50 and raw[:80] == b'\x00' * 80
+    assert struct.unpack('<I', raw[80:84])[0] == 2
+    rec = struct.unpack('<12fH', raw[84:134])
+    assert rec[:3] == (0.0, 0.0, 1.0) and rec[3:12] == (0, 0, 0, 1, 0, 0, 0, 1, 0) and rec[12] == 0
+
+
+def test_generate_verbose_lines(monkeypatch, capsys):
+    """The verbose output keeps the reference's format strings (core.py:105-108,125-126,145-148)."""
+    fake_info = dict(triangles=2, skipped=3, empty=4, nonempty=1)
+
+    def fake_run(sdf, X, Y, Z, batch_size, sparse, precision, **kw):
+        return np.zeros((2, 9), np.float32), dict(fake_info)
+    monkeypatch.setattr(core, 'run_batches', fake_run)
+    pts = core.generate(sdf_b200.sphere(1), step=0.5, bounds=((-1, -1, -1), (1, 1, 1)), workers=7)
+    out = capsys.readouterr().out
+    assert 'min -1, -1, -1' in out and 'max 1, 1, 1' in out and 'step 0.5, 0.5, 0.5' in out
+    assert '64 samples in 1 batches with 7 workers' in out
+    assert '3 skipped, 4 empty, 1 nonempty' in out and re.search(r'2 triangles in [0-9.e+-]+ seconds', out)
+    assert pts.shape == (6, 3)
+
+
+def test_drop_in_package_names():
+    import sdf
+    for name in ['sphere', 'box', 'cylinder', 'torus', 'union', 'intersection', 'difference', 'translate', 'rotate',
+                 'scale', 'orient', 'shell', 'generate', 'save', 'sample_slice', 'show_slice', 'write_binary_stl',
+                 'pi', 'degrees', 'radians', 'X', 'Y', 'Z', 'ORIGIN', 'UP', 'sdf3', 'op3', 'op32', 'sdf2', 'op2',
+                 'op23', 'SDF3', 'SDF2', 'np']:
+        assert hasattr(sdf, name), name
+    assert sdf.X.shape == (3,)                    # 3-D constants win over the 2-D ones (__init__.py:5-7)
+
+
+# ------------------------------------------------------------------ C-ABI surface
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'sdfb200.h')).read()
+    declared = set(re.findall(r'\b(sdfb200_[a-z0-9_]+)\s*\(', header)) - {'sdfb200_prog'}
+    assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.sdfb200_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    """On a box without a CUDA device the product path must raise (never route through the oracle)."""
+    if _abi.device_count() > 0:
+        pytest.skip('a GPU is present')
+    with pytest.raises(_abi.SdfB200Error) as ei:
+        sdf_b200.sphere(1).generate(step=0.5, bounds=((-1, -1, -1), (1, 1, 1)), verbose=False)
+    assert ei.value.code == _abi.E_NOGPU and 'no CPU fallback' in str(ei.value)
+    with pytest.raises(_abi.SdfB200Error):
+        sdf_b200.sphere(1)(np.zeros((1, 3)))
+
+
+def test_program_create_validates():
+    lib = _abi.lib()
+    h = ctypes.c_void_p()
+    bad = np.array([250], np.uint32)                    # unknown opcode
+    assert lib.sdfb200_program_create(bad.ctypes.data, 1, None, 0, ctypes.byref(h)) == _abi.E_INVALID
+    assert b'unknown opcode' in lib.sdfb200_last_error()
+    code = np.array([ir.OPCODE['SPHERE'] | (0 << 16)], np.uint32)
+    assert lib.sdfb200_program_create(code.ctypes.data, 1, np.zeros(2).ctypes.data, 2, ctypes.byref(h)) == _abi.E_INVALID
+    assert lib.sdfb200_program_create(code.ctypes.data, 1, np.zeros(4).ctypes.data, 4, ctypes.byref(h)) == 0
+    lib.sdfb200_program_free(h)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'sdf_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle|oracle/|oracle\.|libmc_oracle|sdf_ref', src, re.M), fn

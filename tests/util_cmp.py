@@ -64,7 +64,14 @@ def mesh_topology(points, decimals=None):
     und = np.sort(e, axis=1)
     ue, counts = np.unique(und, axis=0, return_counts=True)
     # directed consistency: every undirected edge once in each direction
-    dire = e[:, 0].astype(np.int64) * (len(uniq) + 1) + e[:, 1]
-    _, dcounts = np.unique(dire, return_counts=True)
+    base = len(uniq) + 1
+    dire = e[:, 0].astype(np.int64) * base + e[:, 1]
+    rev = e[:, 1].astype(np.int64) * base + e[:, 0]
+    dk, dcounts = np.unique(dire, return_counts=True)
+    rk, rcounts = np.unique(rev, return_counts=True)
+    # orientation: every directed edge is matched by as many opposite ones
+    fwd = dict(zip(dk.tolist(), dcounts.tolist()))
+    unbalanced = sum(1 for k, c in zip(rk.tolist(), rcounts.tolist()) if fwd.get(k, 0) != c)
     return dict(V=len(uniq), E=len(ue), F=len(f), boundary=int((counts == 1).sum()),
-                nonmanifold=int((counts > 2).sum()), repeated_directed=int((dcounts > 1).sum()))
+                nonmanifold=int((counts > 2).sum()), repeated_directed=int((dcounts > 1).sum()),
+                unbalanced=int(unbalanced))

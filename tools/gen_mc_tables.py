@@ -156,8 +156,17 @@ def tri_list(flat):
     return [tuple(flat[i:i + 3]) for i in range(0, len(flat), 3)]
 
 
-def check_tiling(index, J, tris, n_components=None):
-    """True iff tris is an oriented manifold patch set bounded by segments()."""
+def count_in_face_chords(tris):
+    return sum(1 for t in tris for a, b in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])) if a < b and in_face(a, b)
+               and (b, a) in {(u, v) for tt in tris for u, v in ((tt[0], tt[1]), (tt[1], tt[2]), (tt[2], tt[0]))})
+
+
+def check_tiling(index, J, tris, n_components=None, strict_chords=False):
+    """True iff tris is an oriented manifold patch set bounded by segments().
+
+    strict_chords additionally rejects interior chords that lie inside a cube face (the
+    generator avoids them wherever a triangulation without them exists; the tunnels of 7.4.2 /
+    13.5.2 cannot avoid them without an extra vertex)."""
     directed = {}
     for t in tris:
         if len(set(t)) != 3:
@@ -169,6 +178,10 @@ def check_tiling(index, J, tris, n_components=None):
     boundary = {e for e in directed if (e[1], e[0]) not in directed}
     if boundary != set(segments(index, J)):
         return False
+    if strict_chords:
+        for (a, b) in directed:
+            if (a, b) not in boundary and in_face(a, b):
+                return False
     if n_components is not None:
         parent = list(range(len(tris)))
 
@@ -195,6 +208,22 @@ def d2(a, b):
     return sum((x - y) ** 2 for x, y in zip(pa, pb))
 
 
+def faces_of_edge(e):
+    a, b = EDGES[e]
+    return {f for f, cs in FACES.items() if a in cs and b in cs}
+
+
+def in_face(a, b):
+    """True when the chord between edge-vertices a and b lies inside a cube face.  Such a chord
+    would make the patch touch the face (and the neighbouring cube's patch) along a line."""
+    if a == 12 or b == 12:
+        return False
+    return bool(faces_of_edge(a) & faces_of_edge(b))
+
+
+FORBID = 1e6   # cost of a chord lying in a cube face
+
+
 def disc(loop):
     """Minimum sum-of-squared-diagonals triangulation of a directed loop."""
     n = len(loop)
@@ -211,9 +240,9 @@ def disc(loop):
             c2, t2 = best(k, j)
             cost = c1 + c2
             if k - i > 1:
-                cost += d2(loop[i], loop[k])
+                cost += d2(loop[i], loop[k]) + (FORBID if in_face(loop[i], loop[k]) else 0)
             if j - k > 1:
-                cost += d2(loop[k], loop[j])
+                cost += d2(loop[k], loop[j]) + (FORBID if in_face(loop[k], loop[j]) else 0)
             cands.append((round(cost, 9), t1 + ((loop[i], loop[k], loop[j]),) + t2))
         return min(cands)
     return list(best(0, n - 1)[1])
@@ -239,7 +268,7 @@ def tube(A, B):
             steps = set(steps)
             i = j = 0
             used = {(0, 0)}
-            cost = d2(A[0], B[j0])
+            cost = d2(A[0], B[j0]) + (FORBID if in_face(A[0], B[j0]) else 0)
             tris, ok = [], True
             for s in range(n + m):
                 ai, bj = A[i % n], B[(j0 - j) % m]
@@ -257,7 +286,7 @@ def tube(A, B):
                         ok = False
                         break
                     used.add(key)
-                    cost += d2(A[i % n], B[(j0 - j) % m])
+                    cost += d2(A[i % n], B[(j0 - j) % m]) + (FORBID if in_face(A[i % n], B[(j0 - j) % m]) else 0)
             if not ok:
                 continue
             cand = (round(cost, 9), tuple(tris))
