@@ -295,7 +295,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default='gearlike')
     ap.add_argument('--grid', type=int, default=None)
-    ap.add_argument('--precision', default='mixed', choices=['f32', 'mixed', 'f64'])
+    ap.add_argument('--precision', default='mixed', choices=['f32', 'mixed', 'f64', 'exact'])
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-batches', type=int, default=4096)

@@ -17,6 +17,7 @@
 #ifndef SDFB200_H
 #define SDFB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -35,12 +36,23 @@ extern "C" {
 #define SDFB200_PREC_F32 0    /* float32 evaluation only                                      */
 #define SDFB200_PREC_MIXED 1  /* float32, then float64 re-evaluation of samples with |d| < tau */
 #define SDFB200_PREC_F64 2    /* float64 evaluation of every sample (reference arithmetic)    */
+#define SDFB200_PREC_EXACT 3  /* fast float32 classification; float64 for samples with |d| < tau and
+                                 for every corner of a surface-crossing cube: output == PREC_F64    */
 
 typedef struct sdfb200_prog sdfb200_prog;
 
 int sdfb200_abi_version(void);
 const char* sdfb200_last_error(void);
 int sdfb200_device_count(int* count);
+
+/*
+ * Page-locked, device-mapped host memory for output buffers (cudaHostAlloc).  Replaces nothing in
+ * the reference (numpy owns its buffers, core.py:128); a tri_out allocated here is either written
+ * directly by the kernel over PCIe (default) or filled by one asynchronous copy
+ * (SDFB200_ZEROCOPY=0), instead of the slow pageable path.
+ */
+int sdfb200_host_alloc(size_t bytes, void** out);
+void sdfb200_host_free(void* p);
 
 /*
  * Replaces: construction of the closure tree by the @sdf3/@op3 factories
@@ -59,6 +71,9 @@ void sdfb200_program_free(sdfb200_prog* prog);
  * bulk async copies.  f64: the reference's float64 arithmetic.
  */
 int sdfb200_eval_f32(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream);
+/* same as sdfb200_eval_f32 with the approximate-math float32 evaluator (MUFU division / sqrt /
+ * sin / cos, polynomial atan2): the classification pass of SDFB200_PREC_EXACT, exposed for benchmarking */
+int sdfb200_eval_f32_fast(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream);
 int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n, double* d_out, int device, void* stream);
 
 /*
@@ -84,6 +99,15 @@ int sdfb200_generate(sdfb200_prog* prog,
                      int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
                      float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
                      double timings_ms[4], int device, void* stream);
+
+/*
+ * Run-time specialisation check (needs no GPU): generate the straight-line evaluator of `prog` for
+ * kernel id 0 (skip pre-pass), 1..4 (fused tile kernel, precision 0..3), 5/6 (streamed float32
+ * evaluator accurate/fast), 7 (streamed float64) and compile it with NVRTC for sm_100a.  The other
+ * entry points do this lazily and fall back to the interpreter kernels when NVRTC is missing or
+ * SDFB200_JIT=0.  Replaces nothing in the reference.
+ */
+int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes);
 
 /*
  * Replaces: nothing in the reference (diagnostic / load balancing): the skip

@@ -13,11 +13,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libsdfb200.so')
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_NOGPU = 0, -1, -2, -3, -4
-PREC = {'f32': 0, 'mixed': 1, 'f64': 2}
+PREC = {'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}
 
 EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
-           'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32',
-           'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags']
+           'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32', 'sdfb200_eval_f32_fast',
+           'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
+           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe']
 
 
 class SdfB200Error(RuntimeError):
@@ -53,8 +54,13 @@ def lib():
     L.sdfb200_program_free.restype = None
     L.sdfb200_eval_f32.argtypes = [vp, vp, i64, vp, i32, vp]
     L.sdfb200_eval_f64.argtypes = [vp, vp, i64, vp, i32, vp]
+    L.sdfb200_eval_f32_fast.argtypes = [vp, vp, i64, vp, i32, vp]
     L.sdfb200_generate.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
                                    vp, i64, ctypes.POINTER(i64), vp, vp, i32, vp]
+    L.sdfb200_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.sdfb200_host_free.argtypes = [vp]
+    L.sdfb200_host_free.restype = None
+    L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
     _lib = L
     return L
@@ -81,6 +87,47 @@ def _ptr(obj):
     return obj.data_ptr()
 
 
+class PinnedPool:
+    """Page-locked output buffers, recycled when the arrays handed to the user are garbage collected.
+
+    ``take(n_floats)`` returns a float32 ndarray over pinned memory; every view of it keeps the
+    block alive, and the block goes back to the pool (it is not freed) once the last view dies --
+    so results stay valid for as long as the caller holds them, and a loop that drops its previous
+    result re-uses the same pinned block without any allocation or extra copy.
+    """
+
+    def __init__(self, max_free=4):
+        self.free = []          # (nbytes, address)
+        self.max_free = max_free
+
+    def take(self, n_floats):
+        import weakref
+        nbytes = max(int(n_floats) * 4, 4096)
+        best = None
+        for i, (sz, addr) in enumerate(self.free):
+            if sz >= nbytes and (best is None or sz < self.free[best][0]):
+                best = i
+        if best is not None:
+            sz, addr = self.free.pop(best)
+        else:
+            sz = 1 << max(12, (nbytes - 1).bit_length())          # round up: fewer distinct sizes
+            p = ctypes.c_void_p()
+            _check(lib().sdfb200_host_alloc(sz, ctypes.byref(p)))
+            addr = p.value
+        base = np.ctypeslib.as_array((ctypes.c_float * (sz // 4)).from_address(addr))
+        weakref.finalize(base, self._release, sz, addr)
+        return base
+
+    def _release(self, sz, addr):
+        if len(self.free) < self.max_free:
+            self.free.append((sz, addr))
+        elif _lib is not None:
+            _lib.sdfb200_host_free(addr)
+
+
+pinned_pool = PinnedPool()
+
+
 class ProgramHandle:
     """Owns one sdfb200_prog (freed on garbage collection)."""
 
@@ -100,6 +147,15 @@ class ProgramHandle:
 
     def eval_f32(self, xyz, out, n, device=0, stream=None):
         _check(lib().sdfb200_eval_f32(self._h, _ptr(xyz), n, _ptr(out), device, stream))
+
+    def jit_probe(self, kernel):
+        """NVRTC-compile the specialised kernel `kernel` (no GPU needed); returns the cubin size."""
+        n = ctypes.c_int64(0)
+        _check(lib().sdfb200_jit_probe(self._h, kernel, ctypes.byref(n)))
+        return n.value
+
+    def eval_f32_fast(self, xyz, out, n, device=0, stream=None):
+        _check(lib().sdfb200_eval_f32_fast(self._h, _ptr(xyz), n, _ptr(out), device, stream))
 
     def eval_f64(self, xyz, out, n, device=0, stream=None):
         _check(lib().sdfb200_eval_f64(self._h, _ptr(xyz), n, _ptr(out), device, stream))

@@ -22,7 +22,8 @@ WORKERS = multiprocessing.cpu_count()
 SAMPLES = 2 ** 22
 BATCH_SIZE = 32
 
-TAU_ULPS = 64.0          # PREC_MIXED guard band, in float32 ulps of the largest magnitude in play
+TAU_ULPS = 64.0          # guard band of the float32 pass, in float32 ulps of the largest magnitude in play
+TAU_ULPS_PER_WORD = 4.0  # ... plus this many per program word (rounding accumulates along the tree)
 
 _handles = {}            # (code bytes, consts bytes) -> ProgramHandle
 _capacity_hint = {}      # (program key, lattice dims, batch, sparse) -> triangles needed last time
@@ -138,7 +139,8 @@ def mixed_tau(program, X, Y, Z):
         if len(a):
             mag = max(mag, abs(float(a[0])), abs(float(a[-1])))
     mag = max(mag, min(program.scale_hint, 1e6))
-    return TAU_ULPS * float(np.finfo(np.float32).eps) * mag
+    ulps = TAU_ULPS + TAU_ULPS_PER_WORD * len(program.code)
+    return ulps * float(np.finfo(np.float32).eps) * mag
 
 
 def default_capacity(X, Y, Z):
@@ -164,7 +166,8 @@ def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='mix
     cap = _capacity_hint.get(hint_key, default_capacity(X, Y, Z)) if own else int(out.shape[0])
     while True:
         if own:
-            out = np.empty((cap, 9), np.float32)
+            # page-locked and device-mapped: the kernel writes the triangles straight into it
+            out = _abi.pinned_pool.take(cap * 9)[:cap * 9].reshape(cap, 9)
         try:
             n_tri, stats, timings = h.generate(X, Y, Z, batch_size, sparse, precision, tau, out, cap,
                                                zb=zb, device=dev, stream=stream)

@@ -23,17 +23,18 @@
 #include <string.h>
 #include <float.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <algorithm>
+#include <dlfcn.h>
+#include <math.h>
 #include <new>
 #include <mutex>
+#include <sstream>
 #include <string>
 #include <vector>
 
 #include "../../include/sdfb200.h"
-#include "sdf_interp.cuh"
-
-#define MC_TABLE_QUAL __device__ const
-#include "mc_tables.inc"
+#include "sdf_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------
 // error plumbing
@@ -59,670 +60,36 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ---------------------------------------------------------------------------------------
-// device-side job description
-
-struct GridDesc {
-    const double* xs;
-    const double* ys;
-    const double* zs;
-    int nx, ny, nz;        // lattice points per axis
-    int bs;                // cubes per batch side (core.py BATCH_SIZE)
-    int nbx, nby, nbz;     // batches per axis = ceil(n / bs)   (core.py:115-117)
-    int zb0, zb1;          // Z batch layers handled by this call
-    int sub;               // sub-tiles per batch side = ceil(bs / TS)
-};
-
-struct Counters {
-    unsigned long long tri_cursor;      // triangles allocated so far
-    unsigned long long pts_f32;         // samples evaluated in float32 (or f64 in PREC_F64)
-    unsigned long long pts_f64;         // samples re-evaluated in float64
-    unsigned long long active_cubes;
-    unsigned int n_active;              // non-skipped batches
-    unsigned int work_cursor;
-    unsigned int skipped, empty, nonempty;
-    unsigned int pad_;
-};
-
-// ---------------------------------------------------------------------------------------
-// float64 helpers that the compiler may not contract into FMAs: the marching-cubes
-// arithmetic must round exactly like the C restatement (and skimage's C code).
-
-__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
-
-// Lewiner corner k = (x,y,z): 0(0,0,0) 1(1,0,0) 2(1,1,0) 3(0,1,0) 4..7 same at z=1; edges 0-3 bottom ring,
-// 4-7 top ring, 8-11 verticals.  Computed arithmetically: per-thread edge ids diverge, and divergent
-// __constant__ reads serialise.
-__device__ __forceinline__ int corner_x(int k) { return (k ^ (k >> 1)) & 1; }
-__device__ __forceinline__ int corner_y(int k) { return (k >> 1) & 1; }
-__device__ __forceinline__ int corner_z(int k) { return (k >> 2) & 1; }
-__device__ __forceinline__ int edge_corner(int e, int s) {
-    if (e < 8) return (e & 4) | ((e + s) & 3);
-    return e - 8 + 4 * s;
-}
-__constant__ int c_face_corners[7][4] = {{0, 0, 0, 0}, {0, 4, 5, 1}, {1, 5, 6, 2}, {2, 6, 7, 3}, {3, 7, 4, 0}, {0, 3, 2, 1}, {4, 7, 6, 5}};
-__constant__ int c_interior_edge[12][8] = {
-    {0, 1, 3, 2, 7, 6, 4, 5}, {1, 2, 0, 3, 4, 7, 5, 6}, {2, 3, 1, 0, 5, 4, 6, 7}, {3, 0, 2, 1, 6, 5, 7, 4},
-    {4, 5, 7, 6, 3, 2, 0, 1}, {5, 6, 4, 7, 0, 3, 1, 2}, {6, 7, 5, 4, 1, 0, 2, 3}, {7, 4, 6, 5, 2, 1, 3, 0},
-    {0, 4, 3, 7, 2, 6, 1, 5}, {1, 5, 0, 4, 3, 7, 2, 6}, {2, 6, 1, 5, 0, 4, 3, 7}, {3, 7, 2, 6, 1, 5, 0, 4}};
-
-// skimage test_face (asymptotic decider with the FLT_EPSILON dead band)
-__device__ __forceinline__ bool mc_test_face(const double* v, int face) {
-    const int af = face < 0 ? -face : face;
-    const double A = v[c_face_corners[af][0]], B = v[c_face_corners[af][1]];
-    const double C = v[c_face_corners[af][2]], D = v[c_face_corners[af][3]];
-    const double acbd = xsub(xmul(A, C), xmul(B, D));
-    if (acbd > -(double)FLT_EPSILON && acbd < (double)FLT_EPSILON) return face >= 0;
-    return xmul(xmul((double)face, A), acbd) >= 0;
-}
-
-// skimage test_internal; mode 12 = cases 4/10, 0..11 = reference edge
-__device__ __forceinline__ bool mc_test_interior(const double* v, int mode, int s) {
-    double t, At = 0, Bt = 0, Ct = 0, Dt = 0;
-    const double eps = (double)FLT_EPSILON;
-    if (mode == 12) {
-        const double a = xsub(xmul(xsub(v[4], v[0]), xsub(v[6], v[2])), xmul(xsub(v[7], v[3]), xsub(v[5], v[1])));
-        const double b = xsub(xsub(xadd(xmul(v[2], xsub(v[4], v[0])), xmul(v[0], xsub(v[6], v[2]))),
-                                   xmul(v[1], xsub(v[7], v[3]))),
-                              xmul(v[3], xsub(v[5], v[1])));
-        t = xdiv(-b, xadd(xmul(2.0, a), eps));
-        if (t < 0 || t > 1) return s > 0;
-        At = xadd(v[0], xmul(xsub(v[4], v[0]), t));
-        Bt = xadd(v[3], xmul(xsub(v[7], v[3]), t));
-        Ct = xadd(v[2], xmul(xsub(v[6], v[2]), t));
-        Dt = xadd(v[1], xmul(xsub(v[5], v[1]), t));
-    } else {
-        const int* e = c_interior_edge[mode];
-        t = xdiv(v[e[0]], xadd(xsub(v[e[0]], v[e[1]]), eps));
-        At = 0;
-        Bt = xadd(v[e[2]], xmul(xsub(v[e[3]], v[e[2]]), t));
-        Ct = xadd(v[e[4]], xmul(xsub(v[e[5]], v[e[4]]), t));
-        Dt = xadd(v[e[6]], xmul(xsub(v[e[7]], v[e[6]]), t));
-    }
-    int test = 0;
-    if (At >= 0) test += 1;
-    if (Bt >= 0) test += 2;
-    if (Ct >= 0) test += 4;
-    if (Dt >= 0) test += 8;
-    switch (test) {
-        case 0: case 1: case 2: case 3: case 4: case 6: case 8: case 9: case 12:
-            return s > 0;
-        case 5:
-            if (xsub(xmul(At, Ct), xmul(Bt, Dt)) < eps) return s > 0;
-            break;
-        case 10:
-            if (xsub(xmul(At, Ct), xmul(Bt, Dt)) >= eps) return s > 0;
-            break;
-        default:
-            return s < 0;
-    }
-    return s < 0;
-}
-
-// ---------------------------------------------------------------------------------------
-// shared-memory copies of the decision tables ("edge table in shared memory")
-
-struct McTablesSmem {
-    unsigned short sub_base[256];
-    unsigned short tile_off[MC_TILE_OFF_LEN];
-    short sub_true[MC_SUB_TRUE_LEN];
-    short sub_false[MC_SUB_FALSE_LEN];
-    signed char sub_interior[MC_SUB_INTERIOR_LEN];
-    unsigned char nface[256];
-    unsigned char faces[256 * 6];
-    unsigned char tile_ntri[MC_TILE_NTRI_LEN];
-    unsigned char tile_data[MC_TILE_DATA_LEN];
-};
-
-__device__ __forceinline__ void load_mc_tables(McTablesSmem* t, int tid, int nthreads) {
-    for (int i = tid; i < 256; i += nthreads) { t->sub_base[i] = MC_SUB_BASE[i]; t->nface[i] = MC_NFACE[i]; }
-    for (int i = tid; i < 256 * 6; i += nthreads) t->faces[i] = MC_FACES[i];
-    for (int i = tid; i < MC_TILE_OFF_LEN; i += nthreads) { t->tile_off[i] = MC_TILE_OFF[i]; t->tile_ntri[i] = MC_TILE_NTRI[i]; }
-    for (int i = tid; i < MC_SUB_TRUE_LEN; i += nthreads) {
-        t->sub_true[i] = MC_SUB_TRUE[i]; t->sub_false[i] = MC_SUB_FALSE[i]; t->sub_interior[i] = MC_SUB_INTERIOR[i];
-    }
-    for (int i = tid; i < MC_TILE_DATA_LEN; i += nthreads) t->tile_data[i] = MC_TILE_DATA[i];
-}
-
-__device__ __forceinline__ int mc_select_tiling(const McTablesSmem* t, int index, const double* v) {
-    const int nf = t->nface[index];
-    const int sgn = (__popc(index) <= 4) ? 1 : -1;
-    int mask = 0;
-    for (int j = 0; j < nf; ++j)
-        if (mc_test_face(v, sgn * (int)t->faces[index * 6 + j])) mask |= 1 << j;
-    const int sub = t->sub_base[index] + mask;
-    const int mode = t->sub_interior[sub];
-    if (mode < 0) return t->sub_true[sub];
-    return mc_test_interior(v, mode, 7 * sgn) ? t->sub_true[sub] : t->sub_false[sub];
-}
-
-// vertex on edge e (12 = centre), Lewiner cube-local coordinates added to (x,y,z)
-__device__ __forceinline__ void mc_edge_vertex(const double* v, int e, int x, int y, int z, float* out) {
-    double fx = 0, fy = 0, fz = 0, ff = 0;
-    const double eps = (double)FLT_EPSILON;
-    if (e == 12) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const double w = xdiv(1.0, xadd(eps, fabs(v[k])));
-            fx = xadd(fx, xmul((double)corner_x(k), w));
-            fy = xadd(fy, xmul((double)corner_y(k), w));
-            fz = xadd(fz, xmul((double)corner_z(k), w));
-            ff = xadd(ff, w);
-        }
-    } else {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int k = edge_corner(e, s);
-            double vk = v[0];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) vk = (k == j) ? v[j] : vk;      // keeps v[] in registers
-            const double w = xdiv(1.0, xadd(eps, fabs(vk)));
-            fx = xadd(fx, xmul((double)corner_x(k), w));
-            fy = xadd(fy, xmul((double)corner_y(k), w));
-            fz = xadd(fz, xmul((double)corner_z(k), w));
-            ff = xadd(ff, w);
-        }
-    }
-    out[0] = (float)xadd((double)x, xdiv(fx, ff));
-    out[1] = (float)xadd((double)y, xdiv(fy, ff));
-    out[2] = (float)xadd((double)z, xdiv(fz, ff));
-}
-
-// ---------------------------------------------------------------------------------------
-// skip pre-pass (core.py:28-43), one thread per batch, float64
-
-__device__ __forceinline__ double eval1_f64(const ProgramImage& img, double px, double py, double pz) {
-    double x[1] = {px}, y[1] = {py}, z[1] = {pz}, d[1];
-    sdf_interp<double, 1>(img, x, y, z, d);
-    return d[0];
-}
+// statically compiled kernels: the interpreter front end, program image in the parameter bank
 
 __global__ void __launch_bounds__(128)
-skip_prepass_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, int sparse,
-                    unsigned char* __restrict__ flags, unsigned int* __restrict__ active_list,
-                    Counters* __restrict__ ctr) {
-    const int nzl = g.zb1 - g.zb0;
-    const int total = g.nbx * g.nby * nzl;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
-    const int bz = g.zb0 + bzl;
-    const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + bz);
-    bool skipped = false;
-    if (sparse) {
-        const int ix0 = bx * g.bs, iy0 = by * g.bs, iz0 = bz * g.bs;
-        const int ix1 = min(ix0 + g.bs, g.nx - 1), iy1 = min(iy0 + g.bs, g.ny - 1), iz1 = min(iz0 + g.bs, g.nz - 1);
-        const double x0 = g.xs[ix0], x1 = g.xs[ix1], y0 = g.ys[iy0], y1 = g.ys[iy1], z0 = g.zs[iz0], z1 = g.zs[iz1];
-        const double x = __ddiv_rn(__dadd_rn(x0, x1), 2.0), y = __ddiv_rn(__dadd_rn(y0, y1), 2.0),
-                     z = __ddiv_rn(__dadd_rn(z0, z1), 2.0);
-        const double r = fabs(eval1_f64(img, x, y, z));
-        const double ex = __dsub_rn(x, x0), ey = __dsub_rn(y, y0), ez = __dsub_rn(z, z0);
-        const double dd = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
-        if (!(r <= dd)) {
-            // corners in itertools.product((x0,x1),(y0,y1),(z0,z1)) order; values[0] decides the sign
-            const double v0 = eval1_f64(img, x0, y0, z0);
-            const bool pos = v0 > 0;
-            bool same = pos ? (v0 > 0) : (v0 < 0);
-#pragma unroll 1
-            for (int k = 1; k < 8 && same; ++k) {
-                const double v = eval1_f64(img, (k & 4) ? x1 : x0, (k & 2) ? y1 : y0, (k & 1) ? z1 : z0);
-                same = pos ? (v > 0) : (v < 0);
-            }
-            skipped = same;
-        }
-    }
-    flags[bid] = skipped ? 1 : 0;
-    if (!skipped) {
-        const unsigned int slot = atomicAdd(&ctr->n_active, 1u);
-        active_list[slot] = bid;
-    } else {
-        atomicAdd(&ctr->skipped, 1u);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// fused tile kernel
-
-#define FUSED_THREADS 512
-#define REFINE_CAP 4096
-#define CHUNK_CUBES 4096
-
-template <int TS>
-struct FusedSmem {
-    static constexpr int TP = TS + 1;
-    static constexpr int NPTS = TP * TP * TP;
-    float tile[(NPTS + 3) & ~3];
-    McTablesSmem mc;
-    double axd[3][TP];
-    float axf[3][TP];
-    // phase-aliased scratch: refine list during evaluation, cube lists during extraction
-    union {
-        unsigned short refine[REFINE_CAP];
-        struct {
-            unsigned short cube[CHUNK_CUBES];
-            short tiling[CHUNK_CUBES];
-            unsigned short scan[CHUNK_CUBES];
-        } mcw;
-    } u;
-    unsigned int warp_sums[FUSED_THREADS / 32];
-    unsigned int n_refine;
-    unsigned int n_cubes;
-    unsigned int n_tris_chunk;
-    unsigned long long tri_base;
-    unsigned int work_item;
-    int minmax[2];       // order-preserving int encoding of float min / max
-    unsigned int tile_tris;
-};
-
-__device__ __forceinline__ int float_to_ordered(float f) {
-    const int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
+skip_prepass_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, int sparse, unsigned char* flags,
+                    unsigned int* active_list, Counters* ctr) {
+    skip_prepass_body(InterpEval{&img}, g, sparse, flags, active_list, ctr);
 }
 
 template <int TS, int PREC>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_tile_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const float tau,
-                  const unsigned int* __restrict__ active_list, unsigned int* __restrict__ batch_tris,
-                  Counters* __restrict__ ctr, float* __restrict__ tri_out, const unsigned long long tri_capacity) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using S = FusedSmem<TS>;
-    S& sm = *reinterpret_cast<S*>(smem_raw);
-    constexpr int TP = S::TP;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-
-    load_mc_tables(&sm.mc, tid, FUSED_THREADS);
-    const unsigned int n_active = ctr->n_active;           // written by the pre-pass (previous kernel)
-    const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
-    const unsigned int n_work = n_active * subs3;
-    unsigned long long my_f32 = 0, my_f64 = 0, my_cubes = 0;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            sm.work_item = atomicAdd(&ctr->work_cursor, 1u);
-            sm.n_refine = 0;
-            sm.minmax[0] = 0x7fffffff;
-            sm.minmax[1] = (int)0x80000000;
-            sm.tile_tris = 0;
-        }
-        __syncthreads();
-        const unsigned int w = sm.work_item;
-        if (w >= n_work) break;
-        const unsigned int bid = active_list[w / subs3];
-        const int sidx = (int)(w % subs3);
-        const int sz = sidx % g.sub, sy = (sidx / g.sub) % g.sub, sx = sidx / (g.sub * g.sub);
-        const int bz = (int)(bid % (unsigned)g.nbz), by = (int)((bid / (unsigned)g.nbz) % (unsigned)g.nby),
-                  bx = (int)(bid / (unsigned)(g.nbz * g.nby));
-        // batch extent in lattice points (core.py:115-117: slices [i, i+s+1) clipped)
-        const int bx0 = bx * g.bs, by0 = by * g.bs, bz0 = bz * g.bs;
-        const int blx = min(g.bs + 1, g.nx - bx0), bly = min(g.bs + 1, g.ny - by0), blz = min(g.bs + 1, g.nz - bz0);
-        // sub-tile extent inside the batch (local point indices)
-        const int ox = sx * TS, oy = sy * TS, oz = sz * TS;
-        const int px = min(TP, blx - ox), py = min(TP, bly - oy), pz = min(TP, blz - oz);
-        if (px <= 0 || py <= 0 || pz <= 0) continue;
-        if (sidx != 0 && (px < 2 || py < 2 || pz < 2)) continue;   // a 1-thick remainder holds no cube
-        const int npts = px * py * pz;
-
-        // stage the axis slices
-        for (int i = tid; i < px; i += FUSED_THREADS) { const double v = g.xs[bx0 + ox + i]; sm.axd[0][i] = v; sm.axf[0][i] = (float)v; }
-        for (int i = tid; i < py; i += FUSED_THREADS) { const double v = g.ys[by0 + oy + i]; sm.axd[1][i] = v; sm.axf[1][i] = (float)v; }
-        for (int i = tid; i < pz; i += FUSED_THREADS) { const double v = g.zs[bz0 + oz + i]; sm.axd[2][i] = v; sm.axf[2][i] = (float)v; }
-        __syncthreads();
-
-        // ---------------------------------------------------------------- evaluation
-        const unsigned int pyz = (unsigned int)(py * pz);
-        float vmin = FLT_MAX, vmax = -FLT_MAX;
-        if (PREC == SDFB200_PREC_F64) {
-            for (int idx = tid; idx < npts; idx += FUSED_THREADS) {
-                const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                sdf_interp<double, 1>(img, x, y, z, d);
-                const float f = (float)d[0];
-                sm.tile[idx] = f;
-                vmin = fminf(vmin, f); vmax = fmaxf(vmax, f);
-            }
-            my_f32 += 0;
-        } else {
-            constexpr int N = 2;
-            for (int base = 0; base < npts; base += FUSED_THREADS * N) {
-                float x[N], y[N], z[N], d[N];
-                int idxs[N];
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    int idx = base + k * FUSED_THREADS + tid;
-                    idxs[k] = idx;
-                    if (idx >= npts) idx = npts - 1;
-                    const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                    x[k] = sm.axf[0][ix]; y[k] = sm.axf[1][iy]; z[k] = sm.axf[2][iz];
-                }
-                sdf_interp<float, N>(img, x, y, z, d);
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    if (idxs[k] < npts) {
-                        sm.tile[idxs[k]] = d[k];
-                        vmin = fminf(vmin, d[k]); vmax = fmaxf(vmax, d[k]);
-                        if (PREC == SDFB200_PREC_MIXED && fabsf(d[k]) < tau) {
-                            const unsigned int slot = atomicAdd(&sm.n_refine, 1u);
-                            if (slot < REFINE_CAP) sm.u.refine[slot] = (unsigned short)idxs[k];
-                        }
-                    }
-                }
-            }
-        }
-        if (tid == 0) my_f32 += (unsigned long long)npts;
-        // warp-shuffle min/max reduction, one shared atomic per warp
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        }
-        if (lane == 0) {
-            atomicMin(&sm.minmax[0], float_to_ordered(vmin));
-            atomicMax(&sm.minmax[1], float_to_ordered(vmax));
-        }
-        __syncthreads();
-
-        // ------------------------------------- float64 re-evaluation of sign-critical samples
-        if (PREC == SDFB200_PREC_MIXED) {
-            const unsigned int nref = sm.n_refine;
-            if (nref > 0) {
-                if (nref <= REFINE_CAP) {
-                    for (unsigned int r = tid; r < nref; r += FUSED_THREADS) {
-                        const int idx = sm.u.refine[r];
-                        const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                        double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                        sdf_interp<double, 1>(img, x, y, z, d);
-                        sm.tile[idx] = (float)d[0];
-                    }
-                } else {   // list overflow: sweep the tile
-                    for (int idx = tid; idx < npts; idx += FUSED_THREADS) {
-                        if (fabsf(sm.tile[idx]) < tau) {
-                            const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                            double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                            sdf_interp<double, 1>(img, x, y, z, d);
-                            sm.tile[idx] = (float)d[0];
-                        }
-                    }
-                }
-                if (tid == 0) my_f64 += nref;
-                __syncthreads();
-            }
-        }
-
-        // -------------------------------------------------------------- early out
-        // No sample can be > 0 (or none <= 0): every cube index is 0 or 255.  (skimage raises
-        // ValueError / RuntimeError here; the reference maps both to an empty batch.)
-        {
-            const int omin = sm.minmax[0], omax = sm.minmax[1];
-            const float fmn = __int_as_float(omin >= 0 ? omin : omin ^ 0x7fffffff);
-            const float fmx = __int_as_float(omax >= 0 ? omax : omax ^ 0x7fffffff);
-            const float guard = (PREC == SDFB200_PREC_MIXED) ? tau : 0.0f;
-            if (fmn > guard || fmx < -guard || px < 2 || py < 2 || pz < 2) continue;
-        }
-
-        // -------------------------------------------------------- marching cubes
-        const int cxn = px - 1, cyn = py - 1, czn = pz - 1;
-        const int ncubes = cxn * cyn * czn;
-        const unsigned int cyz = (unsigned int)(cyn * czn);
-        // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
-        const double scx = __dsub_rn(g.xs[min(bx0 + 1, g.nx - 1)], g.xs[bx0]), ofx = g.xs[bx0];
-        const double scy = __dsub_rn(g.ys[min(by0 + 1, g.ny - 1)], g.ys[by0]), ofy = g.ys[by0];
-        const double scz = __dsub_rn(g.zs[min(bz0 + 1, g.nz - 1)], g.zs[bz0]), ofz = g.zs[bz0];
-
-        for (int c0 = 0; c0 < ncubes; c0 += CHUNK_CUBES) {
-            __syncthreads();
-            if (tid == 0) { sm.n_cubes = 0; }
-            __syncthreads();
-            // 1. classify: which cubes cross the level set
-            const int cend = min(ncubes, c0 + CHUNK_CUBES);
-            for (int cb = c0; cb < cend; cb += FUSED_THREADS) {
-                const int c = cb + tid;
-                bool act = false;
-                if (c < cend) {
-                    const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                    const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                    // Lewiner corner k -> (x_L, y_L, z_L) = (array axis 2, axis 1, axis 0)
-                    int index = 0;
-                    index |= (p[0] > 0.0f) ? 1 : 0;
-                    index |= (p[1] > 0.0f) ? 2 : 0;
-                    index |= (p[pz + 1] > 0.0f) ? 4 : 0;
-                    index |= (p[pz] > 0.0f) ? 8 : 0;
-                    index |= (p[pyz] > 0.0f) ? 16 : 0;
-                    index |= (p[pyz + 1] > 0.0f) ? 32 : 0;
-                    index |= (p[pyz + pz + 1] > 0.0f) ? 64 : 0;
-                    index |= (p[pyz + pz] > 0.0f) ? 128 : 0;
-                    act = (index != 0 && index != 255);
-                }
-                const unsigned int m = __ballot_sync(0xffffffffu, act);
-                if (act) {
-                    const unsigned int leader = __ffs(m) - 1;
-                    unsigned int basep = 0;
-                    if ((unsigned)lane == leader) basep = atomicAdd(&sm.n_cubes, (unsigned)__popc(m));
-                    basep = __shfl_sync(m, basep, leader);
-                    sm.u.mcw.cube[basep + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(c - c0);
-                }
-            }
-            __syncthreads();
-            const int nact = (int)sm.n_cubes;
-            if (nact == 0) continue;
-            if (tid == 0) my_cubes += (unsigned long long)nact;
-            // 2. choose the tiling of every active cube, 3. exclusive scan of triangle counts
-            unsigned int running = 0;
-            for (int a0 = 0; a0 < nact; a0 += FUSED_THREADS) {
-                const int ai = a0 + tid;
-                unsigned int nt = 0;
-                if (ai < nact) {
-                    const int c = c0 + (int)sm.u.mcw.cube[ai];
-                    const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                    const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                    double v[8];
-                    v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
-                    v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
-                    int index = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) index |= (v[k] > 0.0) ? (1 << k) : 0;
-                    const int tiling = mc_select_tiling(&sm.mc, index, v);
-                    sm.u.mcw.tiling[ai] = (short)tiling;
-                    nt = tiling >= 0 ? sm.mc.tile_ntri[tiling] : 0;
-                }
-                // block-wide exclusive scan of nt (warp shuffle + warp sums)
-                unsigned int incl = nt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += nb;
-                }
-                if (lane == 31) sm.warp_sums[warp] = incl;
-                __syncthreads();
-                unsigned int warp_off = 0, total = 0;
-#pragma unroll
-                for (int wi = 0; wi < FUSED_THREADS / 32; ++wi) {
-                    const unsigned int s = sm.warp_sums[wi];
-                    if (wi < warp) warp_off += s;
-                    total += s;
-                }
-                if (ai < nact) sm.u.mcw.scan[ai] = (unsigned short)(running + warp_off + incl - nt);
-                running += total;
-                __syncthreads();
-            }
-            // 4. reserve output space: one global atomic per chunk
-            if (tid == 0) {
-                sm.n_tris_chunk = running;
-                sm.tri_base = atomicAdd(&ctr->tri_cursor, (unsigned long long)running);
-                sm.tile_tris += running;
-            }
-            __syncthreads();
-            const unsigned int ntris = sm.n_tris_chunk;
-            const unsigned long long tbase = sm.tri_base;
-            if (tri_out == nullptr || tbase + ntris > tri_capacity) continue;   // count only / overflow
-            // 5. one thread per triangle: find its cube (binary search in the scan), emit 9 floats
-            for (unsigned int t = tid; t < ntris; t += FUSED_THREADS) {
-                int lo = 0, hi = nact - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (sm.u.mcw.scan[mid] <= t) lo = mid; else hi = mid - 1;
-                }
-                // skip cubes that emit nothing but share the scan value
-                const int ai = lo;
-                const int tiling = sm.u.mcw.tiling[ai];
-                const int tri = (int)(t - sm.u.mcw.scan[ai]);
-                const int c = c0 + (int)sm.u.mcw.cube[ai];
-                const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                double v[8];
-                v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
-                v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
-                const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling] + 3 * tri];
-                float* dst = tri_out + (tbase + t) * 9ull;
-                // batch-local voxel coordinates (the reference runs MC per batch)
-                const int lx = oz + cz, ly = oy + cy, lz = ox + cx;   // Lewiner x,y,z
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float q[3];
-                    mc_edge_vertex(v, ed[k], lx, ly, lz, q);
-                    // verts flipped to array-axis order (z,y,x)_L; faces flipped (a,b,c)->(c,b,a)
-                    float* o = dst + (2 - k) * 3;
-                    o[0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
-                    o[1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
-                    o[2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && sm.tile_tris) atomicAdd(&batch_tris[bid], sm.tile_tris);
-    }
-    if (tid == 0) {
-        atomicAdd(&ctr->pts_f32, my_f32);
-        atomicAdd(&ctr->pts_f64, my_f64);
-        atomicAdd(&ctr->active_cubes, my_cubes);
-    }
+                  const unsigned int* active_list, unsigned int* batch_tris, Counters* ctr, float* tri_out,
+                  const unsigned long long tri_capacity) {
+    fused_tile_body<TS, PREC>(InterpEval{&img}, g, tau, active_list, batch_tris, ctr, tri_out, tri_capacity);
 }
 
-__global__ void batch_stats_kernel(const GridDesc g, const unsigned char* __restrict__ flags,
-                                   const unsigned int* __restrict__ batch_tris, Counters* __restrict__ ctr) {
-    const int nzl = g.zb1 - g.zb0;
-    const int total = g.nbx * g.nby * nzl;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
-    const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + g.zb0 + bzl);
-    if (flags[bid]) return;
-    if (batch_tris[bid]) atomicAdd(&ctr->nonempty, 1u); else atomicAdd(&ctr->empty, 1u);
+__global__ void batch_stats_kernel(const GridDesc g, const unsigned char* flags, const unsigned int* batch_tris,
+                                   Counters* ctr) {
+    batch_stats_body(g, flags, batch_tris, ctr);
 }
 
-// ---------------------------------------------------------------------------------------
-// streamed point evaluation (SDF3.__call__): float3 AoS in HBM -> smem by TMA bulk copy
-
-#define STREAM_THREADS 256
-#define STREAM_PTS_PER_THREAD 4
-#define STREAM_TILE (STREAM_THREADS * STREAM_PTS_PER_THREAD)      // 1024 points = 12288 B
-#define STREAM_STAGES 3
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Persistent CTAs; each owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a 3-stage ring of
-// 12 KB point tiles is kept in flight by one elected thread issuing cp.async.bulk.
+template <bool FAST>
 __global__ void __launch_bounds__(STREAM_THREADS)
-eval_stream_f32_kernel(const __grid_constant__ ProgramImage img, const float* __restrict__ xyz, long long n,
-                       float* __restrict__ out) {
-    __shared__ __align__(128) float stage[STREAM_STAGES][STREAM_TILE * 3];
-    __shared__ __align__(8) uint64_t full[STREAM_STAGES];
-    const int tid = threadIdx.x;
-    const long long n_tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(xyz) & 15u) == 0);
-    if (tid == 0) {
-        for (int s = 0; s < STREAM_STAGES; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto tile_bytes = [&](long long t) -> unsigned {
-        const long long pts = min((long long)STREAM_TILE, n - t * STREAM_TILE);
-        return (unsigned)(pts * 12);
-    };
-    auto issue = [&](long long t, int s) {
-        const unsigned bytes = tile_bytes(t);
-        if (aligned && (bytes & 15u) == 0) {
-            mbar_expect_tx(&full[s], bytes);
-            tma_bulk_g2s(&stage[s][0], xyz + t * (long long)STREAM_TILE * 3, bytes, &full[s]);
-        }
-    };
-    // prologue
-    if (tid == 0) {
-        for (int s = 0; s < STREAM_STAGES; ++s) {
-            const long long t = blockIdx.x + (long long)s * gridDim.x;
-            if (t < n_tiles) issue(t, s);
-        }
-    }
-    int it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int s = it % STREAM_STAGES;
-        const unsigned parity = (unsigned)((it / STREAM_STAGES) & 1);
-        const unsigned bytes = tile_bytes(t);
-        const bool via_tma = aligned && (bytes & 15u) == 0;
-        const long long p0 = t * (long long)STREAM_TILE;
-        const int pts = (int)min((long long)STREAM_TILE, n - p0);
-        if (via_tma) {
-            mbar_wait(&full[s], parity);
-        } else {   // ragged / unaligned tail: plain coalesced loads into the same stage
-            for (int i = tid; i < pts * 3; i += STREAM_THREADS) stage[s][i] = xyz[p0 * 3 + i];
-            __syncthreads();
-        }
-        float x[STREAM_PTS_PER_THREAD], y[STREAM_PTS_PER_THREAD], z[STREAM_PTS_PER_THREAD], d[STREAM_PTS_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < STREAM_PTS_PER_THREAD; ++k) {
-            int i = k * STREAM_THREADS + tid;
-            if (i >= pts) i = pts - 1;
-            x[k] = stage[s][3 * i + 0]; y[k] = stage[s][3 * i + 1]; z[k] = stage[s][3 * i + 2];
-        }
-        sdf_interp<float, STREAM_PTS_PER_THREAD>(img, x, y, z, d);
-#pragma unroll
-        for (int k = 0; k < STREAM_PTS_PER_THREAD; ++k) {
-            const int i = k * STREAM_THREADS + tid;
-            if (i < pts) out[p0 + i] = d[k];
-        }
-        __syncthreads();                      // everyone is done reading stage s
-        if (tid == 0) {
-            const long long tn = t + (long long)STREAM_STAGES * gridDim.x;
-            if (tn < n_tiles) issue(tn, s);
-        }
-    }
+eval_stream_f32_kernel(const __grid_constant__ ProgramImage img, const float* xyz, long long n, float* out) {
+    eval_stream_f32_body<FAST>(InterpEval{&img}, xyz, n, out);
 }
 
 __global__ void __launch_bounds__(256)
-eval_stream_f64_kernel(const __grid_constant__ ProgramImage img, const double* __restrict__ xyz, long long n,
-                       double* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        double x[1] = {xyz[3 * i]}, y[1] = {xyz[3 * i + 1]}, z[1] = {xyz[3 * i + 2]}, d[1];
-        sdf_interp<double, 1>(img, x, y, z, d);
-        out[i] = d[0];
-    }
+eval_stream_f64_kernel(const __grid_constant__ ProgramImage img, const double* xyz, long long n, double* out) {
+    eval_stream_f64_body(InterpEval{&img}, xyz, n, out);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -740,11 +107,166 @@ struct DeviceCtx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
+enum JitKernel { JK_SKIP = 0, JK_FUSED0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_COUNT = 8 };
+
+struct JitEntry {
+    bool tried = false;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    bool smem_set[64] = {false};
+};
+
 struct sdfb200_prog {
     ProgramImage img;
+    int n_consts = 0;
     std::mutex lock;
     std::vector<DeviceCtx> ctxs;
+    JitEntry jit[JK_COUNT];
+    std::string jit_log;        // last NVRTC failure, if any
 };
+
+// ---------------------------------------------------------------------------------------
+// run-time specialisation: the lowered tree as straight-line CUDA, compiled with NVRTC for sm_100a
+//
+// Mode (env SDFB200_JIT): "1"/unset = use a specialised kernel when NVRTC is available and fall back
+// to the interpreter kernels otherwise; "0" = interpreter only.  NVRTC is loaded with dlopen so that a
+// box without it still runs (on the interpreter).
+
+struct NvrtcApi {
+    void* h = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    bool ok = false;
+};
+
+static NvrtcApi& nvrtc_api() {
+    static NvrtcApi api = [] {
+        NvrtcApi a;
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+        for (const char* n : names) { a.h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (a.h) break; }
+        if (!a.h) return a;
+        a.CreateProgram = (decltype(a.CreateProgram))dlsym(a.h, "nvrtcCreateProgram");
+        a.CompileProgram = (decltype(a.CompileProgram))dlsym(a.h, "nvrtcCompileProgram");
+        a.GetCUBINSize = (decltype(a.GetCUBINSize))dlsym(a.h, "nvrtcGetCUBINSize");
+        a.GetCUBIN = (decltype(a.GetCUBIN))dlsym(a.h, "nvrtcGetCUBIN");
+        a.GetProgramLogSize = (decltype(a.GetProgramLogSize))dlsym(a.h, "nvrtcGetProgramLogSize");
+        a.GetProgramLog = (decltype(a.GetProgramLog))dlsym(a.h, "nvrtcGetProgramLog");
+        a.DestroyProgram = (decltype(a.DestroyProgram))dlsym(a.h, "nvrtcDestroyProgram");
+        a.ok = a.CreateProgram && a.CompileProgram && a.GetCUBINSize && a.GetCUBIN && a.GetProgramLogSize &&
+               a.GetProgramLog && a.DestroyProgram;
+        return a;
+    }();
+    return api;
+}
+
+// 0 = interpreter only, 1 = specialise when the job is big enough to repay the compile (default),
+// 2 = always specialise.  Read on every call so tests can switch it.
+static int jit_mode() {
+    const char* e = getenv("SDFB200_JIT");
+    return e ? atoi(e) : 1;
+}
+
+static std::string csrc_dir() {
+    Dl_info info;
+    if (dladdr((const void*)&csrc_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        const size_t k = p.rfind('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/csrc";
+    }
+    return "csrc";
+}
+
+// The generated evaluator: one SdfOps call per program word, constants as literals.
+static std::string jit_source(const sdfb200_prog* p, int kernel) {
+    std::ostringstream o;
+    o << "#define SDF_JIT_KERNEL " << kernel << "\n#include \"sdf_kernels.cuh\"\n";
+    o << "struct SpecEval {\n  template <typename T, int N, bool FAST>\n"
+         "  __device__ __forceinline__ void run(T (&x)[N], T (&y)[N], T (&z)[N], T (&d)[N]) const {\n"
+         "    typedef SdfOps<T, N, FAST> O;\n    typename O::State st(x, y, z, d);\n";
+    o << "    const T C[" << (p->n_consts > 0 ? p->n_consts : 1) << "] = {";
+    for (int i = 0; i < p->n_consts; ++i) {
+        const double v = p->img.cd[i];
+        char buf[80];
+        if (isfinite(v)) snprintf(buf, sizeof(buf), "(T)%a", v);
+        else { long long bits; memcpy(&bits, &v, 8); snprintf(buf, sizeof(buf), "(T)__longlong_as_double(0x%llxLL)", bits); }
+        o << (i ? ", " : "") << buf;
+    }
+    if (p->n_consts == 0) o << "(T)0";
+    o << "};\n";
+    for (uint32_t i = 0; i < p->img.n_code; ++i) {
+        const uint32_t w = p->img.code[i];
+        o << "    O::" << SDF_OP_NAME[w & 0xff] << "(st, C + " << (w >> 16) << ", " << ((w >> 8) & 0xff) << ");\n";
+    }
+    o << "  }\n};\n#include \"sdf_jit_entry.cuh\"\n";
+    return o.str();
+}
+
+// NVRTC: source -> cubin for sm_100a.  Needs no GPU.
+static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_out) {
+    NvrtcApi& rt = nvrtc_api();
+    if (!rt.ok) { p->jit_log = "NVRTC (libnvrtc.so.12) not available"; return false; }
+    const std::string src = jit_source(p, kernel);
+    void* prog = nullptr;
+    if (rt.CreateProgram(&prog, src.c_str(), "sdfb200_jit.cu", 0, nullptr, nullptr) != 0) { p->jit_log = "nvrtcCreateProgram failed"; return false; }
+    const std::string inc = "-I" + csrc_dir();
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo", "--extra-device-vectorization"};
+    const int rc = rt.CompileProgram(prog, 5, opts);
+    if (rc != 0) {
+        size_t n = 0;
+        rt.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) rt.GetProgramLog(prog, &log[0]);
+        p->jit_log = "NVRTC compile failed (kernel " + std::to_string(kernel) + "): " + log;
+        if (getenv("SDFB200_JIT_VERBOSE")) fprintf(stderr, "%s\n", p->jit_log.c_str());
+        rt.DestroyProgram(&prog);
+        return false;
+    }
+    size_t sz = 0;
+    rt.GetCUBINSize(prog, &sz);
+    cubin_out->resize(sz);
+    rt.GetCUBIN(prog, cubin_out->data());
+    rt.DestroyProgram(&prog);
+    if (const char* dump = getenv("SDFB200_JIT_DUMP")) {       // debugging aid: keep source + cubin
+        const std::string base = std::string(dump) + "/jit_k" + std::to_string(kernel);
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fputs(src.c_str(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin_out->data(), 1, sz, f); fclose(f); }
+    }
+    return true;
+}
+
+// Compile (once) and return the specialised kernel, or nullptr when unavailable.
+static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true) {
+    const int mode = jit_mode();
+    if (mode == 0 || (mode == 1 && !big_enough)) return nullptr;
+    JitEntry& e = p->jit[kernel];
+    if (e.tried) return e.kern;
+    e.tried = true;
+    std::vector<char> cubin;
+    if (!jit_compile(p, kernel, &cubin)) return nullptr;
+    cudaLibrary_t lib = nullptr;
+    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+        p->jit_log = std::string("cudaLibraryLoadData failed: ") + cudaGetErrorString(cudaGetLastError());
+        return nullptr;
+    }
+    cudaKernel_t k = nullptr;
+    if (cudaLibraryGetKernel(&k, lib, "jit_kernel") != cudaSuccess) {
+        p->jit_log = std::string("cudaLibraryGetKernel failed: ") + cudaGetErrorString(cudaGetLastError());
+        cudaLibraryUnload(lib);
+        return nullptr;
+    }
+    e.lib = lib;
+    e.kern = k;
+    return k;
+}
+
+static cudaError_t jit_launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
+    return cudaLaunchKernel((const void*)k, grid, block, args, smem, stream);
+}
 
 static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     int count = 0;
@@ -774,6 +296,15 @@ static bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// 0 = pageable host, 1 = device, 2 = pinned (page-locked, device-mapped) host
+static int mem_kind(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 1;
+    if (a.type == cudaMemoryTypeHost) return 2;
+    return 0;
+}
+
 static int ensure_stage(DeviceCtx* c, size_t bytes) {
     if (bytes <= c->stage_cap) return 0;
     if (c->stage) cudaFree(c->stage);
@@ -794,6 +325,21 @@ extern "C" int sdfb200_device_count(int* count) {
     if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
     *count = n;
     return 0;
+}
+
+extern "C" int sdfb200_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(SDFB200_E_INVALID, "host_alloc: out is NULL");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(SDFB200_E_NOGPU, "no CUDA device available; libsdfb200 has no CPU fallback");
+    }
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    return 0;
+}
+
+extern "C" void sdfb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int sdfb200_program_create(const uint32_t* code, int n_code, const double* consts, int n_consts,
@@ -819,6 +365,7 @@ extern "C" int sdfb200_program_create(const uint32_t* code, int n_code, const do
     if (!p) return fail(SDFB200_E_INVALID, "out of host memory");
     memset(&p->img, 0, sizeof(ProgramImage));
     p->img.n_code = (uint32_t)n_code;
+    p->n_consts = n_consts;
     memcpy(p->img.code, code, sizeof(uint32_t) * n_code);
     for (int i = 0; i < n_consts; ++i) { p->img.cd[i] = consts[i]; p->img.cf[i] = (float)consts[i]; }
     *out = p;
@@ -833,10 +380,11 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         for (int i = 0; i < 4; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
     }
+    for (auto& e : prog->jit) if (e.lib) cudaLibraryUnload(e.lib);
     delete prog;
 }
 
-extern "C" int sdfb200_eval_f32(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream_) {
+static int eval_f32_impl(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream_, bool fast) {
     if (!prog || n < 0 || (n > 0 && (!xyz || !d_out))) return fail(SDFB200_E_INVALID, "eval_f32: bad argument");
     if (n == 0) return 0;
     std::lock_guard<std::mutex> guard(prog->lock);
@@ -853,11 +401,24 @@ extern "C" int sdfb200_eval_f32(sdfb200_prog* prog, const float* xyz, int64_t n,
     }
     const long long tiles = (n + STREAM_TILE - 1) / STREAM_TILE;
     const int grid = (int)std::min<long long>(tiles, (long long)c->sms * 4);
-    eval_stream_f32_kernel<<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    if (cudaKernel_t jk = jit_get(prog, fast ? JK_STREAM_F32_FAST : JK_STREAM_F32, n >= (1 << 20))) {
+        long long nn = (long long)n;
+        void* args[] = {(void*)&dx, (void*)&nn, (void*)&dd};
+        CUDA_TRY(jit_launch(jk, dim3(grid), dim3(STREAM_THREADS), 0, stream, args));
+    } else if (fast) eval_stream_f32_kernel<true><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    else eval_stream_f32_kernel<false><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
     CUDA_TRY(cudaGetLastError());
     if (!out_dev) CUDA_TRY(cudaMemcpyAsync(d_out, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
     if (!in_dev || !out_dev) CUDA_TRY(cudaStreamSynchronize(stream));
     return 0;
+}
+
+extern "C" int sdfb200_eval_f32(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream) {
+    return eval_f32_impl(prog, xyz, n, d_out, device, stream, false);
+}
+
+extern "C" int sdfb200_eval_f32_fast(sdfb200_prog* prog, const float* xyz, int64_t n, float* d_out, int device, void* stream) {
+    return eval_f32_impl(prog, xyz, n, d_out, device, stream, true);
 }
 
 extern "C" int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n, double* d_out, int device, void* stream_) {
@@ -876,7 +437,11 @@ extern "C" int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n
         if (!out_dev) dd = (double*)((char*)c->stage + in_pad);
     }
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sms * 8);
-    eval_stream_f64_kernel<<<grid, 256, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    if (cudaKernel_t jk = jit_get(prog, JK_STREAM_F64, n >= (1 << 20))) {     // small probes: not worth a compile
+        long long nn = (long long)n;
+        void* args[] = {(void*)&dx, (void*)&nn, (void*)&dd};
+        CUDA_TRY(jit_launch(jk, dim3(grid), dim3(256), 0, stream, args));
+    } else eval_stream_f64_kernel<<<grid, 256, 0, stream>>>(prog->img, dx, (long long)n, dd);
     CUDA_TRY(cudaGetLastError());
     if (!out_dev) CUDA_TRY(cudaMemcpyAsync(d_out, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
     if (!in_dev || !out_dev) CUDA_TRY(cudaStreamSynchronize(stream));
@@ -945,7 +510,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                                 int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
                                 double timings_ms[4], int device, void* stream_) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
-    if (precision < 0 || precision > 2) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
+    if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
     std::lock_guard<std::mutex> guard(prog->lock);
     DeviceCtx* c; int rc = get_ctx(prog, device, &c); if (rc) return rc;
@@ -953,9 +518,18 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     GridDesc g;
     CUDA_TRY(cudaEventRecord(c->ev[0], stream));
     rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, zb_begin, zb_end, &g); if (rc) return rc;
-    const bool out_dev = tri_out ? is_device_ptr(tri_out) : true;
+    // output placement: device pointer -> written in place; pinned host -> either written in place by
+    // the kernel over PCIe (zero copy, overlaps the transfer with the computation) or staged + one async
+    // copy; pageable host -> staged + copy
+    const int out_kind = tri_out ? mem_kind(tri_out) : 1;
+    static const bool zero_copy = [] { const char* e = getenv("SDFB200_ZEROCOPY"); return e ? atoi(e) != 0 : true; }();
+    bool out_dev = (out_kind == 1) || (out_kind == 2 && zero_copy);
     float* dtri = tri_out;
-    if (tri_out && !out_dev) {
+    if (tri_out && out_kind == 2 && zero_copy) {
+        void* dp = nullptr;
+        CUDA_TRY(cudaHostGetDevicePointer(&dp, tri_out, 0));
+        dtri = (float*)dp;
+    } else if (tri_out && !out_dev) {
         rc = ensure_stage(c, (size_t)tri_capacity * 36 + 256); if (rc) return rc;
         dtri = (float*)c->stage;
     }
@@ -971,10 +545,28 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
         const float tau = (float)tau_;
         const unsigned long long cap = tri_out ? (unsigned long long)tri_capacity : 0ull;
         cudaError_t e;
-        if (precision == SDFB200_PREC_F32)
+        const long long lattice = (long long)nx * ny * nz;
+        cudaKernel_t jk = jit_get(prog, JK_FUSED0 + precision, lattice >= (1 << 21));
+        if (jk) {
+            const size_t smem = sizeof(FusedSmem<kTS>);
+            JitEntry& je = prog->jit[JK_FUSED0 + precision];
+            if (!je.smem_set[device]) {
+                CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
+                je.smem_set[device] = true;
+            }
+            const unsigned int* act = c->active;
+            unsigned int* bt = c->batch_tris;
+            Counters* ctrp = c->ctr;
+            unsigned long long capv = cap;
+            float tauv = tau;
+            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&bt, (void*)&ctrp, (void*)&dtri, (void*)&capv};
+            e = jit_launch(jk, dim3(grid), dim3(FUSED_THREADS), smem, stream, args);
+        } else if (precision == SDFB200_PREC_F32)
             e = launch_fused<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
         else if (precision == SDFB200_PREC_MIXED)
             e = launch_fused<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
+        else if (precision == SDFB200_PREC_EXACT)
+            e = launch_fused<SDFB200_PREC_EXACT>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
         else
             e = launch_fused<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
         if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "fused_tile_kernel launch failed: %s", cudaGetErrorString(e));
@@ -1009,6 +601,15 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     if (overflow)
         return fail(SDFB200_E_CAPACITY, "triangle buffer too small: %lld needed, %lld given", (long long)h.tri_cursor,
                     (long long)tri_capacity);
+    return 0;
+}
+
+extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {
+    if (!prog || kernel < 0 || kernel >= JK_COUNT) return fail(SDFB200_E_INVALID, "jit_probe: bad argument");
+    std::lock_guard<std::mutex> guard(prog->lock);
+    std::vector<char> cubin;
+    if (!jit_compile(prog, kernel, &cubin)) return fail(SDFB200_E_INVALID, "%s", prog->jit_log.c_str());
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
 }
 

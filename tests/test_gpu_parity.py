@@ -10,6 +10,20 @@ pytestmark = pytest.mark.gpu
 SMALL = [('sphere', 64), ('csg', 96), ('gearlike', 128), ('blobby', 128), ('knurling', 160)]
 
 
+@pytest.fixture(scope='module', params=['interp', 'jit'], autouse=True)
+def evaluator_front_end(request):
+    """Every test runs twice: on the interpreter kernels (SDFB200_JIT=0) and on the run-time
+    specialised kernels (SDFB200_JIT=2: always compile, whatever the job size)."""
+    import os
+    old = os.environ.get('SDFB200_JIT')
+    os.environ['SDFB200_JIT'] = '0' if request.param == 'interp' else '2'
+    yield request.param
+    if old is None:
+        os.environ.pop('SDFB200_JIT', None)
+    else:
+        os.environ['SDFB200_JIT'] = old
+
+
 @pytest.fixture(scope='module')
 def sdf():
     import sdf_b200
@@ -79,7 +93,7 @@ def test_eval_ragged_sizes(sdf, ref):
 
 
 @pytest.mark.parametrize('name,n', SMALL)
-@pytest.mark.parametrize('precision', ['f64', 'mixed'])
+@pytest.mark.parametrize('precision', ['f64', 'mixed', 'exact'])
 def test_generate_matches_oracle(sdf, ref, golden_dir, name, n, precision):
     """Whole hot path: batch classification == reference goldens, triangles == oracle."""
     f = models.CONFIGS[name](sdf)
@@ -99,6 +113,42 @@ def test_generate_matches_oracle(sdf, ref, golden_dir, name, n, precision):
         assert rep['exact_triangles'] >= 0.999 * rep['n_ref'], rep
     topo = mesh_topology(pts)
     assert topo['boundary'] == 0 and topo['nonmanifold'] == 0 and topo['repeated_directed'] == 0, topo
+
+
+@pytest.mark.parametrize('name,n', SMALL)
+def test_exact_mode_equals_f64_mode_bitwise(sdf, name, n):
+    """PREC_EXACT (fast float32 classification + float64 on everything that reaches the output)
+    must reproduce the all-float64 run triangle for triangle."""
+    f = models.CONFIGS[name](sdf)
+    _, L = models.CONFIG_GRIDS[name]
+    bounds, step = ((-L, -L, -L), (L, L, L)), 2.0 * L / n
+    a, ia = sdf.generate(f, step=step, bounds=bounds, verbose=False, precision='f64', return_info=True)
+    b, ib = sdf.generate(f, step=step, bounds=bounds, verbose=False, precision='exact', return_info=True)
+    assert (ia['skipped'], ia['empty'], ia['nonempty'], ia['active_cubes']) == (ib['skipped'], ib['empty'], ib['nonempty'], ib['active_cubes'])
+    rep = compare_soups(b, a)
+    assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], rep
+    assert ib['refined'] < 0.2 * ib['evaluated']
+
+
+def test_fast_stream_evaluator_error_is_inside_the_guard_band(sdf, ref, corpus):
+    """The approximate-math evaluator may only be wrong by less than tau (the samples it gets
+    'wrong enough to matter' are exactly the ones PREC_EXACT re-evaluates in float64)."""
+    import torch
+    from sdf_b200 import core
+    P64 = models.random_points(1 << 16, seed=5, L=2.5)
+    P32 = P64.astype(np.float32)
+    Pd = torch.from_numpy(P32).cuda()
+    X = np.array([-2.5, 2.5])
+    for name, f in corpus.items():
+        h, _ = core.program_handle(f)
+        out = torch.empty(len(P32), device='cuda')
+        h.eval_f32_fast(Pd, out, len(P32))
+        d = out.cpu().numpy()
+        r = ref.evaluate(f, P32.astype(np.float64)).reshape(-1)
+        ok = np.isfinite(r) & np.isfinite(d) & (np.abs(r) < 1.0)
+        tau = core.mixed_tau(h.program, X, X, X)
+        err = np.abs(d[ok] - r[ok])
+        assert err.max() < tau, (name, float(err.max()), tau)
 
 
 def test_generate_auto_bounds_matches_reference_goldens(sdf, golden_dir):

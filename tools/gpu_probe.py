@@ -17,7 +17,7 @@ from sdf_b200 import core
 
 def main():
     names = sys.argv[1].split(',') if len(sys.argv) > 1 else list(models.CONFIGS)
-    precs = sys.argv[2].split(',') if len(sys.argv) > 2 else ['f32', 'mixed', 'f64']
+    precs = sys.argv[2].split(',') if len(sys.argv) > 2 else ['f32', 'mixed', 'exact', 'f64']
     for name in names:
         n, L = models.CONFIG_GRIDS[name]
         f = models.CONFIGS[name](sdf_b200)
@@ -44,22 +44,23 @@ def main():
     npts = 512 ** 3
     rng = torch.Generator(device='cuda').manual_seed(0)
     P = (torch.rand((npts, 3), device='cuda', generator=rng) * 5 - 2.5)
-    for name in names:
+    for name, fast in [(n, fa) for n in names for fa in (False, True)]:
         f = models.CONFIGS[name](sdf_b200)
         h, _ = core.program_handle(f)
         out = torch.empty(npts, device='cuda')
         s = torch.cuda.current_stream().cuda_stream
+        fn = h.eval_f32_fast if fast else h.eval_f32
         for _ in range(2):
-            h.eval_f32(P, out, npts, stream=s)
+            fn(P, out, npts, stream=s)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            h.eval_f32(P, out, npts, stream=s)
+            fn(P, out, npts, stream=s)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        print(json.dumps(dict(stream_eval=name, ms=round(ms, 3), gpts_per_s=round(npts / ms / 1e6, 2),
+        print(json.dumps(dict(stream_eval=name, fast=fast, ms=round(ms, 3), gpts_per_s=round(npts / ms / 1e6, 2),
                               gbs_12B=round(npts * 12 / ms / 1e6, 1), gbs_16B=round(npts * 16 / ms / 1e6, 1))), flush=True)
 
 
