@@ -258,7 +258,7 @@ def run_ours(args):
             'metric': 'Mpoints/s', 'value': n_points / (ms_per_step / 1e3) / 1e6, 'unit': 'Mpoints/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'mixed': 'f32 (+f64 re-evaluation of |d|<tau samples)', 'f32': 'f32', 'f64': 'f64'}[args.precision],
+            'dtype': {'mixed': 'f32 (+f64 re-evaluation of |d|<tau samples)', 'f32': 'f32', 'f64': 'f64', 'exact': 'f32 classification + f64 for every sample that reaches the output'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': '%s tree (reference examples/%s.py), %d^3 lattice, bounds +-%g, sparse skip on, batch 32'
                                    % (w['model'], w['model'], w['n'], w['L']),
@@ -295,7 +295,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default='gearlike')
     ap.add_argument('--grid', type=int, default=None)
-    ap.add_argument('--precision', default='mixed', choices=['f32', 'mixed', 'f64', 'exact'])
+    ap.add_argument('--precision', default='exact', choices=['f32', 'mixed', 'f64', 'exact'])
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-batches', type=int, default=4096)

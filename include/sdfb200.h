@@ -47,9 +47,9 @@ int sdfb200_device_count(int* count);
 
 /*
  * Page-locked, device-mapped host memory for output buffers (cudaHostAlloc).  Replaces nothing in
- * the reference (numpy owns its buffers, core.py:128); a tri_out allocated here is either written
- * directly by the kernel over PCIe (default) or filled by one asynchronous copy
- * (SDFB200_ZEROCOPY=0), instead of the slow pageable path.
+ * the reference (numpy owns its buffers, core.py:128); a tri_out allocated here is filled by one asynchronous
+ * copy at PCIe rate (default) or, with SDFB200_ZEROCOPY=1, written directly by the kernel over PCIe --
+ * measured slower on B200 (scattered 4-byte stores) -- instead of the slow pageable path.
  */
 int sdfb200_host_alloc(size_t bytes, void** out);
 void sdfb200_host_free(void* p);

@@ -148,7 +148,7 @@ def default_capacity(X, Y, Z):
     return int(max(1 << 16, 8 * (nx * ny + ny * nz + nx * nz)))
 
 
-def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='mixed',
+def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='exact',
                 zb=(0, -1), device=None, out=None, stream=None):
     """One C-ABI generate call (with the retry on capacity overflow).
 
@@ -189,7 +189,7 @@ def generate(
         step=None, bounds=None, samples=SAMPLES,
         workers=WORKERS, batch_size=BATCH_SIZE,
         verbose=True, sparse=True, *,
-        precision='mixed', device=None, return_info=False):
+        precision='exact', device=None, return_info=False):
     """Mesh ``sdf`` (core.py:84-150).
 
     Returns the triangle soup as an ``(3*T, 3)`` float32 ndarray of world-space

@@ -9,11 +9,15 @@ jit_kernel(const GridDesc g, int sparse, unsigned char* flags, unsigned int* act
     skip_prepass_body(SpecEval(), g, sparse, flags, active_list, ctr);
 }
 #elif SDF_JIT_KERNEL >= 1 && SDF_JIT_KERNEL <= 4
-extern "C" __global__ void __launch_bounds__(FUSED_THREADS, 1)
-jit_kernel(const GridDesc g, const float tau, const unsigned int* active_list, unsigned int* batch_tris,
-           Counters* ctr, float* tri_out, const unsigned long long tri_capacity) {
-    fused_tile_body<32, SDF_JIT_KERNEL - 1>(SpecEval(), g, tau, active_list, batch_tris, ctr, tri_out, tri_capacity);
+#define SDF_JIT_TILE_THREADS ((SDF_JIT_KERNEL - 1) == SDFB200_PREC_F64 ? 512 : 1024)
+extern "C" __global__ void __launch_bounds__(SDF_JIT_TILE_THREADS, 1)
+jit_kernel(const GridDesc g, const float tau, const unsigned int* active_list, const unsigned int work_begin,
+           const unsigned int work_end, const TileLists L, Counters* ctr) {
+    tile_eval_body<32, SDF_JIT_KERNEL - 1, SDF_JIT_TILE_THREADS>(SpecEval(), g, tau, active_list, work_begin, work_end, L, ctr);
 }
+#elif SDF_JIT_KERNEL == 8
+extern "C" __global__ void __launch_bounds__(128)
+jit_kernel(const GridDesc g, const TileLists L, Counters* ctr) { refine_points_body<32>(SpecEval(), g, L, ctr); }
 #elif SDF_JIT_KERNEL == 5
 extern "C" __global__ void __launch_bounds__(STREAM_THREADS)
 jit_kernel(const float* xyz, long long n, float* out) { eval_stream_f32_body<false>(SpecEval(), xyz, n, out); }

@@ -58,7 +58,9 @@ struct Counters {
     unsigned int n_active;              // non-skipped batches
     unsigned int work_cursor;
     unsigned int skipped, empty, nonempty;
-    unsigned int pad_;
+    unsigned int n_slots, n_cubes, n_pts;       // per round: stored tiles, candidate cubes, queued samples
+    unsigned int max_cubes, max_pts;            // high-water marks over rounds (capacity check)
+    unsigned int pad_[2];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -176,6 +178,30 @@ __device__ __forceinline__ int mc_select_tiling(const McTablesSmem* t, int index
     return mc_test_interior(v, mode, 7 * sgn) ? t->sub_true[sub] : t->sub_false[sub];
 }
 
+// Vertex on a cube edge e < 12, same rounding as mc_edge_vertex(): with w = 1/(eps+|v|) per corner,
+// the coordinate along the edge is x + w_far/(w0+w1); across the edge both corners share the
+// coordinate c, where the generic form gives (c*w0 + c*w1)/(w0+w1) = 0 or exactly 1.
+__device__ __forceinline__ void mc_edge_vertex_fast(const double* v, int e, int x, int y, int z, float* out) {
+    const double eps = (double)FLT_EPSILON;
+    const int k0 = edge_corner(e, 0), k1 = edge_corner(e, 1);
+    double v0 = v[0], v1 = v[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { v0 = (k0 == j) ? v[j] : v0; v1 = (k1 == j) ? v[j] : v1; }
+    const double w0 = xdiv(1.0, xadd(eps, fabs(v0)));
+    const double w1 = xdiv(1.0, xadd(eps, fabs(v1)));
+    const double ff = xadd(w0, w1);
+    const int dx = corner_x(k0) ^ corner_x(k1), dy = corner_y(k0) ^ corner_y(k1);
+    // the corner that sits at coordinate 1 along the edge contributes its weight
+    const int far_is_k1 = dx ? corner_x(k1) : (dy ? corner_y(k1) : corner_z(k1));
+    const double q = xdiv(far_is_k1 ? w1 : w0, ff);
+    const double fx = dx ? q : (double)corner_x(k0);
+    const double fy = dx ? (double)corner_y(k0) : (dy ? q : (double)corner_y(k0));
+    const double fz = (dx | dy) ? (double)corner_z(k0) : q;
+    out[0] = (float)xadd((double)x, fx);
+    out[1] = (float)xadd((double)y, fy);
+    out[2] = (float)xadd((double)z, fz);
+}
+
 // vertex on edge e (12 = centre), Lewiner cube-local coordinates added to (x,y,z)
 __device__ __forceinline__ void mc_edge_vertex(const double* v, int e, int x, int y, int z, float* out) {
     double fx = 0, fy = 0, fz = 0, ff = 0;
@@ -263,40 +289,65 @@ __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc&
 }
 
 // ---------------------------------------------------------------------------------------
-// fused tile kernel
+// tile pipeline: (A) fused evaluate + classify per tile, (B) float64 refinement of the samples that
+// can reach the output, (C) marching-cubes extraction -- B and C are flat, full-occupancy kernels
+// over the compacted lists that A builds, so the sparse, latency-bound work never runs inside one
+// lonely CTA.
 
-#define FUSED_THREADS 512
-#define REFINE_CAP 4096
-#define CHUNK_CUBES 4096
-#define CORNER_ROUND 1024      // (cube, corner) pairs examined per refinement round of PREC_EXACT
+#define VOL_STRIDE 35968            // floats per stored tile: 33^3 = 35937 rounded up to a multiple of 32
 
+struct TileLists {
+    float* vol;                     // [slot][VOL_STRIDE] float32 tile volumes (tile-local linearisation)
+    uint2* tile_meta;               // [slot] {batch id, sub-tile index}
+    uint2* cubes;                   // candidate cubes {slot, tile-local cube id}
+    uint2* pts;                     // samples to re-evaluate in float64 {slot, tile-local sample id}
+    unsigned int slot_cap, cube_cap, pt_cap;
+};
+
+struct TileGeom {
+    int bx0, by0, bz0;              // lattice index of the batch origin
+    int ox, oy, oz;                 // sub-tile offset inside the batch (samples)
+    int px, py, pz;                 // sub-tile extent (samples)
+};
+
+// batch id + sub-tile index -> extents (core.py:115-117: slices [i, i+s+1) clipped to the axis)
 template <int TS>
-struct FusedSmem {
+__device__ __forceinline__ bool tile_geom(const GridDesc& g, unsigned int bid, int sidx, TileGeom& t) {
+    const int sz = sidx % g.sub, sy = (sidx / g.sub) % g.sub, sx = sidx / (g.sub * g.sub);
+    const int bz = (int)(bid % (unsigned)g.nbz), by = (int)((bid / (unsigned)g.nbz) % (unsigned)g.nby),
+              bx = (int)(bid / (unsigned)(g.nbz * g.nby));
+    t.bx0 = bx * g.bs; t.by0 = by * g.bs; t.bz0 = bz * g.bs;
+    const int blx = min(g.bs + 1, g.nx - t.bx0), bly = min(g.bs + 1, g.ny - t.by0), blz = min(g.bs + 1, g.nz - t.bz0);
+    t.ox = sx * TS; t.oy = sy * TS; t.oz = sz * TS;
+    t.px = min(TS + 1, blx - t.ox); t.py = min(TS + 1, bly - t.oy); t.pz = min(TS + 1, blz - t.oz);
+    if (t.px <= 0 || t.py <= 0 || t.pz <= 0) return false;
+    if (sidx != 0 && (t.px < 2 || t.py < 2 || t.pz < 2)) return false;   // a 1-thick remainder holds no cube
+    return true;
+}
+
+// n / d for n < 2^16 * d, d >= 1, through a precomputed reciprocal (the tile loops divide a lot)
+struct FastDiv {
+    unsigned int m; unsigned int d;
+    __device__ __forceinline__ void init(unsigned int d_) { d = d_; m = (unsigned int)((0xffffffffull / d_) + 1ull); }
+    __device__ __forceinline__ unsigned int div(unsigned int n) const {
+        unsigned int q = __umulhi(n, m);
+        return (d == 1) ? n : q;
+    }
+};
+
+template <int TS, bool F64>
+struct TileSmem {
     static constexpr int TP = TS + 1;
     static constexpr int NPTS = TP * TP * TP;
     float tile[(NPTS + 3) & ~3];
-    McTablesSmem mc;
-    double axd[3][TP];
+    unsigned int bits[(NPTS + 31) / 32];            // samples already queued for float64
+    unsigned int cand[(TS * TS * TS + 31) / 32];    // candidate cubes, one bit per cube (tile-local id)
     float axf[3][TP];
-    // phase-aliased scratch: refine list during evaluation, cube lists during extraction
-    union {
-        unsigned short refine[REFINE_CAP];
-        struct {
-            unsigned short cube[CHUNK_CUBES];
-            short tiling[CHUNK_CUBES];
-            unsigned short scan[CHUNK_CUBES];
-        } mcw;
-    } u;
-    unsigned int refined_bits[(NPTS + 31) / 32];     // samples whose tile value already is float64-derived
-    unsigned short corner_list[CORNER_ROUND];
-    unsigned int warp_sums[FUSED_THREADS / 32];
-    unsigned int n_refine;
-    unsigned int n_cubes;
-    unsigned int n_tris_chunk;
-    unsigned long long tri_base;
-    unsigned int work_item;
-    int minmax[2];       // order-preserving int encoding of float min / max
-    unsigned int tile_tris;
+    double axd[F64 ? 3 : 1][F64 ? TP : 1];
+    int minmax[2];
+    unsigned int work_item, slot, any_cand;
+    unsigned int warp_sums[32];
+    unsigned int cube_gbase, pt_gbase;
 };
 
 __device__ __forceinline__ int float_to_ordered(float f) {
@@ -304,101 +355,92 @@ __device__ __forceinline__ int float_to_ordered(float f) {
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
 
-template <int TS, int PREC, class EV>
-__device__ __forceinline__ void fused_tile_body(const EV& img, const GridDesc& g, const float tau,
-                                                const unsigned int* __restrict__ active_list,
-                                                unsigned int* __restrict__ batch_tris, Counters* __restrict__ ctr,
-                                                float* __restrict__ tri_out, const unsigned long long tri_capacity) {
+// (A) one CTA per tile: evaluate the lattice samples into shared memory, classify every cube, queue the
+// candidate cubes and the samples float64 must confirm, store the tile volume.
+//   PREC_F32   accurate float32; candidates = cubes with mixed `v > 0` corners
+//   PREC_MIXED accurate float32; samples with |d| < tau are uncertain -> queued for float64
+//   PREC_F64   float64 evaluation of every sample
+//   PREC_EXACT fast float32; uncertain samples AND every corner of a candidate cube queued for float64
+template <int TS, int PREC, int THREADS, class EV>
+__device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, const float tau,
+                                               const unsigned int* __restrict__ active_list,
+                                               const unsigned int work_begin, const unsigned int work_end,
+                                               const TileLists L, Counters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using S = FusedSmem<TS>;
-    S& sm = *reinterpret_cast<S*>(smem_raw);
-    constexpr int TP = S::TP;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    constexpr bool F64 = (PREC == SDFB200_PREC_F64);
     constexpr bool REFINE = (PREC == SDFB200_PREC_MIXED || PREC == SDFB200_PREC_EXACT);
     constexpr bool EXACT = (PREC == SDFB200_PREC_EXACT);
-
-    load_mc_tables(&sm.mc, tid, FUSED_THREADS);
-    const unsigned int n_active = ctr->n_active;           // written by the pre-pass (previous kernel)
+    using S = TileSmem<TS, F64>;
+    S& sm = *reinterpret_cast<S*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
-    const unsigned int n_work = n_active * subs3;
-    unsigned long long my_f32 = 0, my_f64 = 0, my_cubes = 0;
+    unsigned long long my_pts = 0;
 
+    // Every barrier below is executed unconditionally by every thread in every iteration: the
+    // per-tile decisions (degenerate tile, early out, no candidates) only predicate the work
+    // between the barriers.
+    if (tid == 0) {
+        sm.work_item = work_begin + atomicAdd(&ctr->work_cursor, 1u);
+        sm.minmax[0] = 0x7fffffff;
+        sm.minmax[1] = (int)0x80000000;
+        sm.any_cand = 0;
+    }
+    __syncthreads();
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            sm.work_item = atomicAdd(&ctr->work_cursor, 1u);
-            sm.n_refine = 0;
-            sm.minmax[0] = 0x7fffffff;
-            sm.minmax[1] = (int)0x80000000;
-            sm.tile_tris = 0;
-        }
-        __syncthreads();
         const unsigned int w = sm.work_item;
-        if (w >= n_work) break;
+        if (w >= work_end) break;
         const unsigned int bid = active_list[w / subs3];
         const int sidx = (int)(w % subs3);
-        const int sz = sidx % g.sub, sy = (sidx / g.sub) % g.sub, sx = sidx / (g.sub * g.sub);
-        const int bz = (int)(bid % (unsigned)g.nbz), by = (int)((bid / (unsigned)g.nbz) % (unsigned)g.nby),
-                  bx = (int)(bid / (unsigned)(g.nbz * g.nby));
-        // batch extent in lattice points (core.py:115-117: slices [i, i+s+1) clipped)
-        const int bx0 = bx * g.bs, by0 = by * g.bs, bz0 = bz * g.bs;
-        const int blx = min(g.bs + 1, g.nx - bx0), bly = min(g.bs + 1, g.ny - by0), blz = min(g.bs + 1, g.nz - bz0);
-        // sub-tile extent inside the batch (local point indices)
-        const int ox = sx * TS, oy = sy * TS, oz = sz * TS;
-        const int px = min(TP, blx - ox), py = min(TP, bly - oy), pz = min(TP, blz - oz);
-        if (px <= 0 || py <= 0 || pz <= 0) continue;
-        if (sidx != 0 && (px < 2 || py < 2 || pz < 2)) continue;   // a 1-thick remainder holds no cube
+        TileGeom t;
+        const bool valid = tile_geom<TS>(g, bid, sidx, t);
+        if (!valid) { t.px = t.py = t.pz = 1; t.bx0 = t.by0 = t.bz0 = t.ox = t.oy = t.oz = 0; }
+        const int px = t.px, py = t.py, pz = t.pz;
         const int npts = px * py * pz;
+        const unsigned int pyz = (unsigned int)(py * pz);
+        FastDiv dpyz, dpz;
+        dpyz.init(pyz); dpz.init((unsigned int)pz);
 
-        if (EXACT) { for (int i = tid; i < (S::NPTS + 31) / 32; i += FUSED_THREADS) sm.refined_bits[i] = 0u; }
-        // stage the axis slices
-        for (int i = tid; i < px; i += FUSED_THREADS) { const double v = g.xs[bx0 + ox + i]; sm.axd[0][i] = v; sm.axf[0][i] = (float)v; }
-        for (int i = tid; i < py; i += FUSED_THREADS) { const double v = g.ys[by0 + oy + i]; sm.axd[1][i] = v; sm.axf[1][i] = (float)v; }
-        for (int i = tid; i < pz; i += FUSED_THREADS) { const double v = g.zs[bz0 + oz + i]; sm.axd[2][i] = v; sm.axf[2][i] = (float)v; }
+        for (int i = tid; i < px; i += THREADS) { const double v = g.xs[t.bx0 + t.ox + i]; sm.axf[0][i] = (float)v; if (F64) sm.axd[0][F64 ? i : 0] = v; }
+        for (int i = tid; i < py; i += THREADS) { const double v = g.ys[t.by0 + t.oy + i]; sm.axf[1][i] = (float)v; if (F64) sm.axd[F64 ? 1 : 0][F64 ? i : 0] = v; }
+        for (int i = tid; i < pz; i += THREADS) { const double v = g.zs[t.bz0 + t.oz + i]; sm.axf[2][i] = (float)v; if (F64) sm.axd[F64 ? 2 : 0][F64 ? i : 0] = v; }
+        if (REFINE) { for (int i = tid; i < (S::NPTS + 31) / 32; i += THREADS) sm.bits[i] = 0u; }
         __syncthreads();
 
         // ---------------------------------------------------------------- evaluation
-        const unsigned int pyz = (unsigned int)(py * pz);
         float vmin = FLT_MAX, vmax = -FLT_MAX;
-        if (PREC == SDFB200_PREC_F64) {
-            for (int idx = tid; idx < npts; idx += FUSED_THREADS) {
-                const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                img.template run<double, 1, false>(x, y, z, d);
+        if (F64) {
+            for (int idx = tid; idx < npts; idx += THREADS) {
+                const unsigned int ix = dpyz.div(idx), rem = idx - ix * pyz, iy = dpz.div(rem), iz = rem - iy * pz;
+                double x[1] = {sm.axd[0][F64 ? ix : 0]}, y[1] = {sm.axd[F64 ? 1 : 0][F64 ? iy : 0]},
+                       z[1] = {sm.axd[F64 ? 2 : 0][F64 ? iz : 0]}, d[1];
+                ev.template run<double, 1, false>(x, y, z, d);
                 const float f = (float)d[0];
                 sm.tile[idx] = f;
                 vmin = fminf(vmin, f); vmax = fmaxf(vmax, f);
             }
-            my_f32 += 0;
         } else {
-            constexpr int N = 2;
-            for (int base = 0; base < npts; base += FUSED_THREADS * N) {
+            constexpr int N = EV::kN;
+            for (int base = 0; base < npts; base += THREADS * N) {
                 float x[N], y[N], z[N], d[N];
-                int idxs[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    int idx = base + k * FUSED_THREADS + tid;
-                    idxs[k] = idx;
+                    int idx = base + k * THREADS + tid;
                     if (idx >= npts) idx = npts - 1;
-                    const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
+                    const unsigned int ix = dpyz.div(idx), rem = idx - ix * pyz, iy = dpz.div(rem), iz = rem - iy * pz;
                     x[k] = sm.axf[0][ix]; y[k] = sm.axf[1][iy]; z[k] = sm.axf[2][iz];
                 }
-                img.template run<float, N, (PREC == SDFB200_PREC_EXACT)>(x, y, z, d);
+                ev.template run<float, N, EXACT>(x, y, z, d);
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    if (idxs[k] < npts) {
-                        sm.tile[idxs[k]] = d[k];
+                    const int idx = base + k * THREADS + tid;
+                    if (idx < npts) {
+                        sm.tile[idx] = d[k];
                         vmin = fminf(vmin, d[k]); vmax = fmaxf(vmax, d[k]);
-                        if (REFINE && fabsf(d[k]) < tau) {
-                            const unsigned int slot = atomicAdd(&sm.n_refine, 1u);
-                            if (slot < REFINE_CAP) sm.u.refine[slot] = (unsigned short)idxs[k];
-                        }
                     }
                 }
             }
         }
-        if (tid == 0) my_f32 += (unsigned long long)npts;
+        if (tid == 0 && valid) my_pts += (unsigned long long)npts;
         // warp-shuffle min/max reduction, one shared atomic per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -410,212 +452,263 @@ __device__ __forceinline__ void fused_tile_body(const EV& img, const GridDesc& g
             atomicMax(&sm.minmax[1], float_to_ordered(vmax));
         }
         __syncthreads();
-
-        // ------------------------------------- float64 re-evaluation of sign-critical samples
-        if (REFINE) {
-            const unsigned int nref = sm.n_refine;
-            if (nref > 0) {
-                if (nref <= REFINE_CAP) {
-                    for (unsigned int r = tid; r < nref; r += FUSED_THREADS) {
-                        const int idx = sm.u.refine[r];
-                        if (EXACT) atomicOr(&sm.refined_bits[idx >> 5], 1u << (idx & 31));
-                        const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                        double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                        img.template run<double, 1, false>(x, y, z, d);
-                        sm.tile[idx] = (float)d[0];
-                    }
-                } else {   // list overflow: sweep the tile
-                    for (int idx = tid; idx < npts; idx += FUSED_THREADS) {
-                        if (fabsf(sm.tile[idx]) < tau) {
-                            if (EXACT) atomicOr(&sm.refined_bits[idx >> 5], 1u << (idx & 31));
-                            const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                            double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                            img.template run<double, 1, false>(x, y, z, d);
-                            sm.tile[idx] = (float)d[0];
-                        }
-                    }
-                }
-                if (tid == 0) my_f64 += nref;
-                __syncthreads();
-            }
-        }
-
-        // -------------------------------------------------------------- early out
-        // No sample can be > 0 (or none <= 0): every cube index is 0 or 255.  (skimage raises
-        // ValueError / RuntimeError here; the reference maps both to an empty batch.)
+        // early out: no sample can be > 0, or none can be <= 0: every cube index is 0 or 255 (skimage
+        // raises ValueError / RuntimeError there; the reference maps both to an empty batch)
+        bool live;
         {
             const int omin = sm.minmax[0], omax = sm.minmax[1];
             const float fmn = __int_as_float(omin >= 0 ? omin : omin ^ 0x7fffffff);
             const float fmx = __int_as_float(omax >= 0 ? omax : omax ^ 0x7fffffff);
             const float guard = REFINE ? tau : 0.0f;
-            if (fmn > guard || fmx < -guard || px < 2 || py < 2 || pz < 2) continue;
+            live = valid && !(fmn > guard || fmx < -guard || px < 2 || py < 2 || pz < 2);
         }
+        if (tid == 0 && live) sm.slot = atomicAdd(&ctr->n_slots, 1u);
+        __syncthreads();
+        const unsigned int slot = sm.slot;
+        live = live && (slot < L.slot_cap);                   // always true: one slot per work item
 
-        // -------------------------------------------------------- marching cubes
-        const int cxn = px - 1, cyn = py - 1, czn = pz - 1;
-        const int ncubes = cxn * cyn * czn;
+        // ------------------------------------------------------------ classification
+        const int cyn = py - 1, czn = pz - 1;
+        const int ncubes = (px - 1) * cyn * czn;
         const unsigned int cyz = (unsigned int)(cyn * czn);
-        // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
-        const double scx = __dsub_rn(g.xs[min(bx0 + 1, g.nx - 1)], g.xs[bx0]), ofx = g.xs[bx0];
-        const double scy = __dsub_rn(g.ys[min(by0 + 1, g.ny - 1)], g.ys[by0]), ofy = g.ys[by0];
-        const double scz = __dsub_rn(g.zs[min(bz0 + 1, g.nz - 1)], g.zs[bz0]), ofz = g.zs[bz0];
-
-        for (int c0 = 0; c0 < ncubes; c0 += CHUNK_CUBES) {
-            __syncthreads();
-            if (tid == 0) { sm.n_cubes = 0; }
-            __syncthreads();
-            // 1. classify: which cubes cross the level set
-            const int cend = min(ncubes, c0 + CHUNK_CUBES);
-            for (int cb = c0; cb < cend; cb += FUSED_THREADS) {
-                const int c = cb + tid;
-                bool act = false;
-                if (c < cend) {
-                    const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                    const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                    // Lewiner corner k -> (x_L, y_L, z_L) = (array axis 2, axis 1, axis 0)
-                    int index = 0;
-                    index |= (p[0] > 0.0f) ? 1 : 0;
-                    index |= (p[1] > 0.0f) ? 2 : 0;
-                    index |= (p[pz + 1] > 0.0f) ? 4 : 0;
-                    index |= (p[pz] > 0.0f) ? 8 : 0;
-                    index |= (p[pyz] > 0.0f) ? 16 : 0;
-                    index |= (p[pyz + 1] > 0.0f) ? 32 : 0;
-                    index |= (p[pyz + pz + 1] > 0.0f) ? 64 : 0;
-                    index |= (p[pyz + pz] > 0.0f) ? 128 : 0;
-                    act = (index != 0 && index != 255);
+        FastDiv dcyz, dcz;
+        dcyz.init(cyz > 0u ? cyz : 1u); dcz.init(czn > 0 ? (unsigned int)czn : 1u);
+        const int ncubes_up = live ? (ncubes + THREADS - 1) / THREADS * THREADS : 0;
+        for (int c = tid; c < ncubes_up; c += THREADS) {
+            bool cand = false;
+            unsigned int want = 0;                            // corners to queue for float64 (bit k)
+            int base_idx = 0;
+            if (c < ncubes) {
+                const unsigned int cx = dcyz.div(c), rem = c - cx * cyz, cy = dcz.div(rem), cz = rem - cy * czn;
+                base_idx = (int)((cx * py + cy) * pz + cz);
+                const float* p = &sm.tile[base_idx];
+                // Lewiner corner k -> (x_L, y_L, z_L) = (array axis 2, axis 1, axis 0)
+                const float v0 = p[0], v1 = p[1], v2 = p[pz + 1], v3 = p[pz], v4 = p[pyz], v5 = p[pyz + 1],
+                            v6 = p[pyz + pz + 1], v7 = p[pyz + pz];
+                unsigned int pos = 0, unc = 0;
+                pos |= (v0 > 0.0f) ? 1u : 0u;  pos |= (v1 > 0.0f) ? 2u : 0u;  pos |= (v2 > 0.0f) ? 4u : 0u;  pos |= (v3 > 0.0f) ? 8u : 0u;
+                pos |= (v4 > 0.0f) ? 16u : 0u; pos |= (v5 > 0.0f) ? 32u : 0u; pos |= (v6 > 0.0f) ? 64u : 0u; pos |= (v7 > 0.0f) ? 128u : 0u;
+                if (REFINE) {
+                    unc |= (fabsf(v0) < tau) ? 1u : 0u;  unc |= (fabsf(v1) < tau) ? 2u : 0u;  unc |= (fabsf(v2) < tau) ? 4u : 0u;  unc |= (fabsf(v3) < tau) ? 8u : 0u;
+                    unc |= (fabsf(v4) < tau) ? 16u : 0u; unc |= (fabsf(v5) < tau) ? 32u : 0u; unc |= (fabsf(v6) < tau) ? 64u : 0u; unc |= (fabsf(v7) < tau) ? 128u : 0u;
                 }
-                const unsigned int m = __ballot_sync(0xffffffffu, act);
-                if (act) {
-                    const unsigned int leader = __ffs(m) - 1;
-                    unsigned int basep = 0;
-                    if ((unsigned)lane == leader) basep = atomicAdd(&sm.n_cubes, (unsigned)__popc(m));
-                    basep = __shfl_sync(m, basep, leader);
-                    sm.u.mcw.cube[basep + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(c - c0);
-                }
+                cand = (unc != 0u) || (pos != 0u && pos != 255u);
+                want = EXACT ? (cand ? 255u : 0u) : unc;
             }
-            __syncthreads();
-            const int nact = (int)sm.n_cubes;
-            if (nact == 0) continue;
-            if (tid == 0) my_cubes += (unsigned long long)nact;
-            if (EXACT) {
-                // 1b. every corner of an active cube feeds the output: replace its float32 value by
-                // the float64 evaluation (once per sample: refined_bits), CORNER_ROUND pairs a round
-                const int npairs = nact * 8;
-                for (int p0 = 0; p0 < npairs; p0 += CORNER_ROUND) {
-                    if (tid == 0) sm.n_refine = 0;
-                    __syncthreads();
-                    const int pend = min(npairs, p0 + CORNER_ROUND);
-                    for (int q = p0 + tid; q < pend; q += FUSED_THREADS) {
-                        const int c = c0 + (int)sm.u.mcw.cube[q >> 3];
-                        const int k = q & 7;
-                        const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                        const int idx = ((cx + corner_z(k)) * py + cy + corner_y(k)) * pz + cz + corner_x(k);
+            // the 32 lanes of a warp hold 32 consecutive cubes: the ballot IS the candidate word
+            const unsigned int m = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0) sm.cand[c >> 5] = m;
+            if (REFINE && m) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if ((want >> k) & 1u) {
+                        const int idx = base_idx + corner_z(k) * (int)pyz + corner_y(k) * pz + corner_x(k);
                         const unsigned int bit = 1u << (idx & 31);
-                        const unsigned int old = atomicOr(&sm.refined_bits[idx >> 5], bit);
-                        if (!(old & bit)) sm.corner_list[atomicAdd(&sm.n_refine, 1u)] = (unsigned short)idx;
+                        if (!(sm.bits[idx >> 5] & bit)) atomicOr(&sm.bits[idx >> 5], bit);
                     }
-                    __syncthreads();
-                    const unsigned int nref = sm.n_refine;
-                    for (unsigned int r = tid; r < nref; r += FUSED_THREADS) {
-                        const int idx = sm.corner_list[r];
-                        const int ix = idx / pyz, rem = idx - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
-                        double x[1] = {sm.axd[0][ix]}, y[1] = {sm.axd[1][iy]}, z[1] = {sm.axd[2][iz]}, d[1];
-                        img.template run<double, 1, false>(x, y, z, d);
-                        sm.tile[idx] = (float)d[0];
-                    }
-                    if (tid == 0) my_f64 += nref;
-                    __syncthreads();
-                }
-            }
-            // 2. choose the tiling of every active cube, 3. exclusive scan of triangle counts
-            unsigned int running = 0;
-            for (int a0 = 0; a0 < nact; a0 += FUSED_THREADS) {
-                const int ai = a0 + tid;
-                unsigned int nt = 0;
-                if (ai < nact) {
-                    const int c = c0 + (int)sm.u.mcw.cube[ai];
-                    const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                    const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                    double v[8];
-                    v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
-                    v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
-                    int index = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) index |= (v[k] > 0.0) ? (1 << k) : 0;
-                    const int tiling = mc_select_tiling(&sm.mc, index, v);
-                    sm.u.mcw.tiling[ai] = (short)tiling;
-                    nt = tiling >= 0 ? sm.mc.tile_ntri[tiling] : 0;
-                }
-                // block-wide exclusive scan of nt (warp shuffle + warp sums)
-                unsigned int incl = nt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += nb;
-                }
-                if (lane == 31) sm.warp_sums[warp] = incl;
-                __syncthreads();
-                unsigned int warp_off = 0, total = 0;
-#pragma unroll
-                for (int wi = 0; wi < FUSED_THREADS / 32; ++wi) {
-                    const unsigned int s = sm.warp_sums[wi];
-                    if (wi < warp) warp_off += s;
-                    total += s;
-                }
-                if (ai < nact) sm.u.mcw.scan[ai] = (unsigned short)(running + warp_off + incl - nt);
-                running += total;
-                __syncthreads();
-            }
-            // 4. reserve output space: one global atomic per chunk
-            if (tid == 0) {
-                sm.n_tris_chunk = running;
-                sm.tri_base = atomicAdd(&ctr->tri_cursor, (unsigned long long)running);
-                sm.tile_tris += running;
-            }
-            __syncthreads();
-            const unsigned int ntris = sm.n_tris_chunk;
-            const unsigned long long tbase = sm.tri_base;
-            if (tri_out == nullptr || tbase + ntris > tri_capacity) continue;   // count only / overflow
-            // 5. one thread per triangle: find its cube (binary search in the scan), emit 9 floats
-            for (unsigned int t = tid; t < ntris; t += FUSED_THREADS) {
-                int lo = 0, hi = nact - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (sm.u.mcw.scan[mid] <= t) lo = mid; else hi = mid - 1;
-                }
-                // skip cubes that emit nothing but share the scan value
-                const int ai = lo;
-                const int tiling = sm.u.mcw.tiling[ai];
-                const int tri = (int)(t - sm.u.mcw.scan[ai]);
-                const int c = c0 + (int)sm.u.mcw.cube[ai];
-                const int cx = c / cyz, rem = c - cx * cyz, cy = rem / czn, cz = rem - cy * czn;
-                const float* p = &sm.tile[(cx * py + cy) * pz + cz];
-                double v[8];
-                v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
-                v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
-                const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling] + 3 * tri];
-                float* dst = tri_out + (tbase + t) * 9ull;
-                // batch-local voxel coordinates (the reference runs MC per batch)
-                const int lx = oz + cz, ly = oy + cy, lz = ox + cx;   // Lewiner x,y,z
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    float q[3];
-                    mc_edge_vertex(v, ed[k], lx, ly, lz, q);
-                    // verts flipped to array-axis order (z,y,x)_L; faces flipped (a,b,c)->(c,b,a)
-                    float* o = dst + (2 - k) * 3;
-                    o[0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
-                    o[1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
-                    o[2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
                 }
             }
         }
         __syncthreads();
-        if (tid == 0 && sm.tile_tris) atomicAdd(&batch_tris[bid], sm.tile_tris);
+        // ---------------------------------------------- compaction of the two bitmaps
+        // one prefix sum over the per-thread popcounts (cubes in the low, samples in the high half
+        // word), ONE pair of global atomics per tile, then every thread writes its own entries
+        {
+            const int nwc = live ? (ncubes + 31) >> 5 : 0;
+            const int nwp = (live && REFINE) ? (npts + 31) >> 5 : 0;
+            unsigned int cnt = 0;
+            for (int wi = tid; wi < nwc; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
+            for (int wi = tid; wi < nwp; wi += THREADS) cnt += ((unsigned)__popc(sm.bits[wi])) << 16;
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            if (lane == 31) sm.warp_sums[tid >> 5] = incl;
+            __syncthreads();
+            unsigned int warp_off = 0, total = 0;
+#pragma unroll
+            for (int wi = 0; wi < THREADS / 32; ++wi) {
+                const unsigned int sv = sm.warp_sums[wi];
+                if (wi < (tid >> 5)) warp_off += sv;
+                total += sv;
+            }
+            if (tid == 0) {
+                sm.any_cand = total & 0xffffu;
+                sm.cube_gbase = (total & 0xffffu) ? atomicAdd(&ctr->n_cubes, total & 0xffffu) : 0u;
+                sm.pt_gbase = (total >> 16) ? atomicAdd(&ctr->n_pts, total >> 16) : 0u;
+            }
+            __syncthreads();
+            const unsigned int excl = warp_off + incl - cnt;
+            unsigned int cat = sm.cube_gbase + (excl & 0xffffu);
+            unsigned int pat = sm.pt_gbase + (excl >> 16);
+            for (int wi = tid; wi < nwc; wi += THREADS) {
+                unsigned int word = sm.cand[wi];
+                while (word) {
+                    const int bpos = __ffs(word) - 1;
+                    word &= word - 1u;
+                    if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)(wi * 32 + bpos));
+                    ++cat;
+                }
+            }
+            for (int wi = tid; wi < nwp; wi += THREADS) {
+                unsigned int word = sm.bits[wi];
+                while (word) {
+                    const int bpos = __ffs(word) - 1;
+                    word &= word - 1u;
+                    if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)(wi * 32 + bpos));
+                    ++pat;
+                }
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------- store the tile volume
+        if (live && sm.any_cand) {
+            float* dst = L.vol + (size_t)slot * VOL_STRIDE;
+            for (int i = tid; i < npts; i += THREADS) dst[i] = sm.tile[i];
+            if (tid == 0) L.tile_meta[slot] = make_uint2(bid, (unsigned int)sidx);
+        }
+        __syncthreads();                                      // everyone is done with this tile's state
+        if (tid == 0) {
+            sm.work_item = work_begin + atomicAdd(&ctr->work_cursor, 1u);
+            sm.minmax[0] = 0x7fffffff;
+            sm.minmax[1] = (int)0x80000000;
+            sm.any_cand = 0;
+        }
+        __syncthreads();
     }
-    if (tid == 0) {
-        atomicAdd(&ctr->pts_f32, my_f32);
-        atomicAdd(&ctr->pts_f64, my_f64);
-        atomicAdd(&ctr->active_cubes, my_cubes);
+    if (tid == 0) atomicAdd(&ctr->pts_f32, my_pts);
+}
+
+// (B) float64 re-evaluation of the queued samples, flat over the whole list.
+template <int TS, class EV>
+__device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc& g, const TileLists L,
+                                                   Counters* __restrict__ ctr) {
+    const unsigned int n = min(ctr->n_pts, L.pt_cap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 e = L.pts[i];
+        const uint2 meta = L.tile_meta[e.x];
+        TileGeom t;
+        tile_geom<TS>(g, meta.x, (int)meta.y, t);
+        const unsigned int pyz = (unsigned int)(t.py * t.pz);
+        const unsigned int ix = e.y / pyz, rem = e.y - ix * pyz, iy = rem / (unsigned)t.pz, iz = rem - iy * t.pz;
+        double x[1] = {g.xs[t.bx0 + t.ox + ix]}, y[1] = {g.ys[t.by0 + t.oy + iy]}, z[1] = {g.zs[t.bz0 + t.oz + iz]}, d[1];
+        ev.template run<double, 1, false>(x, y, z, d);
+        L.vol[(size_t)e.x * VOL_STRIDE + e.y] = (float)d[0];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->pts_f64, (unsigned long long)n);
+}
+
+// (C) Lewiner marching cubes over the candidate list: one thread per cube selects the tiling
+// (tables in shared memory), a CTA prefix sum reserves the output range with one global atomic,
+// every thread then writes its cube's triangles (world-mapped, core.py:58-60).
+#define EXTRACT_THREADS 256
+
+struct ExtractSmem {
+    McTablesSmem mc;
+    unsigned int warp_sums[EXTRACT_THREADS / 32];
+    unsigned long long tri_base;
+    unsigned int n_active;
+};
+
+template <int TS>
+__device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists L, Counters* __restrict__ ctr,
+                                             unsigned int* __restrict__ batch_tris, float* __restrict__ tri_out,
+                                             const unsigned long long tri_capacity) {
+    __shared__ ExtractSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_mc_tables(&sm.mc, tid, EXTRACT_THREADS);
+    const unsigned int n = min(ctr->n_cubes, L.cube_cap);
+    const unsigned int n_up = (n + EXTRACT_THREADS - 1) / EXTRACT_THREADS * EXTRACT_THREADS;
+    unsigned int my_active = 0;
+    for (unsigned int i0 = blockIdx.x * EXTRACT_THREADS; i0 < n_up; i0 += gridDim.x * EXTRACT_THREADS) {
+        __syncthreads();
+        const unsigned int i = i0 + tid;
+        double v[8];
+        int tiling = -1;
+        unsigned int nt = 0;
+        uint2 e = make_uint2(0u, 0u), meta = make_uint2(0u, 0u);
+        TileGeom t;
+        int cx = 0, cy = 0, cz = 0;
+        if (i < n) {
+            e = L.cubes[i];
+            meta = L.tile_meta[e.x];
+            tile_geom<TS>(g, meta.x, (int)meta.y, t);
+            const int czn = t.pz - 1, cyz = (t.py - 1) * czn;
+            const int pz = t.pz, pyz = t.py * t.pz;
+            cx = (int)e.y / cyz; const int rem = (int)e.y - cx * cyz; cy = rem / czn; cz = rem - cy * czn;
+            const float* p = L.vol + (size_t)e.x * VOL_STRIDE + (size_t)((cx * t.py + cy) * pz + cz);
+            v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
+            v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
+            int index = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) index |= (v[k] > 0.0) ? (1 << k) : 0;
+            if (index != 0 && index != 255) {
+                ++my_active;
+                tiling = mc_select_tiling(&sm.mc, index, v);
+                nt = tiling >= 0 ? sm.mc.tile_ntri[tiling] : 0;
+            }
+        }
+        // CTA-wide exclusive scan of nt
+        unsigned int incl = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        __syncthreads();
+        unsigned int warp_off = 0, total = 0;
+#pragma unroll
+        for (int wi = 0; wi < EXTRACT_THREADS / 32; ++wi) {
+            const unsigned int s = sm.warp_sums[wi];
+            if (wi < warp) warp_off += s;
+            total += s;
+        }
+        if (tid == 0) sm.tri_base = total ? atomicAdd(&ctr->tri_cursor, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        if (nt != 0) atomicAdd(&batch_tris[meta.x], nt);
+        const unsigned long long first = sm.tri_base + warp_off + incl - nt;
+        if (nt != 0 && tri_out != nullptr && first + nt <= tri_capacity) {   // else: count only / overflow
+        // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
+        const double scx = __dsub_rn(g.xs[min(t.bx0 + 1, g.nx - 1)], g.xs[t.bx0]), ofx = g.xs[t.bx0];
+        const double scy = __dsub_rn(g.ys[min(t.by0 + 1, g.ny - 1)], g.ys[t.by0]), ofy = g.ys[t.by0];
+        const double scz = __dsub_rn(g.zs[min(t.bz0 + 1, g.nz - 1)], g.zs[t.bz0]), ofz = g.zs[t.bz0];
+        const int lx = t.oz + cz, ly = t.oy + cy, lz = t.ox + cx;             // Lewiner x,y,z (batch-local)
+        const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling]];
+        float* dst = tri_out + first * 9ull;
+        // every edge vertex of the cube is computed once (a cube with nt triangles touches about
+        // nt + 2 edges, not 3 nt) and already world-mapped; triangles then only copy
+        float ev[13][3];
+        unsigned int have = 0;
+        for (unsigned int tri = 0; tri < nt; ++tri, dst += 9, ed += 3) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = ed[k];
+                if (!((have >> e) & 1u)) {
+                    float q[3];
+                    if (e < 12) mc_edge_vertex_fast(v, e, lx, ly, lz, q);
+                    else mc_edge_vertex(v, e, lx, ly, lz, q);
+                    // verts flipped to array-axis order (z,y,x)_L, then core.py:58-60
+                    ev[e][0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
+                    ev[e][1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
+                    ev[e][2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
+                    have |= 1u << e;
+                }
+                float* o = dst + (2 - k) * 3;            // faces flipped (a,b,c) -> (c,b,a)
+                o[0] = ev[e][0]; o[1] = ev[e][1]; o[2] = ev[e][2];
+            }
+        }
+        }
+    }
+    // statistics
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_active += __shfl_xor_sync(0xffffffffu, my_active, o);
+    if (lane == 0 && my_active) atomicAdd(&ctr->active_cubes, (unsigned long long)my_active);
+    if (blockIdx.x == 0 && tid == 0) {
+        atomicMax(&ctr->max_cubes, ctr->n_cubes);
+        atomicMax(&ctr->max_pts, ctr->n_pts);
     }
 }
 

@@ -601,6 +601,7 @@ __device__ __forceinline__ void sdf_interp(const ProgramImage& img, T (&x)[N], T
 // Evaluator handed to the kernels (sdf_kernels.cuh): the interpreter over a ProgramImage.  The
 // run-time-generated evaluator (struct SpecEval in the JIT translation unit) has the same shape.
 struct InterpEval {
+    static constexpr int kN = 2;             // samples per thread in the tile kernel
     const ProgramImage* img;
     template <typename T, int N, bool FAST>
     __device__ __forceinline__ void run(T (&x)[N], T (&y)[N], T (&z)[N], T (&d)[N]) const {

@@ -68,12 +68,27 @@ skip_prepass_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, 
     skip_prepass_body(InterpEval{&img}, g, sparse, flags, active_list, ctr);
 }
 
+#define INTERP_TILE_THREADS 512
+
 template <int TS, int PREC>
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
-fused_tile_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const float tau,
-                  const unsigned int* active_list, unsigned int* batch_tris, Counters* ctr, float* tri_out,
-                  const unsigned long long tri_capacity) {
-    fused_tile_body<TS, PREC>(InterpEval{&img}, g, tau, active_list, batch_tris, ctr, tri_out, tri_capacity);
+__global__ void __launch_bounds__(INTERP_TILE_THREADS, 1)
+tile_eval_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const float tau,
+                 const unsigned int* active_list, const unsigned int work_begin, const unsigned int work_end,
+                 const TileLists L, Counters* ctr) {
+    tile_eval_body<TS, PREC, INTERP_TILE_THREADS>(InterpEval{&img}, g, tau, active_list, work_begin, work_end, L, ctr);
+}
+
+template <int TS>
+__global__ void __launch_bounds__(128)
+refine_points_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const TileLists L, Counters* ctr) {
+    refine_points_body<TS>(InterpEval{&img}, g, L, ctr);
+}
+
+template <int TS>
+__global__ void __launch_bounds__(EXTRACT_THREADS)
+extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
+               const unsigned long long tri_capacity) {
+    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity);
 }
 
 __global__ void batch_stats_kernel(const GridDesc g, const unsigned char* flags, const unsigned int* batch_tris,
@@ -104,10 +119,14 @@ struct DeviceCtx {
     Counters* ctr = nullptr;
     Counters* ctr_host = nullptr;       // pinned
     void* stage = nullptr; size_t stage_cap = 0;   // staging for host in/out buffers
+    // tile pipeline work lists (TileLists)
+    float* vol = nullptr; size_t slot_cap = 0; uint2* tile_meta = nullptr; size_t meta_cap = 0;
+    uint2* cubes = nullptr; size_t cube_cap = 0;
+    uint2* pts = nullptr; size_t pt_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
-enum JitKernel { JK_SKIP = 0, JK_FUSED0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_COUNT = 8 };
+enum JitKernel { JK_SKIP = 0, JK_TILE0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_REFINE = 8, JK_COUNT = 9 };
 
 struct JitEntry {
     bool tried = false;
@@ -185,7 +204,7 @@ static std::string csrc_dir() {
 static std::string jit_source(const sdfb200_prog* p, int kernel) {
     std::ostringstream o;
     o << "#define SDF_JIT_KERNEL " << kernel << "\n#include \"sdf_kernels.cuh\"\n";
-    o << "struct SpecEval {\n  template <typename T, int N, bool FAST>\n"
+    o << "struct SpecEval {\n  static constexpr int kN = 4;\n  template <typename T, int N, bool FAST>\n"
          "  __device__ __forceinline__ void run(T (&x)[N], T (&y)[N], T (&z)[N], T (&d)[N]) const {\n"
          "    typedef SdfOps<T, N, FAST> O;\n    typename O::State st(x, y, z, d);\n";
     o << "    const T C[" << (p->n_consts > 0 ? p->n_consts : 1) << "] = {";
@@ -378,6 +397,7 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaSetDevice(c.device);
         cudaFree(c.axes); cudaFree(c.flags); cudaFree(c.active); cudaFree(c.batch_tris); cudaFree(c.ctr);
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
+        cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
         for (int i = 0; i < 4; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
     }
     for (auto& e : prog->jit) if (e.lib) cudaLibraryUnload(e.lib);
@@ -494,21 +514,33 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
     return 0;
 }
 
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc(p, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
 template <int PREC>
-static cudaError_t launch_fused(int grid, cudaStream_t stream, const ProgramImage& img, const GridDesc& g, float tau,
-                                const unsigned int* active, unsigned int* batch_tris, Counters* ctr, float* tri_out,
-                                unsigned long long cap) {
-    const size_t smem = sizeof(FusedSmem<kTS>);
-    cudaError_t e = cudaFuncSetAttribute(fused_tile_kernel<kTS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t launch_tile_eval(int grid, cudaStream_t stream, const ProgramImage& img, const GridDesc& g, float tau,
+                                    const unsigned int* active, unsigned int wb, unsigned int we, const TileLists& L,
+                                    Counters* ctr) {
+    const size_t smem = sizeof(TileSmem<kTS, PREC == SDFB200_PREC_F64>);
+    cudaError_t e = cudaFuncSetAttribute(tile_eval_kernel<kTS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fused_tile_kernel<kTS, PREC><<<grid, FUSED_THREADS, smem, stream>>>(img, g, tau, active, batch_tris, ctr, tri_out, cap);
+    tile_eval_kernel<kTS, PREC><<<grid, INTERP_TILE_THREADS, smem, stream>>>(img, g, tau, active, wb, we, L, ctr);
     return cudaGetLastError();
 }
 
+static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kept per round
+
 extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                                 const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
-                                int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
-                                double timings_ms[4], int device, void* stream_) {
+                                int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
+                                int64_t stats[6], double timings_ms[4], int device, void* stream_) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
     if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
@@ -522,7 +554,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     // the kernel over PCIe (zero copy, overlaps the transfer with the computation) or staged + one async
     // copy; pageable host -> staged + copy
     const int out_kind = tri_out ? mem_kind(tri_out) : 1;
-    static const bool zero_copy = [] { const char* e = getenv("SDFB200_ZEROCOPY"); return e ? atoi(e) != 0 : true; }();
+    static const bool zero_copy = [] { const char* e = getenv("SDFB200_ZEROCOPY"); return e ? atoi(e) != 0 : false; }();
     bool out_dev = (out_kind == 1) || (out_kind == 2 && zero_copy);
     float* dtri = tri_out;
     if (tri_out && out_kind == 2 && zero_copy) {
@@ -535,41 +567,115 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     }
     const int nzl = g.zb1 - g.zb0;
     const long long total_b = (long long)g.nbx * g.nby * nzl;
+    const unsigned long long cap = tri_out ? (unsigned long long)tri_capacity : 0ull;
+    const float tau = (float)tau_;
+    const long long lattice = (long long)nx * ny * nz;
+    const bool big = lattice >= (1 << 21);
+    Counters& h = *c->ctr_host;
     if (total_b > 0) {
         const int pb = (int)((total_b + 127) / 128);
-        skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->ctr);
-        CUDA_TRY(cudaGetLastError());
+        // ---- skip pre-pass
+        if (cudaKernel_t jk = jit_get(prog, JK_SKIP, big)) {
+            unsigned char* fl = c->flags; unsigned int* act = c->active; Counters* ctrp = c->ctr;
+            void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&ctrp};
+            CUDA_TRY(jit_launch(jk, dim3(pb), dim3(128), 0, stream, args));
+        } else {
+            skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->ctr);
+            CUDA_TRY(cudaGetLastError());
+        }
         CUDA_TRY(cudaEventRecord(c->ev[1], stream));
-        const long long max_work = total_b * g.sub * g.sub * g.sub;
-        const int grid = (int)std::min<long long>(max_work, (long long)c->sms);
-        const float tau = (float)tau_;
-        const unsigned long long cap = tri_out ? (unsigned long long)tri_capacity : 0ull;
-        cudaError_t e;
-        const long long lattice = (long long)nx * ny * nz;
-        cudaKernel_t jk = jit_get(prog, JK_FUSED0 + precision, lattice >= (1 << 21));
-        if (jk) {
-            const size_t smem = sizeof(FusedSmem<kTS>);
-            JitEntry& je = prog->jit[JK_FUSED0 + precision];
-            if (!je.smem_set[device]) {
-                CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
-                je.smem_set[device] = true;
+        // the number of active batches sizes the work lists
+        CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        const unsigned long long n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
+        const unsigned long long max_round = std::max<unsigned long long>(1ull, kVolBudgetBytes / ((size_t)VOL_STRIDE * 4));
+        const unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
+        if (n_work > 0) {
+            rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
+            rc = grow(&c->tile_meta, &c->meta_cap, (size_t)round); if (rc) return rc;
+            size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, (size_t)round * 3072)));
+            size_t want_pts = std::max<size_t>(c->pt_cap, precision == SDFB200_PREC_EXACT ? want_cubes * 3 : want_cubes);
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                rc = grow(&c->cubes, &c->cube_cap, want_cubes); if (rc) return rc;
+                rc = grow(&c->pts, &c->pt_cap, want_pts); if (rc) return rc;
+                TileLists L;
+                L.vol = c->vol; L.tile_meta = c->tile_meta; L.cubes = c->cubes; L.pts = c->pts;
+                L.slot_cap = round; L.cube_cap = (unsigned int)std::min<size_t>(c->cube_cap, 0xffffffffu);
+                L.pt_cap = (unsigned int)std::min<size_t>(c->pt_cap, 0xffffffffu);
+                if (attempt > 0) {      // redo from a clean slate (the pre-pass results stay valid)
+                    const size_t nb = (size_t)g.nbx * g.nby * g.nbz;
+                    CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->tri_cursor, 0, 4 * sizeof(unsigned long long), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->max_cubes, 0, 2 * sizeof(unsigned int), stream));
+                }
+                for (unsigned long long wb = 0; wb < n_work; wb += round) {
+                    const unsigned int we = (unsigned int)std::min<unsigned long long>(n_work, wb + round);
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
+                    const unsigned int wbu = (unsigned int)wb;
+                    const int grid = (int)std::min<unsigned long long>(we - wb, (unsigned long long)c->sms);
+                    // ---- (A) evaluate + classify
+                    cudaError_t e;
+                    if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
+                        const bool f64 = precision == SDFB200_PREC_F64;
+                        const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
+                        JitEntry& je = prog->jit[JK_TILE0 + precision];
+                        if (!je.smem_set[device]) {
+                            CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
+                            je.smem_set[device] = true;
+                        }
+                        const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
+                        void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
+                        e = jit_launch(jk, dim3(grid), dim3(f64 ? 512 : 1024), smem, stream, args);
+                    } else if (precision == SDFB200_PREC_F32)
+                        e = launch_tile_eval<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                    else if (precision == SDFB200_PREC_MIXED)
+                        e = launch_tile_eval<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                    else if (precision == SDFB200_PREC_EXACT)
+                        e = launch_tile_eval<SDFB200_PREC_EXACT>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                    else
+                        e = launch_tile_eval<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                    if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile_eval_kernel launch failed: %s", cudaGetErrorString(e));
+                    // ---- (B) float64 refinement of the queued samples
+                    if (precision == SDFB200_PREC_MIXED || precision == SDFB200_PREC_EXACT) {
+                        const int rgrid = c->sms * 8;
+                        if (cudaKernel_t jk = jit_get(prog, JK_REFINE, big)) {
+                            Counters* ctrp = c->ctr;
+                            void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
+                            CUDA_TRY(jit_launch(jk, dim3(rgrid), dim3(128), 0, stream, args));
+                        } else {
+                            refine_points_kernel<kTS><<<rgrid, 128, 0, stream>>>(prog->img, g, L, c->ctr);
+                            CUDA_TRY(cudaGetLastError());
+                        }
+                    }
+                    // ---- (C) extraction
+                    extract_kernel<kTS><<<c->sms * 2, EXTRACT_THREADS, 0, stream>>>(g, L, c->ctr, c->batch_tris, dtri, cap);
+                    CUDA_TRY(cudaGetLastError());
+                }
+                CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                if (const char* dd = getenv("SDFB200_DEBUG_DUMP")) {
+                    auto dump = [&](const char* name, const void* dptr, size_t bytes) {
+                        std::vector<char> hb(bytes);
+                        cudaMemcpy(hb.data(), dptr, bytes, cudaMemcpyDeviceToHost);
+                        std::string fn = std::string(dd) + "/" + name;
+                        if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hb.data(), 1, bytes, f); fclose(f); }
+                    };
+                    dump("vol.bin", c->vol, (size_t)h.n_slots * VOL_STRIDE * 4);
+                    dump("meta.bin", c->tile_meta, (size_t)h.n_slots * 8);
+                    dump("cubes.bin", c->cubes, (size_t)std::min<unsigned>(h.n_cubes, L.cube_cap) * 8);
+                    dump("pts.bin", c->pts, (size_t)std::min<unsigned>(h.n_pts, L.pt_cap) * 8);
+                }
+                if (getenv("SDFB200_DEBUG"))
+                    fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu nan=%u\n",
+                            h.n_active, h.n_slots, h.n_cubes, h.n_pts, h.max_cubes, h.max_pts, L.cube_cap, L.pt_cap,
+                            h.tri_cursor, h.pts_f64, h.pad_[0]);
+                if (h.max_cubes <= L.cube_cap && h.max_pts <= L.pt_cap) break;
+                want_cubes = std::max<size_t>(want_cubes, (size_t)h.max_cubes + (h.max_cubes >> 3));
+                want_pts = std::max<size_t>(want_pts, (size_t)h.max_pts + (h.max_pts >> 3));
+                if (attempt == 2) return fail(SDFB200_E_CUDA, "work lists kept overflowing (%u cubes, %u samples)", h.max_cubes, h.max_pts);
             }
-            const unsigned int* act = c->active;
-            unsigned int* bt = c->batch_tris;
-            Counters* ctrp = c->ctr;
-            unsigned long long capv = cap;
-            float tauv = tau;
-            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&bt, (void*)&ctrp, (void*)&dtri, (void*)&capv};
-            e = jit_launch(jk, dim3(grid), dim3(FUSED_THREADS), smem, stream, args);
-        } else if (precision == SDFB200_PREC_F32)
-            e = launch_fused<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
-        else if (precision == SDFB200_PREC_MIXED)
-            e = launch_fused<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
-        else if (precision == SDFB200_PREC_EXACT)
-            e = launch_fused<SDFB200_PREC_EXACT>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
-        else
-            e = launch_fused<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, c->batch_tris, c->ctr, dtri, cap);
-        if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "fused_tile_kernel launch failed: %s", cudaGetErrorString(e));
+        }
         CUDA_TRY(cudaEventRecord(c->ev[2], stream));
         batch_stats_kernel<<<pb, 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
         CUDA_TRY(cudaGetLastError());
@@ -579,7 +685,6 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     }
     CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    const Counters& h = *c->ctr_host;
     *n_tri = (int64_t)h.tri_cursor;
     if (stats) {
         stats[0] = h.skipped; stats[1] = h.empty; stats[2] = h.nonempty;

@@ -72,7 +72,7 @@ def allgather_triangles(local, group=None):
 
 
 def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batch_size=core.BATCH_SIZE,
-                         sparse=True, precision='mixed', plan=None, gather='host', group=None,
+                         sparse=True, precision='exact', plan=None, gather='host', group=None,
                          compute=None, device=None):
     """SPMD entry: every rank calls this with the same arguments.
 
