@@ -5,8 +5,9 @@
 
 #if SDF_JIT_KERNEL == 0
 extern "C" __global__ void __launch_bounds__(128)
-jit_kernel(const GridDesc g, int sparse, unsigned char* flags, unsigned int* active_list, Counters* ctr) {
-    skip_prepass_body(SpecEval(), g, sparse, flags, active_list, ctr);
+jit_kernel(const GridDesc g, int sparse, unsigned char* flags, unsigned int* active_list, unsigned int* batch_tris,
+           Counters* ctr) {
+    skip_prepass_body(SpecEval(), g, sparse, flags, active_list, batch_tris, ctr);
 }
 #elif SDF_JIT_KERNEL >= 1 && SDF_JIT_KERNEL <= 4
 #define SDF_JIT_TILE_THREADS ((SDF_JIT_KERNEL - 1) == SDFB200_PREC_F64 ? 512 : 1024)

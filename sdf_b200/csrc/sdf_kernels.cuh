@@ -248,6 +248,7 @@ template <class EV>
 __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc& g, int sparse,
                                                   unsigned char* __restrict__ flags,
                                                   unsigned int* __restrict__ active_list,
+                                                  unsigned int* __restrict__ batch_tris,
                                                   Counters* __restrict__ ctr) {
     const int nzl = g.zb1 - g.zb0;
     const int total = g.nbx * g.nby * nzl;
@@ -280,6 +281,7 @@ __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc&
         }
     }
     flags[bid] = skipped ? 1 : 0;
+    batch_tris[bid] = 0u;
     if (!skipped) {
         const unsigned int slot = atomicAdd(&ctr->n_active, 1u);
         active_list[slot] = bid;
@@ -364,7 +366,7 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 template <int TS, int PREC, int THREADS, class EV>
 __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, const float tau,
                                                const unsigned int* __restrict__ active_list,
-                                               const unsigned int work_begin, const unsigned int work_end,
+                                               const unsigned int work_begin, const unsigned int work_end_arg,
                                                const TileLists L, Counters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool F64 = (PREC == SDFB200_PREC_F64);
@@ -374,6 +376,9 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
     S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
+    // work_end == ~0u: "every active batch" -- the count is read from the pre-pass's counter, so the
+    // host does not have to synchronise between the two kernels
+    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
     unsigned long long my_pts = 0;
 
     // Every barrier below is executed unconditionally by every thread in every iteration: the

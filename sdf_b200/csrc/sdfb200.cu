@@ -64,8 +64,8 @@ static int fail(int code, const char* fmt, ...) {
 
 __global__ void __launch_bounds__(128)
 skip_prepass_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, int sparse, unsigned char* flags,
-                    unsigned int* active_list, Counters* ctr) {
-    skip_prepass_body(InterpEval{&img}, g, sparse, flags, active_list, ctr);
+                    unsigned int* active_list, unsigned int* batch_tris, Counters* ctr) {
+    skip_prepass_body(InterpEval{&img}, g, sparse, flags, active_list, batch_tris, ctr);
 }
 
 #define INTERP_TILE_THREADS 512
@@ -114,7 +114,7 @@ struct DeviceCtx {
     int device = -1;
     int sms = 0;
     // workspace, grown on demand
-    double* axes = nullptr; size_t axes_cap = 0;
+    double* axes = nullptr; size_t axes_cap = 0; std::vector<double> axes_host;
     unsigned char* flags = nullptr; unsigned int* active = nullptr; unsigned int* batch_tris = nullptr; size_t nb_cap = 0;
     Counters* ctr = nullptr;
     Counters* ctr_host = nullptr;       // pinned
@@ -483,10 +483,26 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
         CUDA_TRY(cudaMalloc(&c->axes, need * sizeof(double)));
         c->axes_cap = need;
     }
-    const cudaMemcpyKind kind = cudaMemcpyDefault;
-    CUDA_TRY(cudaMemcpyAsync(c->axes, xs, nx * sizeof(double), kind, stream));
-    CUDA_TRY(cudaMemcpyAsync(c->axes + nx, ys, ny * sizeof(double), kind, stream));
-    CUDA_TRY(cudaMemcpyAsync(c->axes + nx + ny, zs, nz * sizeof(double), kind, stream));
+    // upload the axes unless they are the ones already resident (host copy kept for the comparison)
+    const bool host_axes = !is_device_ptr(xs) && !is_device_ptr(ys) && !is_device_ptr(zs);
+    bool same = host_axes && c->axes_host.size() == need;
+    if (same) same = memcmp(c->axes_host.data(), xs, nx * 8) == 0 && memcmp(c->axes_host.data() + nx, ys, ny * 8) == 0 &&
+                     memcmp(c->axes_host.data() + nx + ny, zs, nz * 8) == 0;
+    if (!same) {
+        if (host_axes) {
+            c->axes_host.resize(need);
+            memcpy(c->axes_host.data(), xs, nx * 8);
+            memcpy(c->axes_host.data() + nx, ys, ny * 8);
+            memcpy(c->axes_host.data() + nx + ny, zs, nz * 8);
+            CUDA_TRY(cudaMemcpyAsync(c->axes, c->axes_host.data(), need * sizeof(double), cudaMemcpyHostToDevice, stream));
+        } else {
+            c->axes_host.clear();
+            const cudaMemcpyKind kind = cudaMemcpyDefault;
+            CUDA_TRY(cudaMemcpyAsync(c->axes, xs, nx * sizeof(double), kind, stream));
+            CUDA_TRY(cudaMemcpyAsync(c->axes + nx, ys, ny * sizeof(double), kind, stream));
+            CUDA_TRY(cudaMemcpyAsync(c->axes + nx + ny, zs, nz * sizeof(double), kind, stream));
+        }
+    }
     g->xs = c->axes; g->ys = c->axes + nx; g->zs = c->axes + nx + ny;
     g->nx = (int)nx; g->ny = (int)ny; g->nz = (int)nz;
     g->bs = batch_size;
@@ -508,9 +524,7 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
         CUDA_TRY(cudaMalloc(&c->batch_tris, nb * sizeof(unsigned int)));
         c->nb_cap = nb;
     }
-    CUDA_TRY(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), stream));
-    CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
-    CUDA_TRY(cudaMemsetAsync(c->flags, 0, nb, stream));
+    CUDA_TRY(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), stream));     // flags / batch_tris: written by the pre-pass
     return 0;
 }
 
@@ -576,24 +590,32 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
         const int pb = (int)((total_b + 127) / 128);
         // ---- skip pre-pass
         if (cudaKernel_t jk = jit_get(prog, JK_SKIP, big)) {
-            unsigned char* fl = c->flags; unsigned int* act = c->active; Counters* ctrp = c->ctr;
-            void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&ctrp};
+            unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;
+            void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&bt, (void*)&ctrp};
             CUDA_TRY(jit_launch(jk, dim3(pb), dim3(128), 0, stream, args));
         } else {
-            skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->ctr);
+            skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->batch_tris, c->ctr);
             CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(c->ev[1], stream));
-        // the number of active batches sizes the work lists
-        CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        const unsigned long long n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
+        // Work-list sizing.  When one tile volume per batch of the range fits the budget, the kernels
+        // read the number of active batches from the pre-pass's counter themselves and the host never
+        // synchronises in the middle; otherwise the host reads it and runs rounds of `max_round` tiles.
         const unsigned long long max_round = std::max<unsigned long long>(1ull, kVolBudgetBytes / ((size_t)VOL_STRIDE * 4));
+        const unsigned long long upper = (unsigned long long)total_b * g.sub * g.sub * g.sub;
+        const bool sync_free = upper <= max_round;
+        unsigned long long n_work = upper;
+        if (!sync_free) {
+            CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
+        }
         const unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
         if (n_work > 0) {
             rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
             rc = grow(&c->tile_meta, &c->meta_cap, (size_t)round); if (rc) return rc;
-            size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, (size_t)round * 3072)));
+            const size_t est_tiles = sync_free ? std::max<size_t>(256, round / 4) : round;     // most batches are skipped / empty
+            size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, est_tiles * 3072)));
             size_t want_pts = std::max<size_t>(c->pt_cap, precision == SDFB200_PREC_EXACT ? want_cubes * 3 : want_cubes);
             for (int attempt = 0; attempt < 3; ++attempt) {
                 rc = grow(&c->cubes, &c->cube_cap, want_cubes); if (rc) return rc;
@@ -609,11 +631,13 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->max_cubes, 0, 2 * sizeof(unsigned int), stream));
                 }
                 for (unsigned long long wb = 0; wb < n_work; wb += round) {
-                    const unsigned int we = (unsigned int)std::min<unsigned long long>(n_work, wb + round);
-                    CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
-                    CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
+                    const unsigned int we = sync_free ? 0xffffffffu : (unsigned int)std::min<unsigned long long>(n_work, wb + round);
+                    if (wb > 0 || attempt > 0) {        // (the first round starts from the zeroed counters)
+                        CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
+                        CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
+                    }
                     const unsigned int wbu = (unsigned int)wb;
-                    const int grid = (int)std::min<unsigned long long>(we - wb, (unsigned long long)c->sms);
+                    const int grid = (int)std::min<unsigned long long>(std::min<unsigned long long>(n_work, wb + round) - wb, (unsigned long long)c->sms);
                     // ---- (A) evaluate + classify
                     cudaError_t e;
                     if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
@@ -728,7 +752,7 @@ extern "C" int sdfb200_skip_flags(sdfb200_prog* prog, const double* xs, int64_t 
     rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, 0, -1, &g); if (rc) return rc;
     const long long total_b = (long long)g.nbx * g.nby * g.nbz;
     const int pb = (int)((total_b + 127) / 128);
-    skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, 1, c->flags, c->active, c->ctr);
+    skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, 1, c->flags, c->active, c->batch_tris, c->ctr);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(flags, c->flags, (size_t)total_b, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
