@@ -213,6 +213,174 @@ _PRIMS = {
 }
 
 
+# ---- 2-D primitives (p is (N,2))                                        sdf/d2.py
+
+def _q_circle(c, p):                        # d2.py:78-79
+    return _length(p - np.array(c[0:2])) - c[2]
+
+
+def _q_line(c, p):                          # d2.py:85-86
+    return np.dot(np.array(c[2:4]) - p, np.array(c[0:2]))
+
+
+def _q_rectangle(c, p):                     # d2.py:111-113 (c[2:4] is size / 2)
+    q = np.abs(p - np.array(c[0:2])) - np.array(c[2:4])
+    return _length(_max(q, 0)) + _min(np.amax(q, axis=1), 0)
+
+
+def _q_rounded_rectangle(c, p):             # d2.py:122-134 (c[0:2] is size / 2)
+    half, (r0, r1, r2, r3) = np.array(c[0:2]), c[2:6]
+    x = p[:, 0]
+    y = p[:, 1]
+    r = np.zeros(len(p)).reshape((-1, 1))
+    r[np.logical_and(x > 0, y > 0)] = r0
+    r[np.logical_and(x > 0, y <= 0)] = r1
+    r[np.logical_and(x <= 0, y <= 0)] = r2
+    r[np.logical_and(x <= 0, y > 0)] = r3
+    q = np.abs(p) - half + r
+    return (_min(_max(q[:, 0], q[:, 1]), 0).reshape((-1, 1)) + _length(_max(q, 0)).reshape((-1, 1)) - r)
+
+
+def _q_equilateral_triangle(c, p):          # d2.py:139-152
+    k = 3 ** 0.5
+    p = _vec(np.abs(p[:, 0]) - 1, p[:, 1] + 1 / k)
+    w = p[:, 0] + k * p[:, 1] > 0
+    q = _vec(p[:, 0] - k * p[:, 1], -k * p[:, 0] - p[:, 1]) / 2
+    p = np.where(w.reshape((-1, 1)), q, p)
+    p = _vec(p[:, 0] - np.clip(p[:, 0], -2, 0), p[:, 1])
+    return -_length(p) * np.sign(p[:, 1])
+
+
+def _q_hexagon(c, p):                       # d2.py:157-166 (c[0] already scaled by sqrt(3)/2)
+    r = c[0]
+    k = np.array((3 ** 0.5 / -2, 0.5, np.tan(np.pi / 6)))
+    p = np.abs(p)
+    p -= 2 * k[:2] * _min(_dot(k[:2], p), 0).reshape((-1, 1))
+    p -= _vec(np.clip(p[:, 0], -k[2] * r, k[2] * r), np.zeros(len(p)) + r)
+    return _length(p) * np.sign(p[:, 1])
+
+
+def _q_rounded_x(c, p):                     # d2.py:171-174
+    w, r = c
+    p = np.abs(p)
+    q = (_min(p[:, 0] + p[:, 1], w) * 0.5).reshape((-1, 1))
+    return _length(p - q) - r
+
+
+def _q_polygon(c, p):                       # d2.py:180-197
+    points = [np.array(c[2 * i:2 * i + 2]) for i in range(len(c) // 2)]
+    n = len(points)
+    d = _dot(p - points[0], p - points[0])
+    s = np.ones(len(p))
+    for i in range(n):
+        j = (i + n - 1) % n
+        vi = points[i]
+        vj = points[j]
+        e = vj - vi
+        w = p - vi
+        b = w - e * np.clip(np.dot(w, e) / np.dot(e, e), 0, 1).reshape((-1, 1))
+        d = _min(d, _dot(b, b))
+        c1 = p[:, 1] >= vi[1]
+        c2 = p[:, 1] < vj[1]
+        c3 = e[0] * w[:, 1] > e[1] * w[:, 0]
+        cc = _vec(c1, c2, c3)
+        s = np.where(np.all(cc, axis=1) | np.all(~cc, axis=1), -s, s)
+    return s * np.sqrt(d)
+
+
+def _q_vesica(c, p):                        # d2.py:202-208
+    r, d = c
+    p = np.abs(p)
+    b = np.sqrt(r * r - d * d)
+    return np.where(((p[:, 1] - b) * d > p[:, 0] * b), _length(p - np.array([0, b])),
+                    _length(p - np.array([-d, 0])) - r)
+
+
+_PRIMS2 = {'CIRCLE': _q_circle, 'LINE2': _q_line, 'RECTANGLE': _q_rectangle,
+           'ROUNDED_RECTANGLE': _q_rounded_rectangle, 'EQUILATERAL_TRIANGLE': _q_equilateral_triangle,
+           'HEXAGON': _q_hexagon, 'ROUNDED_X': _q_rounded_x, 'POLYGON': _q_polygon, 'VESICA': _q_vesica}
+
+
+# ---- easing functions, by opcode operand                                sdf/ease.py:3-162
+
+def _out_bounce(t):
+    a = (121 * t * t) / 16
+    b = (363 / 40 * t * t) - (99 / 10 * t) + 17 / 5
+    c = (4356 / 361 * t * t) - (35442 / 1805 * t) + 16061 / 1805
+    d = (54 / 5 * t * t) - (513 / 25 * t) + 268 / 25
+    return np.where(t < 4 / 11, a, np.where(t < 8 / 11, b, np.where(t < 9 / 10, c, d)))
+
+
+def _in_bounce(t):
+    return 1 - _out_bounce(1 - t)
+
+
+def _w(cond, a, b):
+    with np.errstate(all='ignore'):
+        return np.where(cond, a, b)
+
+
+_EASE = [
+    lambda t: t,
+    lambda t: t * t,
+    lambda t: -t * (t - 2),
+    lambda t: _w(t < 0.5, 2 * t * t, -0.5 * ((2 * t - 1) * ((2 * t - 1) - 2) - 1)),
+    lambda t: t * t * t,
+    lambda t: (t - 1) * (t - 1) * (t - 1) + 1,
+    lambda t: _w(t * 2 < 1, 0.5 * (t * 2) * (t * 2) * (t * 2), 0.5 * ((t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) + 2)),
+    lambda t: t * t * t * t,
+    lambda t: -((t - 1) * (t - 1) * (t - 1) * (t - 1) - 1),
+    lambda t: _w(t * 2 < 1, 0.5 * (t * 2) * (t * 2) * (t * 2) * (t * 2),
+                 -0.5 * ((t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) - 2)),
+    lambda t: t * t * t * t * t,
+    lambda t: (t - 1) * (t - 1) * (t - 1) * (t - 1) * (t - 1) + 1,
+    lambda t: _w(t * 2 < 1, 0.5 * (t * 2) * (t * 2) * (t * 2) * (t * 2) * (t * 2),
+                 0.5 * ((t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) * (t * 2 - 2) + 2)),
+    lambda t: -np.cos(t * np.pi / 2) + 1,
+    lambda t: np.sin(t * np.pi / 2),
+    lambda t: -0.5 * (np.cos(np.pi * t) - 1),
+    lambda t: _w(t == 0, np.zeros(len(t)), 2 ** (10 * (t - 1))),
+    lambda t: _w(t == 1, np.zeros(len(t)) + 1, 1 - 2 ** (-10 * t)),
+    lambda t: _w(t == 0, np.zeros(len(t)), _w(t == 1, np.zeros(len(t)) + 1,
+                 _w(t < 0.5, 0.5 * 2 ** (20 * t - 10), 1 - 0.5 * 2 ** (-20 * t + 10)))),
+    lambda t: -1 * (np.sqrt(1 - t * t) - 1),
+    lambda t: np.sqrt(1 - (t - 1) * (t - 1)),
+    lambda t: _w(t * 2 < 1, -0.5 * (_sqrt_q(1 - (t * 2) * (t * 2)) - 1), 0.5 * (_sqrt_q(1 - (t * 2 - 2) * (t * 2 - 2)) + 1)),
+    lambda t: -1 * (2 ** (10 * (t - 1)) * np.sin(((t - 1) - 0.5 / 4) * (2 * np.pi) / 0.5)),
+    lambda t: 2 ** (-10 * t) * np.sin((t - 0.5 / 4) * (2 * np.pi / 0.5)) + 1,
+    lambda t: _w(t * 2 < 1, -0.5 * (2 ** (10 * (t * 2 - 1)) * np.sin(((t * 2 - 1) - 0.5 / 4) * 2 * np.pi / 0.5)),
+                 2 ** (-10 * (t * 2 - 1)) * np.sin(((t * 2 - 1) - 0.5 / 4) * 2 * np.pi / 0.5) * 0.5 + 1),
+    lambda t: t * t * ((1.70158 + 1) * t - 1.70158),
+    lambda t: (t - 1) * (t - 1) * ((1.70158 + 1) * (t - 1) + 1.70158) + 1,
+    lambda t: _w(t * 2 < 1, 0.5 * ((t * 2) * (t * 2) * ((1.70158 * 1.525 + 1) * (t * 2) - 1.70158 * 1.525)),
+                 0.5 * ((t * 2 - 2) * (t * 2 - 2) * ((1.70158 * 1.525 + 1) * (t * 2 - 2) + 1.70158 * 1.525) + 2)),
+    _in_bounce,
+    _out_bounce,
+    lambda t: _w(t < 0.5, _in_bounce(2 * t) * 0.5, _out_bounce(2 * t - 1) * 0.5 + 0.5),
+    lambda t: _w(t < 1, np.zeros(len(t)), np.zeros(len(t)) + 1),
+    lambda t: _w(t > 0, np.zeros(len(t)) + 1, np.zeros(len(t))),
+    lambda t: _w(t < 0.5, np.zeros(len(t)), np.zeros(len(t)) + 1),
+]
+
+
+def _sqrt_q(v):
+    with np.errstate(invalid='ignore'):
+        return np.sqrt(v)
+
+
+def _tparam(tp, p):
+    name, c = tp
+    if name == 'TPARAM_LINEAR':             # d3.py:442 / 464
+        p0, ab = np.array(c[0:3]), np.array(c[3:6])
+        return np.clip(np.dot(p - p0, ab) / np.dot(ab, ab), 0, 1)
+    if name == 'TPARAM_RADIAL':             # d3.py:453-454 / 476-477
+        r = np.hypot(p[:, 0], p[:, 1])
+        return np.clip((r - c[0]) / (c[1] - c[0]), 0, 1)
+    if name == 'TPARAM_Z':                  # d2.py:273
+        return np.clip(p[:, 2] / c[0], -0.5, 0.5) + 0.5
+    raise KeyError(name)
+
+
 def _fold(name, K, d1, d2):
     if name == 'union':                     # dn.py:13-18
         if K is None:
@@ -242,6 +410,10 @@ def evaluate(obj, p):
     kind, c = n.kind, n.consts
     if kind == 'opaque':
         return obj.f(p).reshape((-1, 1))
+    if kind == 'prim' and n.op in _PRIMS2:
+        return _PRIMS2[n.op](c, p[:, :2]).reshape((-1, 1))
+    if kind == 'polygon':
+        return _q_polygon(c, p[:, :2]).reshape((-1, 1))
     if kind == 'prim':
         return _PRIMS[n.op](c, p).reshape((-1, 1))
     child = n.children[0] if n.children else None
@@ -250,6 +422,9 @@ def evaluate(obj, p):
             return evaluate(child, p - np.array(c))
         if n.op == 'ROTATE':                # d3.py:358-359
             return evaluate(child, np.dot(p, np.array(c).reshape(3, 3)))
+        if n.op == 'REVOLVE':               # d2.py:282-285 (2-D child sees (|xy| - offset, z))
+            q = _vec(_length(p[:, [0, 1]]) - c[0], p[:, 2])
+            return evaluate(child, np.concatenate([q, np.zeros((len(p), 1))], axis=1))
         if n.op in ('TWIST', 'BEND'):       # d3.py:409-418, 423-432
             x, y, z = p[:, 0], p[:, 1], p[:, 2]
             arg = c[0] * (z if n.op == 'TWIST' else x)
@@ -266,6 +441,48 @@ def evaluate(obj, p):
         z = q[:, 2].reshape((-1, 1))
         w = _min(_max(x, _max(y, z)), 0)
         return evaluate(child, _max(q, 0)) + w
+    if kind == 'extrude':                   # d2.py:263-265
+        d = evaluate(child, p)
+        w = _vec(d.reshape(-1), np.abs(p[:, 2]) - c[0] / 2)
+        return (_min(_max(w[:, 0], w[:, 1]), 0) + _length(_max(w, 0))).reshape((-1, 1))
+    if kind == 'warp':
+        if n.op in ('BEND_LINEAR', 'BEND_RADIAL'):      # d3.py:441-444, 449-456
+            (tp, _, tc), (_, eid, _), (_, _, v) = n.extra
+            t = _EASE[eid](_tparam((tp, tc), p)).reshape((-1, 1))
+            if n.op == 'BEND_LINEAR':
+                return evaluate(child, p + t * np.array(v))
+            x, y, z = p[:, 0], p[:, 1], p[:, 2]
+            return evaluate(child, _vec(x, y, z - (-v[2]) * t.reshape(-1)))
+        if n.op == 'WRAP_AROUND':                       # d3.py:490-501
+            (_, _, (r,)), (_, eid, _), (_, _, (x0, x1)) = n.extra
+            p0 = np.array((1, 0, 0)) * x0
+            p1 = np.array((1, 0, 0)) * x1
+            v = -np.array((0, 1, 0))
+            x, y, z = p[:, 0], p[:, 1], p[:, 2]
+            d = (np.hypot(x, y) - r).reshape((-1, 1))
+            a = np.arctan2(y, x)
+            t = _EASE[eid]((a + np.pi) / (2 * np.pi)).reshape((-1, 1))
+            q = p0 + (p1 - p0) * t + v * d
+            q[:, 2] = z
+            return evaluate(child, q)
+        raise KeyError(n.op)
+    if kind == 'transition':
+        tp, eid, mix, tail = n.extra
+        d1 = evaluate(n.children[0], p)
+        d2 = evaluate(n.children[1], p)
+        t = _EASE[eid](_tparam(tp, p)).reshape((-1, 1))
+        if mix == 'LERP_POP2':                          # d3.py:466, 479
+            return t * d2 + (1 - t) * d1
+        d = d1 + (d2 - d1) * t                          # d2.py:274-277 (extrude_to)
+        w = _vec(d.reshape(-1), np.abs(p[:, 2]) - tail[0] / 2)
+        return (_min(_max(w[:, 0], w[:, 1]), 0) + _length(_max(w, 0))).reshape((-1, 1))
+    if kind == 'slice':                     # d3.py:513-519
+        q = _vec(p[:, 0], p[:, 1], np.zeros(len(p)))
+        A = evaluate(n.children[0], q).reshape(-1)
+        B = -evaluate(n.children[1], q).reshape(-1)
+        w = A <= 0
+        A[w] = B[w]
+        return A.reshape((-1, 1))
     if kind == 'circular':                  # d3.py:381-391
         da, offset = c
         shifted = lambda q: evaluate(child, q - np.array((1, 0, 0)) * offset)

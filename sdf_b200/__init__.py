@@ -3,7 +3,7 @@
 Star-exports the same public names as the reference package (sdf/__init__.py:1-27):
 3-D names win over 2-D names of the same spelling, as there.
 """
-from . import d2, d3
+from . import d2, d3, ease
 
 from .util import *            # noqa: F401,F403
 

@@ -342,8 +342,10 @@ struct TileSmem {
     static constexpr int TP = TS + 1;
     static constexpr int NPTS = TP * TP * TP;
     float tile[(NPTS + 3) & ~3];
-    unsigned int bits[(NPTS + 31) / 32];            // samples already queued for float64
-    unsigned int cand[(TS * TS * TS + 31) / 32];    // candidate cubes, one bit per cube (tile-local id)
+    unsigned long long posm[TP * TP];               // per z-line: bit j <=> sample j of the line is > 0
+    unsigned long long uncm[TP * TP];               //             bit j <=> |sample j| < tau (sign not trusted)
+    unsigned long long refm[TP * TP];               //             bit j <=> sample j is queued for float64
+    unsigned int cand[TS * TS];                     // per (cx, cy): bit cz <=> cube (cx, cy, cz) is a candidate
     float axf[3][TP];
     double axd[F64 ? 3 : 1][F64 ? TP : 1];
     int minmax[2];
@@ -408,7 +410,6 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
         for (int i = tid; i < px; i += THREADS) { const double v = g.xs[t.bx0 + t.ox + i]; sm.axf[0][i] = (float)v; if (F64) sm.axd[0][F64 ? i : 0] = v; }
         for (int i = tid; i < py; i += THREADS) { const double v = g.ys[t.by0 + t.oy + i]; sm.axf[1][i] = (float)v; if (F64) sm.axd[F64 ? 1 : 0][F64 ? i : 0] = v; }
         for (int i = tid; i < pz; i += THREADS) { const double v = g.zs[t.bz0 + t.oz + i]; sm.axf[2][i] = (float)v; if (F64) sm.axd[F64 ? 2 : 0][F64 ? i : 0] = v; }
-        if (REFINE) { for (int i = tid; i < (S::NPTS + 31) / 32; i += THREADS) sm.bits[i] = 0u; }
         __syncthreads();
 
         // ---------------------------------------------------------------- evaluation
@@ -473,57 +474,54 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
         live = live && (slot < L.slot_cap);                   // always true: one slot per work item
 
         // ------------------------------------------------------------ classification
-        const int cyn = py - 1, czn = pz - 1;
-        const int ncubes = (px - 1) * cyn * czn;
-        const unsigned int cyz = (unsigned int)(cyn * czn);
-        FastDiv dcyz, dcz;
-        dcyz.init(cyz > 0u ? cyz : 1u); dcz.init(czn > 0 ? (unsigned int)czn : 1u);
-        const int ncubes_up = live ? (ncubes + THREADS - 1) / THREADS * THREADS : 0;
-        for (int c = tid; c < ncubes_up; c += THREADS) {
-            bool cand = false;
-            unsigned int want = 0;                            // corners to queue for float64 (bit k)
-            int base_idx = 0;
-            if (c < ncubes) {
-                const unsigned int cx = dcyz.div(c), rem = c - cx * cyz, cy = dcz.div(rem), cz = rem - cy * czn;
-                base_idx = (int)((cx * py + cy) * pz + cz);
-                const float* p = &sm.tile[base_idx];
-                // Lewiner corner k -> (x_L, y_L, z_L) = (array axis 2, axis 1, axis 0)
-                const float v0 = p[0], v1 = p[1], v2 = p[pz + 1], v3 = p[pz], v4 = p[pyz], v5 = p[pyz + 1],
-                            v6 = p[pyz + pz + 1], v7 = p[pyz + pz];
-                unsigned int pos = 0, unc = 0;
-                pos |= (v0 > 0.0f) ? 1u : 0u;  pos |= (v1 > 0.0f) ? 2u : 0u;  pos |= (v2 > 0.0f) ? 4u : 0u;  pos |= (v3 > 0.0f) ? 8u : 0u;
-                pos |= (v4 > 0.0f) ? 16u : 0u; pos |= (v5 > 0.0f) ? 32u : 0u; pos |= (v6 > 0.0f) ? 64u : 0u; pos |= (v7 > 0.0f) ? 128u : 0u;
+        // (1) one thread per z-line: sign / uncertainty bit masks of the line's <= 33 samples
+        const int nlines = live ? px * py : 0;
+        for (int ln = tid; ln < nlines; ln += THREADS) {
+            const float* p = &sm.tile[ln * pz];
+            unsigned long long pm = 0ull, um = 0ull;
+            for (int j = 0; j < pz; ++j) {
+                const float v = p[j];
+                pm |= (unsigned long long)(v > 0.0f ? 1u : 0u) << j;
+                if (REFINE) um |= (unsigned long long)(fabsf(v) < tau ? 1u : 0u) << j;
+            }
+            sm.posm[ln] = pm; sm.uncm[ln] = um; sm.refm[ln] = um;
+        }
+        __syncthreads();
+        // (2) one thread per (cx, cy) column of cubes: 32 cubes classified with a few word operations.
+        //     cube (cx,cy,cz) is a candidate when its corners are not all > 0, not all <= 0, or one of
+        //     them is uncertain; PREC_EXACT queues every corner of a candidate for float64.
+        const int cxn = px - 1, cyn = py - 1, czn = pz - 1;
+        for (int col = tid; col < TS * TS; col += THREADS) {
+            const int cx = col >> 5, cy = col & 31;          // TS == 32
+            unsigned int W = 0u;
+            if (live && cx < cxn && cy < cyn) {
+                const int l00 = cx * py + cy, l01 = l00 + 1, l10 = l00 + py, l11 = l10 + 1;
+                const unsigned long long p0 = sm.posm[l00], p1 = sm.posm[l01], p2 = sm.posm[l10], p3 = sm.posm[l11];
+                const unsigned long long allp = (p0 & (p0 >> 1)) & (p1 & (p1 >> 1)) & (p2 & (p2 >> 1)) & (p3 & (p3 >> 1));
+                const unsigned long long anyp = (p0 | (p0 >> 1)) | (p1 | (p1 >> 1)) | (p2 | (p2 >> 1)) | (p3 | (p3 >> 1));
+                unsigned long long c64 = anyp & ~allp;
                 if (REFINE) {
-                    unc |= (fabsf(v0) < tau) ? 1u : 0u;  unc |= (fabsf(v1) < tau) ? 2u : 0u;  unc |= (fabsf(v2) < tau) ? 4u : 0u;  unc |= (fabsf(v3) < tau) ? 8u : 0u;
-                    unc |= (fabsf(v4) < tau) ? 16u : 0u; unc |= (fabsf(v5) < tau) ? 32u : 0u; unc |= (fabsf(v6) < tau) ? 64u : 0u; unc |= (fabsf(v7) < tau) ? 128u : 0u;
+                    const unsigned long long u0 = sm.uncm[l00], u1 = sm.uncm[l01], u2 = sm.uncm[l10], u3 = sm.uncm[l11];
+                    c64 |= (u0 | (u0 >> 1)) | (u1 | (u1 >> 1)) | (u2 | (u2 >> 1)) | (u3 | (u3 >> 1));
                 }
-                cand = (unc != 0u) || (pos != 0u && pos != 255u);
-                want = EXACT ? (cand ? 255u : 0u) : unc;
-            }
-            // the 32 lanes of a warp hold 32 consecutive cubes: the ballot IS the candidate word
-            const unsigned int m = __ballot_sync(0xffffffffu, cand);
-            if (lane == 0) sm.cand[c >> 5] = m;
-            if (REFINE && m) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if ((want >> k) & 1u) {
-                        const int idx = base_idx + corner_z(k) * (int)pyz + corner_y(k) * pz + corner_x(k);
-                        const unsigned int bit = 1u << (idx & 31);
-                        if (!(sm.bits[idx >> 5] & bit)) atomicOr(&sm.bits[idx >> 5], bit);
-                    }
+                W = (unsigned int)c64 & (czn >= 32 ? 0xffffffffu : ((1u << czn) - 1u));
+                if (EXACT && W) {
+                    const unsigned long long zm = (unsigned long long)W | ((unsigned long long)W << 1);
+                    atomicOr(&sm.refm[l00], zm); atomicOr(&sm.refm[l01], zm);
+                    atomicOr(&sm.refm[l10], zm); atomicOr(&sm.refm[l11], zm);
                 }
             }
+            sm.cand[col] = W;
         }
         __syncthreads();
         // ---------------------------------------------- compaction of the two bitmaps
         // one prefix sum over the per-thread popcounts (cubes in the low, samples in the high half
         // word), ONE pair of global atomics per tile, then every thread writes its own entries
         {
-            const int nwc = live ? (ncubes + 31) >> 5 : 0;
-            const int nwp = (live && REFINE) ? (npts + 31) >> 5 : 0;
+            const int nwp = (live && REFINE) ? nlines : 0;
             unsigned int cnt = 0;
-            for (int wi = tid; wi < nwc; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
-            for (int wi = tid; wi < nwp; wi += THREADS) cnt += ((unsigned)__popc(sm.bits[wi])) << 16;
+            for (int wi = tid; wi < TS * TS; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
+            for (int wi = tid; wi < nwp; wi += THREADS) cnt += ((unsigned)__popcll(sm.refm[wi])) << 16;
             unsigned int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -548,21 +546,22 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
             const unsigned int excl = warp_off + incl - cnt;
             unsigned int cat = sm.cube_gbase + (excl & 0xffffu);
             unsigned int pat = sm.pt_gbase + (excl >> 16);
-            for (int wi = tid; wi < nwc; wi += THREADS) {
+            for (int wi = tid; wi < TS * TS; wi += THREADS) {
                 unsigned int word = sm.cand[wi];
                 while (word) {
                     const int bpos = __ffs(word) - 1;
                     word &= word - 1u;
-                    if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)(wi * 32 + bpos));
+                    // cube id with fixed strides: cx << 10 | cy << 5 | cz
+                    if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)((wi << 5) | bpos));
                     ++cat;
                 }
             }
             for (int wi = tid; wi < nwp; wi += THREADS) {
-                unsigned int word = sm.bits[wi];
+                unsigned long long word = sm.refm[wi];
                 while (word) {
-                    const int bpos = __ffs(word) - 1;
-                    word &= word - 1u;
-                    if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)(wi * 32 + bpos));
+                    const int bpos = __ffsll((long long)word) - 1;
+                    word &= word - 1ull;
+                    if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)(wi * pz + bpos));
                     ++pat;
                 }
             }
@@ -609,6 +608,9 @@ __device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc&
 // (tables in shared memory), a CTA prefix sum reserves the output range with one global atomic,
 // every thread then writes its cube's triangles (world-mapped, core.py:58-60).
 #define EXTRACT_THREADS 256
+#ifndef EXTRACT_BLOCKS_PER_SM
+#define EXTRACT_BLOCKS_PER_SM 3      // register cap 85/thread: the fp64 divides are latency bound, occupancy wins
+#endif
 
 struct ExtractSmem {
     McTablesSmem mc;
@@ -640,9 +642,8 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             e = L.cubes[i];
             meta = L.tile_meta[e.x];
             tile_geom<TS>(g, meta.x, (int)meta.y, t);
-            const int czn = t.pz - 1, cyz = (t.py - 1) * czn;
             const int pz = t.pz, pyz = t.py * t.pz;
-            cx = (int)e.y / cyz; const int rem = (int)e.y - cx * cyz; cy = rem / czn; cz = rem - cy * czn;
+            cx = (int)(e.y >> 10); cy = (int)((e.y >> 5) & 31u); cz = (int)(e.y & 31u);
             const float* p = L.vol + (size_t)e.x * VOL_STRIDE + (size_t)((cx * t.py + cy) * pz + cz);
             v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
             v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];

@@ -56,6 +56,7 @@ template <bool FAST> struct MathP<double, FAST> {
     static __device__ __forceinline__ T atan2_(T y, T x) { return atan2(y, x); }
     static __device__ __forceinline__ T hypot_(T x, T y) { return hypot(x, y); }
     static __device__ __forceinline__ T rint_(T a) { return rint(a); }
+    static __device__ __forceinline__ T exp2_(T a) { return exp2(a); }
     // numpy's floored modulo (np.mod / %): fmod, then shift into the divisor's sign
     static __device__ __forceinline__ T pymod(T a, T b) {
         T m = fmod(a, b);
@@ -76,6 +77,7 @@ template <> struct MathP<float, false> {
     static __device__ __forceinline__ T atan2_(T y, T x) { return atan2f(y, x); }
     static __device__ __forceinline__ T hypot_(T x, T y) { return sqrtf(x * x + y * y); }
     static __device__ __forceinline__ T rint_(T a) { return rintf(a); }
+    static __device__ __forceinline__ T exp2_(T a) { return exp2f(a); }
     static __device__ __forceinline__ T pymod(T a, T b) {
         T m = fmodf(a, b);
         if (m != T(0)) { if ((b < T(0)) != (m < T(0))) m += b; }
@@ -123,6 +125,7 @@ template <> struct MathP<float, true> {
     }
     static __device__ __forceinline__ T hypot_(T x, T y) { return sqrt_(x * x + y * y); }
     static __device__ __forceinline__ T rint_(T a) { return rintf(a); }
+    static __device__ __forceinline__ T exp2_(T a) { return exp2f(a); }
     static __device__ __forceinline__ T pymod(T a, T b) {
         const T m = fmaf(-floorf(__fdividef(a, b)), b, a);
         return m;
@@ -575,6 +578,238 @@ struct SdfOps {
         if (a == 0) { SDF_FOR_N { x[i] = r0x[i]; y[i] = r0y[i]; z[i] = r0z[i]; } }
         else { SDF_FOR_N { x[i] = ps[a][0][i]; y[i] = ps[a][1][i]; z[i] = ps[a][2][i]; } }
         }
+
+    // ------------------------------------------------------------------ 2-D primitives (P.xy)
+    static __device__ __forceinline__ void CIRCLE(State& st, const T* c, const int a) {   // d2.py:78-79
+        SDF_BIND_STATE;
+        const T cx = c[0], cy = c[1], r = c[2];
+        SDF_FOR_N d[i] = m_len2(x[i] - cx, y[i] - cy) - r;
+    }
+    static __device__ __forceinline__ void LINE2(State& st, const T* c, const int a) {    // d2.py:85-86
+        SDF_BIND_STATE;
+        const T nx = c[0], ny = c[1], px = c[2], py = c[3];
+        SDF_FOR_N d[i] = (px - x[i]) * nx + (py - y[i]) * ny;
+    }
+    static __device__ __forceinline__ void RECTANGLE(State& st, const T* c, const int a) {    // d2.py:111-113
+        SDF_BIND_STATE;
+        const T cx = c[0], cy = c[1], hx = c[2], hy = c[3];
+        SDF_FOR_N {
+            const T qx = m_abs(x[i] - cx) - hx, qy = m_abs(y[i] - cy) - hy;
+            d[i] = m_len2(m_max(qx, T(0)), m_max(qy, T(0))) + m_min(m_max(qx, qy), T(0));
+        }
+    }
+    static __device__ __forceinline__ void ROUNDED_RECTANGLE(State& st, const T* c, const int a) {    // d2.py:122-134
+        SDF_BIND_STATE;
+        const T hx = c[0], hy = c[1], r0 = c[2], r1 = c[3], r2 = c[4], r3 = c[5];
+        SDF_FOR_N {
+            const bool xp = x[i] > T(0), yp = y[i] > T(0);
+            const T r = xp ? (yp ? r0 : r1) : (yp ? r3 : r2);
+            const T qx = m_abs(x[i]) - hx + r, qy = m_abs(y[i]) - hy + r;
+            d[i] = m_min(m_max(qx, qy), T(0)) + m_len2(m_max(qx, T(0)), m_max(qy, T(0))) - r;
+        }
+    }
+    static __device__ __forceinline__ void EQUILATERAL_TRIANGLE(State& st, const T* c, const int a) {   // d2.py:139-152
+        SDF_BIND_STATE;
+        const T k = m_sqrt(T(3));
+        SDF_FOR_N {
+            T px = m_abs(x[i]) - T(1), py = y[i] + m_div(T(1), k);
+            if (px + k * py > T(0)) {
+                const T qx = m_div(px - k * py, T(2)), qy = m_div(-k * px - py, T(2));
+                px = qx; py = qy;
+            }
+            px = px - m_min(m_max(px, T(-2)), T(0));
+            d[i] = -m_len2(px, py) * m_sign(py);
+        }
+    }
+    static __device__ __forceinline__ void HEXAGON(State& st, const T* c, const int a) {   // d2.py:157-166
+        SDF_BIND_STATE;
+        const T r = c[0];
+        const T k0 = m_div(m_sqrt(T(3)), T(-2)), k1 = T(0.5), k2 = T(0.57735026918962573);   // tan(pi/6)
+        SDF_FOR_N {
+            T px = m_abs(x[i]), py = m_abs(y[i]);
+            const T h = m_min(k0 * px + k1 * py, T(0));
+            px -= T(2) * k0 * h; py -= T(2) * k1 * h;
+            px -= m_min(m_max(px, -k2 * r), k2 * r);
+            py -= r;
+            d[i] = m_len2(px, py) * m_sign(py);
+        }
+    }
+    static __device__ __forceinline__ void ROUNDED_X(State& st, const T* c, const int a) {   // d2.py:171-174
+        SDF_BIND_STATE;
+        const T w = c[0], r = c[1];
+        SDF_FOR_N {
+            const T px = m_abs(x[i]), py = m_abs(y[i]);
+            const T q = m_min(px + py, w) * T(0.5);
+            d[i] = m_len2(px - q, py - q) - r;
+        }
+    }
+    static __device__ __forceinline__ void POLYGON(State& st, const T* c, const int a) {   // d2.py:180-197 (a = n)
+        SDF_BIND_STATE;
+        const int n = a;
+        SDF_FOR_N {
+            const T px = x[i], py = y[i];
+            T dd = (px - c[0]) * (px - c[0]) + (py - c[1]) * (py - c[1]);
+            T s = T(1);
+            for (int q = 0; q < n; ++q) {
+                const int j = (q + n - 1) % n;
+                const T vix = c[2 * q], viy = c[2 * q + 1], vjx = c[2 * j], vjy = c[2 * j + 1];
+                const T ex = vjx - vix, ey = vjy - viy;
+                const T wx = px - vix, wy = py - viy;
+                const T h = m_clip01(m_div(wx * ex + wy * ey, ex * ex + ey * ey));
+                const T bx = wx - ex * h, by = wy - ey * h;
+                dd = m_min(dd, bx * bx + by * by);
+                const bool c1 = py >= viy, c2 = py < vjy, c3 = ex * wy > ey * wx;
+                if ((c1 && c2 && c3) || (!c1 && !c2 && !c3)) s = -s;
+            }
+            d[i] = s * m_sqrt(dd);
+        }
+    }
+    static __device__ __forceinline__ void VESICA(State& st, const T* c, const int a) {   // d2.py:202-208
+        SDF_BIND_STATE;
+        const T r = c[0], dd = c[1];
+        const T b = m_sqrt(r * r - dd * dd);
+        SDF_FOR_N {
+            const T px = m_abs(x[i]), py = m_abs(y[i]);
+            d[i] = ((py - b) * dd > px * b) ? m_len2(px, py - b) : m_len2(px + dd, py) - r;
+        }
+    }
+    // ------------------------------------------------------------------ 2-D <-> 3-D
+    static __device__ __forceinline__ void REVOLVE(State& st, const T* c, const int a) {   // d2.py:282-285
+        SDF_BIND_STATE;
+        const T off = c[0];
+        SDF_FOR_N { const T q = m_len2(x[i], y[i]) - off; x[i] = q; y[i] = z[i]; }
+    }
+    static __device__ __forceinline__ void EXTRUDE_PRE(State& st, const T* c, const int a) {   // d2.py:264 (pushes w)
+        SDF_BIND_STATE;
+        const T hh = c[0] / T(2);
+        if (a > 0) { SDF_FOR_N vs[a - 1][i] = s0[i]; }
+        SDF_FOR_N s0[i] = m_abs(z[i]) - hh;
+    }
+    static __device__ __forceinline__ void EXTRUDE_POST(State& st, const T* c, const int a) {   // d2.py:265
+        SDF_BIND_STATE;
+        SDF_FOR_N {
+            const T w0 = d[i], w1 = s0[i];
+            d[i] = m_min(m_max(w0, w1), T(0)) + m_len2(m_max(w0, T(0)), m_max(w1, T(0)));
+        }
+        if (a > 0) { SDF_FOR_N s0[i] = vs[a - 1][i]; }
+    }
+    static __device__ __forceinline__ void SLICE_PRE(State& st, const T* c, const int a) {   // d3.py:514
+        SDF_BIND_STATE;
+        SDF_FOR_N z[i] = T(0);
+    }
+    static __device__ __forceinline__ void SLICE_SELECT(State& st, const T* c, const int a) {   // d3.py:515-519
+        SDF_BIND_STATE;
+        SDF_FOR_N { const T A = s0[i], B = -d[i]; d[i] = (A <= T(0)) ? B : A; }
+        if (a > 0) { SDF_FOR_N s0[i] = vs[a - 1][i]; }
+    }
+    // ------------------------------------------------------------------ eased warps / transitions
+    static __device__ __forceinline__ void TPARAM_LINEAR(State& st, const T* c, const int a) {   // d3.py:442,464
+        SDF_BIND_STATE;
+        const T ax = c[3], ay = c[4], az = c[5];
+        const T abab = ax * ax + ay * ay + az * az;
+        SDF_FOR_N d[i] = m_clip01(m_div((x[i] - c[0]) * ax + (y[i] - c[1]) * ay + (z[i] - c[2]) * az, abab));
+    }
+    static __device__ __forceinline__ void TPARAM_RADIAL(State& st, const T* c, const int a) {   // d3.py:453-454
+        SDF_BIND_STATE;
+        const T r0 = c[0], dr = c[1] - c[0];
+        SDF_FOR_N d[i] = m_clip01(m_div(M::hypot_(x[i], y[i]) - r0, dr));
+    }
+    static __device__ __forceinline__ void TPARAM_Z(State& st, const T* c, const int a) {   // d2.py:273
+        SDF_BIND_STATE;
+        const T h = c[0];
+        SDF_FOR_N d[i] = m_min(m_max(m_div(z[i], h), T(-0.5)), T(0.5)) + T(0.5);
+    }
+    static __device__ __forceinline__ T ease_bounce_out(T t) {                             // ease.py:131-140
+        const T aa = m_div(T(121) * t * t, T(16));
+        const T bb = (T(363) / T(40) * t * t) - (T(99) / T(10) * t) + T(17) / T(5);
+        const T cc = (T(4356) / T(361) * t * t) - (T(35442) / T(1805) * t) + T(16061) / T(1805);
+        const T dd = (T(54) / T(5) * t * t) - (T(513) / T(25) * t) + T(268) / T(25);
+        return t < T(4) / T(11) ? aa : (t < T(8) / T(11) ? bb : (t < T(9) / T(10) ? cc : dd));
+    }
+    static __device__ __forceinline__ T ease_eval(int id, T t) {                          // ease.py:3-162
+        const T PI = T(3.141592653589793);
+        T sn, cs;
+        switch (id) {
+            case 0: return t;                                                              // linear
+            case 1: return t * t;                                                          // in_quad
+            case 2: return -t * (t - T(2));                                                // out_quad
+            case 3: { const T u = T(2) * t - T(1); return t < T(0.5) ? T(2) * t * t : T(-0.5) * (u * (u - T(2)) - T(1)); }
+            case 4: return t * t * t;                                                      // in_cubic
+            case 5: { const T u = t - T(1); return u * u * u + T(1); }
+            case 6: { const T u = t * T(2), v = u - T(2); return u < T(1) ? T(0.5) * u * u * u : T(0.5) * (v * v * v + T(2)); }
+            case 7: return t * t * t * t;                                                  // in_quart
+            case 8: { const T u = t - T(1); return -(u * u * u * u - T(1)); }
+            case 9: { const T u = t * T(2), v = u - T(2); return u < T(1) ? T(0.5) * u * u * u * u : T(-0.5) * (v * v * v * v - T(2)); }
+            case 10: return t * t * t * t * t;                                             // in_quint
+            case 11: { const T u = t - T(1); return u * u * u * u * u + T(1); }
+            case 12: { const T u = t * T(2), v = u - T(2); return u < T(1) ? T(0.5) * u * u * u * u * u : T(0.5) * (v * v * v * v * v + T(2)); }
+            case 13: M::sincos_(m_div(t * PI, T(2)), &sn, &cs); return -cs + T(1);         // in_sine
+            case 14: M::sincos_(m_div(t * PI, T(2)), &sn, &cs); return sn;                 // out_sine
+            case 15: M::sincos_(PI * t, &sn, &cs); return T(-0.5) * (cs - T(1));           // in_out_sine
+            case 16: return t == T(0) ? T(0) : M::exp2_(T(10) * (t - T(1)));               // in_expo
+            case 17: return t == T(1) ? T(1) : T(1) - M::exp2_(T(-10) * t);                // out_expo
+            case 18: return t == T(0) ? T(0) : (t == T(1) ? T(1) : (t < T(0.5) ? T(0.5) * M::exp2_(T(20) * t - T(10))
+                                                                              : T(1) - T(0.5) * M::exp2_(T(-20) * t + T(10))));
+            case 19: return T(-1) * (m_sqrt(T(1) - t * t) - T(1));                         // in_circ
+            case 20: { const T u = t - T(1); return m_sqrt(T(1) - u * u); }
+            case 21: { const T u = t * T(2), v = u - T(2);
+                       return u < T(1) ? T(-0.5) * (m_sqrt(T(1) - u * u) - T(1)) : T(0.5) * (m_sqrt(T(1) - v * v) + T(1)); }
+            case 22: { const T u = t - T(1), k = T(0.5);                                   // in_elastic
+                       M::sincos_(m_div((u - k / T(4)) * (T(2) * PI), k), &sn, &cs); return T(-1) * (M::exp2_(T(10) * u) * sn); }
+            case 23: { const T k = T(0.5);                                                 // out_elastic
+                       M::sincos_((t - k / T(4)) * m_div(T(2) * PI, k), &sn, &cs); return M::exp2_(T(-10) * t) * sn + T(1); }
+            case 24: { const T u = t * T(2), v = u - T(1), k = T(0.5);                     // in_out_elastic
+                       M::sincos_(m_div((v - k / T(4)) * T(2) * PI, k), &sn, &cs);
+                       return u < T(1) ? T(-0.5) * (M::exp2_(T(10) * v) * sn) : M::exp2_(T(-10) * v) * sn * T(0.5) + T(1); }
+            case 25: { const T k = T(1.70158); return t * t * ((k + T(1)) * t - k); }      // in_back
+            case 26: { const T k = T(1.70158), u = t - T(1); return u * u * ((k + T(1)) * u + k) + T(1); }
+            case 27: { const T k = T(1.70158) * T(1.525), u = t * T(2), v = u - T(2);
+                       return u < T(1) ? T(0.5) * (u * u * ((k + T(1)) * u - k)) : T(0.5) * (v * v * ((k + T(1)) * v + k) + T(2)); }
+            case 28: return T(1) - ease_bounce_out(T(1) - t);                              // in_bounce
+            case 29: return ease_bounce_out(t);                                            // out_bounce
+            case 30: return t < T(0.5) ? (T(1) - ease_bounce_out(T(1) - T(2) * t)) * T(0.5)
+                                       : ease_bounce_out(T(2) * t - T(1)) * T(0.5) + T(0.5);
+            case 31: return t < T(1) ? T(0) : T(1);                                        // in_square
+            case 32: return t > T(0) ? T(1) : T(0);                                        // out_square
+            case 33: return t < T(0.5) ? T(0) : T(1);                                      // in_out_square
+            default: return t;
+        }
+    }
+    static __device__ __forceinline__ void EASE(State& st, const T* c, const int a) {
+        SDF_BIND_STATE;
+        if (a != 0) { SDF_FOR_N d[i] = ease_eval(a, d[i]); }
+    }
+    static __device__ __forceinline__ void DISPLACE(State& st, const T* c, const int a) {   // d3.py:444,455
+        SDF_BIND_STATE;
+        const T vx = c[0], vy = c[1], vz = c[2];
+        SDF_FOR_N { x[i] = x[i] + d[i] * vx; y[i] = y[i] + d[i] * vy; z[i] = z[i] + d[i] * vz; }
+    }
+    static __device__ __forceinline__ void LERP_POP2(State& st, const T* c, const int a) {   // d3.py:466,479
+        SDF_BIND_STATE;
+        SDF_FOR_N { const T t = d[i], d2 = s0[i], d1 = vs[a][i]; d[i] = t * d2 + (T(1) - t) * d1; }
+        if (a > 0) { SDF_FOR_N s0[i] = vs[a - 1][i]; }
+    }
+    static __device__ __forceinline__ void MIX_POP2(State& st, const T* c, const int a) {   // d2.py:274
+        SDF_BIND_STATE;
+        SDF_FOR_N { const T t = d[i], d2 = s0[i], d1 = vs[a][i]; d[i] = d1 + (d2 - d1) * t; }
+        if (a > 0) { SDF_FOR_N s0[i] = vs[a - 1][i]; }
+    }
+    static __device__ __forceinline__ void WRAP_PRE(State& st, const T* c, const int a) {   // d3.py:490-497
+        SDF_BIND_STATE;
+        const T r = c[0];
+        const T PI = T(3.141592653589793);
+        SDF_FOR_N {
+            const T dd = M::hypot_(x[i], y[i]) - r;
+            const T ang = M::atan2_(y[i], x[i]);
+            d[i] = m_div(ang + PI, T(2) * PI);
+            y[i] = -dd;
+        }
+    }
+    static __device__ __forceinline__ void WRAP_POST(State& st, const T* c, const int a) {   // d3.py:498-499
+        SDF_BIND_STATE;
+        const T x0 = c[0], dx = c[1] - c[0];
+        SDF_FOR_N x[i] = x0 + dx * d[i];
+    }
 };
 
 // Interpreter front end: evaluate the program at N points.  On return d[i] = sdf(x[i], y[i], z[i]);

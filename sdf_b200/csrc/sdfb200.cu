@@ -85,7 +85,7 @@ refine_points_kernel(const __grid_constant__ ProgramImage img, const GridDesc g,
 }
 
 template <int TS>
-__global__ void __launch_bounds__(EXTRACT_THREADS)
+__global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_BLOCKS_PER_SM)
 extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
                const unsigned long long tri_capacity) {
     extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity);
@@ -136,7 +136,10 @@ struct JitEntry {
 };
 
 struct sdfb200_prog {
-    ProgramImage img;
+    ProgramImage img;                   // interpreter image (valid only when the program fits it)
+    bool img_valid = false;
+    std::vector<uint32_t> code;         // the whole program (the specialised kernels are generated from it)
+    std::vector<double> consts;
     int n_consts = 0;
     std::mutex lock;
     std::vector<DeviceCtx> ctxs;
@@ -209,7 +212,7 @@ static std::string jit_source(const sdfb200_prog* p, int kernel) {
          "    typedef SdfOps<T, N, FAST> O;\n    typename O::State st(x, y, z, d);\n";
     o << "    const T C[" << (p->n_consts > 0 ? p->n_consts : 1) << "] = {";
     for (int i = 0; i < p->n_consts; ++i) {
-        const double v = p->img.cd[i];
+        const double v = p->consts[i];
         char buf[80];
         if (isfinite(v)) snprintf(buf, sizeof(buf), "(T)%a", v);
         else { long long bits; memcpy(&bits, &v, 8); snprintf(buf, sizeof(buf), "(T)__longlong_as_double(0x%llxLL)", bits); }
@@ -217,8 +220,8 @@ static std::string jit_source(const sdfb200_prog* p, int kernel) {
     }
     if (p->n_consts == 0) o << "(T)0";
     o << "};\n";
-    for (uint32_t i = 0; i < p->img.n_code; ++i) {
-        const uint32_t w = p->img.code[i];
+    for (size_t i = 0; i < p->code.size(); ++i) {
+        const uint32_t w = p->code[i];
         o << "    O::" << SDF_OP_NAME[w & 0xff] << "(st, C + " << (w >> 16) << ", " << ((w >> 8) & 0xff) << ");\n";
     }
     o << "  }\n};\n#include \"sdf_jit_entry.cuh\"\n";
@@ -261,7 +264,7 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
 // Compile (once) and return the specialised kernel, or nullptr when unavailable.
 static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true) {
     const int mode = jit_mode();
-    if (mode == 0 || (mode == 1 && !big_enough)) return nullptr;
+    if (p->img_valid && (mode == 0 || (mode == 1 && !big_enough))) return nullptr;      // (no image: only this path exists)
     JitEntry& e = p->jit[kernel];
     if (e.tried) return e.kern;
     e.tried = true;
@@ -282,6 +285,13 @@ static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true)
     e.kern = k;
     return k;
 }
+
+#define REQUIRE_IMAGE(prog)                                                                                   \
+    do {                                                                                                      \
+        if (!(prog)->img_valid)                                                                               \
+            return fail(SDFB200_E_INVALID, "program (%zu words) exceeds the interpreter image and its run-time " \
+                        "specialisation is unavailable: %s", (prog)->code.size(), (prog)->jit_log.c_str());  \
+    } while (0)
 
 static cudaError_t jit_launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
     return cudaLaunchKernel((const void*)k, grid, block, args, smem, stream);
@@ -365,28 +375,35 @@ extern "C" int sdfb200_program_create(const uint32_t* code, int n_code, const do
                                       sdfb200_prog** out) {
     if (!code || !out || n_code <= 0 || n_consts < 0 || (n_consts > 0 && !consts))
         return fail(SDFB200_E_INVALID, "program_create: NULL/empty argument");
-    if (n_code > SDF_MAX_CODE || n_consts > SDF_MAX_CONSTS)
+    if (n_code > SDF_PROG_MAX_CODE || n_consts > SDF_PROG_MAX_CONSTS)
         return fail(SDFB200_E_INVALID, "program too large: %d words / %d constants (limits %d / %d)", n_code, n_consts,
-                    SDF_MAX_CODE, SDF_MAX_CONSTS);
+                    SDF_PROG_MAX_CODE, SDF_PROG_MAX_CONSTS);
     // validate: opcodes known, constant windows inside the table, stack / slot operands in range
     for (int i = 0; i < n_code; ++i) {
         const uint32_t w = code[i];
         const int op = (int)(w & 0xff), a = (int)((w >> 8) & 0xff), ci = (int)(w >> 16);
         if (op <= 0 || op >= OP__COUNT) return fail(SDFB200_E_INVALID, "instruction %d: unknown opcode %d", i, op);
-        if (ci + SDF_OP_NCONST[op] > n_consts)
-            return fail(SDFB200_E_INVALID, "instruction %d: constants [%d,%d) outside table of %d", i, ci,
-                        ci + SDF_OP_NCONST[op], n_consts);
+        const int nc = SDF_OP_NCONST[op] >= 0 ? SDF_OP_NCONST[op] : 2 * a;        // POLYGON: a points, 2a constants
+        if (ci + nc > n_consts)
+            return fail(SDFB200_E_INVALID, "instruction %d: constants [%d,%d) outside table of %d", i, ci, ci + nc, n_consts);
         const bool slot_op = (op == OP_SAVEP || op == OP_LOADP || op == OP_CIRCULAR_PRE);
+        const bool free_op = (op == OP_POLYGON || op == OP_EASE);                 // operand is a count / an id
         if (slot_op && a >= SDF_MAX_PSLOTS) return fail(SDFB200_E_INVALID, "instruction %d: point slot %d too deep", i, a);
-        if (!slot_op && a > SDF_MAX_VSTACK) return fail(SDFB200_E_INVALID, "instruction %d: value stack %d too deep", i, a);
+        if (!slot_op && !free_op && a > SDF_MAX_VSTACK) return fail(SDFB200_E_INVALID, "instruction %d: value stack %d too deep", i, a);
+        if (op == OP_EASE && a > 33) return fail(SDFB200_E_INVALID, "instruction %d: unknown ease id %d", i, a);
     }
     sdfb200_prog* p = new (std::nothrow) sdfb200_prog();
     if (!p) return fail(SDFB200_E_INVALID, "out of host memory");
     memset(&p->img, 0, sizeof(ProgramImage));
-    p->img.n_code = (uint32_t)n_code;
+    p->code.assign(code, code + n_code);
+    p->consts.assign(consts, consts + n_consts);
     p->n_consts = n_consts;
-    memcpy(p->img.code, code, sizeof(uint32_t) * n_code);
-    for (int i = 0; i < n_consts; ++i) { p->img.cd[i] = consts[i]; p->img.cf[i] = (float)consts[i]; }
+    p->img_valid = (n_code <= SDF_MAX_CODE && n_consts <= SDF_MAX_CONSTS);
+    if (p->img_valid) {
+        p->img.n_code = (uint32_t)n_code;
+        memcpy(p->img.code, code, sizeof(uint32_t) * n_code);
+        for (int i = 0; i < n_consts; ++i) { p->img.cd[i] = consts[i]; p->img.cf[i] = (float)consts[i]; }
+    }
     *out = p;
     return 0;
 }
@@ -425,8 +442,11 @@ static int eval_f32_impl(sdfb200_prog* prog, const float* xyz, int64_t n, float*
         long long nn = (long long)n;
         void* args[] = {(void*)&dx, (void*)&nn, (void*)&dd};
         CUDA_TRY(jit_launch(jk, dim3(grid), dim3(STREAM_THREADS), 0, stream, args));
-    } else if (fast) eval_stream_f32_kernel<true><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
-    else eval_stream_f32_kernel<false><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    } else {
+        REQUIRE_IMAGE(prog);
+        if (fast) eval_stream_f32_kernel<true><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
+        else eval_stream_f32_kernel<false><<<grid, STREAM_THREADS, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    }
     CUDA_TRY(cudaGetLastError());
     if (!out_dev) CUDA_TRY(cudaMemcpyAsync(d_out, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
     if (!in_dev || !out_dev) CUDA_TRY(cudaStreamSynchronize(stream));
@@ -461,7 +481,10 @@ extern "C" int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n
         long long nn = (long long)n;
         void* args[] = {(void*)&dx, (void*)&nn, (void*)&dd};
         CUDA_TRY(jit_launch(jk, dim3(grid), dim3(256), 0, stream, args));
-    } else eval_stream_f64_kernel<<<grid, 256, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    } else {
+        REQUIRE_IMAGE(prog);
+        eval_stream_f64_kernel<<<grid, 256, 0, stream>>>(prog->img, dx, (long long)n, dd);
+    }
     CUDA_TRY(cudaGetLastError());
     if (!out_dev) CUDA_TRY(cudaMemcpyAsync(d_out, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
     if (!in_dev || !out_dev) CUDA_TRY(cudaStreamSynchronize(stream));
@@ -594,6 +617,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
             void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&bt, (void*)&ctrp};
             CUDA_TRY(jit_launch(jk, dim3(pb), dim3(128), 0, stream, args));
         } else {
+            REQUIRE_IMAGE(prog);
             skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->batch_tris, c->ctr);
             CUDA_TRY(cudaGetLastError());
         }
@@ -651,6 +675,9 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                         const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
                         void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
                         e = jit_launch(jk, dim3(grid), dim3(f64 ? 512 : 1024), smem, stream, args);
+                    } else if (!prog->img_valid) {
+                        REQUIRE_IMAGE(prog);
+                        e = cudaSuccess;
                     } else if (precision == SDFB200_PREC_F32)
                         e = launch_tile_eval<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
                     else if (precision == SDFB200_PREC_MIXED)
@@ -668,12 +695,13 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                             void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
                             CUDA_TRY(jit_launch(jk, dim3(rgrid), dim3(128), 0, stream, args));
                         } else {
+                            REQUIRE_IMAGE(prog);
                             refine_points_kernel<kTS><<<rgrid, 128, 0, stream>>>(prog->img, g, L, c->ctr);
                             CUDA_TRY(cudaGetLastError());
                         }
                     }
                     // ---- (C) extraction
-                    extract_kernel<kTS><<<c->sms * 2, EXTRACT_THREADS, 0, stream>>>(g, L, c->ctr, c->batch_tris, dtri, cap);
+                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, stream>>>(g, L, c->ctr, c->batch_tris, dtri, cap);
                     CUDA_TRY(cudaGetLastError());
                 }
                 CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -752,7 +780,15 @@ extern "C" int sdfb200_skip_flags(sdfb200_prog* prog, const double* xs, int64_t 
     rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, 0, -1, &g); if (rc) return rc;
     const long long total_b = (long long)g.nbx * g.nby * g.nbz;
     const int pb = (int)((total_b + 127) / 128);
-    skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, 1, c->flags, c->active, c->batch_tris, c->ctr);
+    if (cudaKernel_t jk = jit_get(prog, JK_SKIP, total_b >= 4096)) {
+        int sparse = 1;
+        unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;
+        void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&bt, (void*)&ctrp};
+        CUDA_TRY(jit_launch(jk, dim3(pb), dim3(128), 0, stream, args));
+    } else {
+        REQUIRE_IMAGE(prog);
+        skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, 1, c->flags, c->active, c->batch_tris, c->ctr);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(flags, c->flags, (size_t)total_b, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));

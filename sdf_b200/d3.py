@@ -17,7 +17,7 @@ import functools
 
 import numpy as np
 
-from . import dn
+from . import dn, ease
 from .ir import Node
 
 # Constants (d3.py:9-17)
@@ -333,28 +333,55 @@ def bend(other, k):
     return Node('transform', 'BEND', [k], [other])
 
 
-def _needs_ease(name):
-    def factory(*args, **kwargs):
-        raise NotImplementedError(
-            '%s is not lowered to the CUDA evaluator yet (needs the ease opcodes; '
-            'SURVEY.md section 8f rank 1)' % name)
-    factory.__name__ = name
-    return factory
+@op3
+def bend_linear(other, p0, p1, v, e=ease.linear):
+    p0 = np.array(p0)
+    p1 = np.array(p1)
+    v = -np.array(v)
+    ab = p1 - p0
+    steps = [('TPARAM_LINEAR', 0, [*_vec3(p0), *_vec3(ab)]), ('EASE', ease.ease_id_of(e), []), ('DISPLACE', 0, _vec3(v))]
+    return Node('warp', 'BEND_LINEAR', children=[other], extra=steps)
 
 
-bend_linear = op3(_needs_ease('bend_linear'))
-bend_radial = op3(_needs_ease('bend_radial'))
-transition_linear = op3(_needs_ease('transition_linear'))
-transition_radial = op3(_needs_ease('transition_radial'))
-wrap_around = op3(_needs_ease('wrap_around'))
+@op3
+def bend_radial(other, r0, r1, dz, e=ease.linear):
+    steps = [('TPARAM_RADIAL', 0, [r0, r1]), ('EASE', ease.ease_id_of(e), []), ('DISPLACE', 0, [0.0, 0.0, -dz])]
+    return Node('warp', 'BEND_RADIAL', children=[other], extra=steps)
+
+
+@op3
+def transition_linear(f0, f1, p0=-Z, p1=Z, e=ease.linear):
+    p0 = np.array(p0)
+    p1 = np.array(p1)
+    ab = p1 - p0
+    return Node('transition', 'TRANSITION_LINEAR', children=[f0, f1],
+                extra=(('TPARAM_LINEAR', [*_vec3(p0), *_vec3(ab)]), ease.ease_id_of(e), 'LERP_POP2', None))
+
+
+@op3
+def transition_radial(f0, f1, r0=0, r1=1, e=ease.linear):
+    return Node('transition', 'TRANSITION_RADIAL', children=[f0, f1],
+                extra=(('TPARAM_RADIAL', [r0, r1]), ease.ease_id_of(e), 'LERP_POP2', None))
+
+
+@op3
+def wrap_around(other, x0, x1, r=None, e=ease.linear):
+    p0 = X * x0
+    p1 = X * x1
+    if r is None:
+        r = np.linalg.norm(p1 - p0) / (2 * np.pi)
+    steps = [('WRAP_PRE', 0, [r]), ('EASE', ease.ease_id_of(e), []), ('WRAP_POST', 0, [x0, x1])]
+    return Node('warp', 'WRAP_AROUND', children=[other], extra=steps)
 
 
 # 3D => 2D
 
 @op32
 def slice(other):
-    raise NotImplementedError('slice (3D -> 2D) is not lowered to the CUDA evaluator yet '
-                              '(SURVEY.md section 8f rank 1)')
+    s = slab(z0=-1e-9, z1=1e-9)
+    a = other & s
+    b = other.negate() & s
+    return Node('slice', 'SLICE', children=[a, b])
 
 
 # Common (dn.py)

@@ -62,6 +62,32 @@ _OPS = [
     ('INTERSECTION', 0),      #                                    dn.py:44
     ('INTERSECTION_K', 1),    # K                                  dn.py:46-48
     ('BLEND', 1),             # K                                  dn.py:52-60
+    # 2-D primitives (read P.xy, write D)                               sdf/d2.py
+    ('CIRCLE', 3),            # cx cy r                            d2.py:76-80
+    ('LINE2', 4),             # nx ny px py                        d2.py:82-87
+    ('RECTANGLE', 4),         # cx cy hx hy                        d2.py:102-114
+    ('ROUNDED_RECTANGLE', 6), # hx hy r0 r1 r2 r3                  d2.py:116-135
+    ('EQUILATERAL_TRIANGLE', 0),  #                                d2.py:137-153
+    ('HEXAGON', 1),           # r * sqrt(3)/2                      d2.py:155-167
+    ('ROUNDED_X', 2),         # w r                                d2.py:169-175
+    ('POLYGON', -1),          # a = n points, 2n constants         d2.py:177-198
+    ('VESICA', 2),            # r d                                d2.py:200-209
+    # 2-D <-> 3-D
+    ('REVOLVE', 1),           # offset ; P <- (|xy| - offset, z)    d2.py:280-286
+    ('EXTRUDE_PRE', 1),       # h ; pushes |z| - h/2               d2.py:261-266
+    ('EXTRUDE_POST', 0),      # D <- min(max(D,w),0)+|max((D,w),0)|, pops
+    ('SLICE_PRE', 0),         # P.z <- 0                            d3.py:506-520
+    ('SLICE_SELECT', 0),      # D <- (A <= 0) ? -D : A with A = pop
+    # eased warps / transitions (the `e=` parameter)                    sdf/ease.py
+    ('TPARAM_LINEAR', 6),     # p0(3) ab(3) ; D <- clip(dot(p-p0,ab)/dot(ab,ab),0,1)   d3.py:442,464
+    ('TPARAM_RADIAL', 2),     # r0 r1 ; D <- clip((|xy|-r0)/(r1-r0),0,1)               d3.py:453-454,476-477
+    ('TPARAM_Z', 1),          # h ; D <- clip(z/h,-.5,.5)+.5                          d2.py:273
+    ('EASE', 0),              # a = ease id ; D <- e(D)            ease.py:3-162
+    ('DISPLACE', 3),          # v ; P <- P + D*v                   d3.py:444,455
+    ('LERP_POP2', 0),         # D <- t*d2 + (1-t)*d1, pops 2       d3.py:466,479
+    ('MIX_POP2', 0),          # D <- d1 + (d2-d1)*t, pops 2        d2.py:274
+    ('WRAP_PRE', 1),          # r ; D <- t, P.y <- -(|xy|-r)       d3.py:490-497
+    ('WRAP_POST', 2),         # x0 x1 ; P.x <- x0 + (x1-x0)*D      d3.py:498
     # stack / slots
     ('PUSH', 0),              # a = 0: S0 <- D ; a = s+1: VS[s] <- S0, S0 <- D
     ('SAVEP', 0),             # a = slot (0 = register slot)
@@ -75,8 +101,10 @@ OPNAME = {v: k for k, v in OPCODE.items()}
 FOLD_OPS = {'union': ('UNION', 'UNION_K'), 'difference': ('DIFFERENCE', 'DIFFERENCE_K'),
             'intersection': ('INTERSECTION', 'INTERSECTION_K')}
 
-MAX_CODE = 512       # instruction words that fit the kernel-parameter program image
-MAX_CONSTS = 1024
+MAX_CODE = 8192      # instruction words (the kernel-parameter image of the interpreter holds 512 / 1024;
+MAX_CONSTS = 32768   #  larger programs run only on the run-time specialised kernels)
+IMG_MAX_CODE = 512   # capacity of the interpreter's kernel-parameter program image
+IMG_MAX_CONSTS = 1024
 MAX_VSTACK = 16
 MAX_PSLOTS = 8
 
@@ -126,7 +154,7 @@ class Program:
         for w in self.code:
             op, a, ci = int(w) & 0xff, (int(w) >> 8) & 0xff, int(w) >> 16
             name = OPNAME[op]
-            n = NCONST[name]
+            n = NCONST[name] if NCONST[name] >= 0 else 2 * a
             out.append('%-16s a=%d  %s' % (name, a, np.array2string(self.consts[ci:ci + n], precision=6)))
         return '\n'.join(out)
 
@@ -142,7 +170,7 @@ def node_of(obj):
 
 def _clobbers(obj):
     n = node_of(obj)
-    if n.kind == 'prim':
+    if n.kind in ('prim', 'polygon'):
         return False
     if n.kind == 'value':
         return _clobbers(n.children[0])
@@ -164,7 +192,7 @@ class _Lowerer:
     def emit(self, name, a=0, consts=None):
         if consts is None:
             consts = ()
-        assert len(consts) == NCONST[name], (name, len(consts))
+        assert NCONST[name] < 0 or len(consts) == NCONST[name], (name, len(consts))
         ci = len(self.consts)
         self.consts.extend(float(c) for c in consts)
         if not (0 <= a < 256 and ci < 65536):
@@ -216,6 +244,22 @@ class _Lowerer:
             self.max_vdepth = max(self.max_vdepth, self.vdepth)
             self.node(n.children[0])
             self.combine('ADD_POP')
+        elif kind == 'extrude':                     # d2.py:261-266
+            self.emit('EXTRUDE_PRE', a=self.vdepth, consts=n.consts)    # pushes |z| - h/2
+            self.vdepth += 1
+            self.max_vdepth = max(self.max_vdepth, self.vdepth)
+            self.node(n.children[0])
+            self.combine('EXTRUDE_POST')
+        elif kind == 'polygon':
+            self.emit('POLYGON', a=len(n.consts) // 2, consts=n.consts)
+        elif kind == 'warp':                        # bend_linear / bend_radial / wrap_around
+            for op, a, consts in n.extra:
+                self.emit(op, a=a, consts=consts)
+            self.node(n.children[0])
+        elif kind == 'transition':                  # transition_linear/_radial, extrude_to
+            self.transition(n)
+        elif kind == 'slice':
+            self.slice(n)
         elif kind == 'fold':
             self.fold(n)
         elif kind == 'blend':
@@ -227,14 +271,22 @@ class _Lowerer:
         else:
             raise NotLowerableError('unknown node kind %r' % (kind,))
 
-    def fold(self, n, blend=False):
+    def fold(self, n, blend=False, shared_slot=None):
+        """``shared_slot``: this fold is the FIRST operand of an enclosing fold, evaluated at the point
+        that fold has just saved -- it restores from the same slot instead of saving P again (keeps
+        the slot depth of ``f |= ...; f -= ...`` chains at one)."""
         kids = n.children
         need_save = any(_clobbers(c) for c in kids[:-1])
-        slot = None
-        if need_save:
+        slot = shared_slot
+        own = need_save and shared_slot is None
+        if own:
             slot = self.alloc_pslot()
             self.emit('SAVEP', a=slot)
-        self.node(kids[0])
+        first = node_of(kids[0])
+        if need_save and first.kind in ('fold', 'blend'):
+            self.fold(first, blend=(first.kind == 'blend'), shared_slot=slot)
+        else:
+            self.node(kids[0])
         dirty = _clobbers(kids[0])
         k_op = n.extra            # the fold-level k (dn.py:12: ``k or getattr(b, '_k', None)``)
         for b in kids[1:]:
@@ -250,8 +302,45 @@ class _Lowerer:
                 self.combine(FOLD_OPS[n.op][0])
             else:
                 self.combine(FOLD_OPS[n.op][1], consts=(K,))
-        if need_save:
+        if own:
             self.free_pslot()
+
+    def transition(self, n):
+        """d1 = f0(p); d2 = f1(p); t = e(param(p)); combine(d1, d2, t)  (d3.py:458-481, d2.py:268-278)"""
+        f0, f1 = n.children
+        tparam, ease_id, mix, tail = n.extra
+        slot = self.alloc_pslot()
+        self.emit('SAVEP', a=slot)
+        self.node(f0)
+        self.push()
+        self.emit('LOADP', a=slot)
+        self.node(f1)
+        self.push()
+        self.emit('LOADP', a=slot)
+        self.emit(tparam[0], consts=tparam[1])
+        self.emit('EASE', a=ease_id)
+        self.vdepth -= 2
+        self.emit(mix, a=self.vdepth)
+        self.free_pslot()
+        if tail is not None:                        # extrude_to finishes like extrude
+            self.emit('EXTRUDE_PRE', a=self.vdepth, consts=tail)
+            # EXTRUDE_PRE pushes w and leaves D untouched; EXTRUDE_POST combines
+            self.vdepth += 1
+            self.max_vdepth = max(self.max_vdepth, self.vdepth)
+            self.combine('EXTRUDE_POST')
+
+    def slice(self, n):
+        """d3.py:506-520: A = (other & s)(x,y,0); B = -(other.negate() & s)(x,y,0); A <= 0 ? B : A"""
+        a_tree, b_tree = n.children
+        self.emit('SLICE_PRE')
+        slot = self.alloc_pslot()
+        self.emit('SAVEP', a=slot)
+        self.node(a_tree)
+        self.push()
+        self.emit('LOADP', a=slot)
+        self.node(b_tree)
+        self.combine('SLICE_SELECT')
+        self.free_pslot()
 
     def circular(self, n):
         # d3.py:379-392: other = other.translate(X * offset); two rotated copies; min

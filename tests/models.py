@@ -115,9 +115,84 @@ def node_corpus(ns):
     return m
 
 
+EASE_NAMES = ['linear', 'in_quad', 'out_quad', 'in_out_quad', 'in_cubic', 'out_cubic', 'in_out_cubic',
+              'in_quart', 'out_quart', 'in_out_quart', 'in_quint', 'out_quint', 'in_out_quint',
+              'in_sine', 'out_sine', 'in_out_sine', 'in_expo', 'out_expo', 'in_out_expo',
+              'in_circ', 'out_circ', 'in_out_circ', 'in_elastic', 'out_elastic', 'in_out_elastic',
+              'in_back', 'out_back', 'in_out_back', 'in_bounce', 'out_bounce', 'in_out_bounce',
+              'in_square', 'out_square', 'in_out_square']
+
+
+def example_pawn(ns):                # examples/pawn.py
+    Z, ease = ns.Z, ns.ease
+
+    def section(z0, z1, d0, d1, e=ease.linear):
+        f = ns.cylinder(d0 / 2).transition_linear(ns.cylinder(d1 / 2), Z * z0, Z * z1, e)
+        return f & ns.slab(z0=z0, z1=z1)
+    f = section(0, 0.2, 1, 1.25)
+    f |= section(0.2, 0.3, 1.25, 1).k(0.05)
+    f |= ns.rounded_cylinder(0.6, 0.1, 0.2).translate(Z * 0.4).k(0.05)
+    f |= section(0.5, 1.75, 1, 0.25, ease.out_quad).k(0.01)
+    f |= section(1.75, 1.85, 0.25, 0.5).k(0.01)
+    f |= section(1.85, 1.90, 0.5, 0.25).k(0.05)
+    f |= ns.sphere(0.3).translate(Z * 2.15).k(0.05)
+    return f
+
+
+def example_weave(ns):               # examples/weave.py
+    X, Z, ease = ns.X, ns.Z, ns.ease
+    f = ns.rounded_box([3.2, 1, 0.25], 0.1).translate((1.5, 0, 0.0625))
+    f = f.bend_linear(X * 0.75, X * 2.25, Z * -0.1875, ease.in_out_quad)
+    f = f.circular_array(3, 0)
+    f = f.repeat((2.7, 5.4, 0), padding=1)
+    f |= f.translate((2.7 / 2, 2.7, 0))
+    f &= ns.cylinder(10)
+    f |= (ns.cylinder(12) - ns.cylinder(10)) & ns.slab(z0=-0.5, z1=0.5).k(0.25)
+    return f
+
+
+def widened_corpus(ns):
+    """the 2-D library, extrude / extrude_to / revolve, slice, the
+    eased warps and transitions, every easing function (d2.py, d3.py:435-520, ease.py)."""
+    X, Y, Z, ease = ns.X, ns.Y, ns.Z, ns.ease
+    m = {}
+    m['x_hexagon'] = ns.hexagon(1).extrude(0.5)
+    m['x_rectangle'] = ns.rectangle((1, 2), (0.1, -0.2)).extrude(1)
+    m['x_rectangle_ab'] = ns.rectangle(a=(-1, -0.5), b=(0.5, 1)).extrude(0.4)
+    m['x_rounded_rectangle'] = ns.rounded_rectangle(np.array((1.0, 2.0)), (0.1, 0.2, 0.3, 0.05)).extrude(0.5)
+    m['x_triangle'] = ns.equilateral_triangle().extrude(0.3)
+    m['x_rounded_x'] = ns.rounded_x(1, 0.1).extrude(0.2)
+    m['x_polygon'] = ns.polygon([(0, 0), (1, 0), (1.2, 0.8), (0.5, 1.5), (-0.3, 0.7)]).extrude(0.4)
+    m['x_vesica'] = ns.vesica(1, 0.3).extrude(0.2)
+    m['x_line_slab'] = ns.d2.slab(x0=-0.5, x1=0.5, y0=-0.2).extrude(0.5)
+    m['revolve'] = ns.circle(0.4).revolve(1.2)
+    m['revolve_hex'] = ns.hexagon(0.3).translate((0.1, 0.2)).revolve(1.0)
+    m['extrude_to'] = ns.rectangle(1).extrude_to(ns.circle(0.7), 1.5, ease.in_out_quad)
+    m['ops2d'] = (ns.circle(0.5).translate((0.3, 0.1)) | ns.rectangle((0.6, 0.4)).rotate(0.5).k(0.1)).scale(1.3).extrude(0.5)
+    m['scale2d_xy'] = ns.circle(0.5).scale((1.0, 2.0)).extrude(0.3)
+    m['circular_array2d'] = ns.rectangle((0.2, 0.8)).translate((0.8, 0)).circular_array(5).extrude(0.3)
+    m['elongate2d'] = ns.circle(0.3).elongate((0.4, 0.2)).extrude(0.3)
+    m['repeat2d'] = ns.circle(0.2).repeat((0.6, 0.6), padding=1).extrude(0.2)
+    m['csg2d'] = ((ns.circle(1) & ns.rectangle(1.5)) - ns.circle(0.4).k(0.1)).shell(0.1).dilate(0.02).extrude(0.4)
+    m['slice'] = (ns.sphere(1) | ns.box(1.2).translate((0.5, 0, 0.3))).slice().extrude(0.3)
+    m['bend_linear'] = ns.rounded_box([3.2, 1, 0.25], 0.1).translate((1.5, 0, 0.0625)).bend_linear(
+        X * 0.75, X * 2.25, Z * -0.1875, ease.in_out_quad)
+    m['bend_radial'] = ns.box((2, 2, 0.2)).bend_radial(0.2, 1.0, 0.5, ease.in_out_sine)
+    m['transition_radial'] = ns.box(1).transition_radial(ns.sphere(0.8), 0.2, 0.9, ease.out_cubic)
+    m['transition_default'] = ns.sphere(0.8).transition_linear(ns.box(1.2))
+    m['wrap_around'] = ns.box((4, 0.3, 0.5)).translate((0, 1.0, 0)).wrap_around(-2, 2)
+    m['wrap_around_r'] = ns.capsule(-X * 2, X * 2, 0.2).wrap_around(-2, 2, r=0.8, e=ease.in_out_cubic)
+    m['pawn'] = example_pawn(ns)
+    m['weave'] = example_weave(ns)
+    for name in EASE_NAMES:
+        m['ease_' + name] = ns.sphere(0.8).transition_linear(ns.box(1.2), -Z * 0.7, Z * 0.9, getattr(ease, name))
+    return m
+
+
 def build(ns):
     out = {('cfg_' + k): f(ns) for k, f in CONFIGS.items()}
     out.update(node_corpus(ns))
+    out.update(widened_corpus(ns))
     return out
 
 

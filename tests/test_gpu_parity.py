@@ -38,9 +38,18 @@ def ref():
     return sdf_ref
 
 
+JIT_MUST = ('cfg_', 'weave', 'pawn', 'slice', 'extrude_to', 'wrap_around', 'x_polygon', 'bend_', 'repeat', 'circular')
+
+
 @pytest.fixture(scope='module')
-def corpus(sdf):
-    return models.build(sdf)
+def corpus(sdf, evaluator_front_end):
+    """All 114 models on the interpreter; every third one plus the structurally interesting ones on
+    the run-time specialised kernels (each costs three NVRTC compiles)."""
+    allm = models.build(sdf)
+    if evaluator_front_end == 'interp':
+        return allm
+    keep = {k: v for i, (k, v) in enumerate(allm.items()) if i % 3 == 0 or any(m in k for m in JIT_MUST)}
+    return keep
 
 
 def test_eval_f64_matches_reference_goldens(sdf, corpus, golden_dir):
@@ -153,6 +162,24 @@ def test_fast_stream_evaluator_error_is_inside_the_guard_band(sdf, ref, corpus):
         tau = core.mixed_tau(h.program, X, X, X)
         err = np.abs(d[ok] - r[ok])
         assert err.max() < tau, (name, float(err.max()), tau)
+
+
+WIDENED = [('pawn', ((-0.8, -0.8, -0.1), (0.8, 0.8, 2.6)), 0.025), ('weave', ((-13, -13, -1), (13, 13, 1)), 0.12),
+           ('x_polygon', ((-0.6, -0.3, -0.4), (1.5, 1.8, 0.4)), 0.02), ('slice', ((-1.3, -1.3, -0.4), (1.5, 1.3, 0.4)), 0.02),
+           ('extrude_to', ((-1, -1, -1), (1, 1, 1)), 0.02), ('wrap_around', ((-1.6, -1.6, -0.5), (1.6, 1.6, 0.5)), 0.02),
+           ('revolve_hex', ((-1.7, -1.7, -0.4), (1.7, 1.7, 0.8)), 0.025)]
+
+
+@pytest.mark.parametrize('name,bounds,step', WIDENED)
+def test_generate_widened_nodes(sdf, ref, name, bounds, step):
+    """SURVEY.md section 8(f) rank 1 nodes through the whole pipeline (default precision) vs the oracle."""
+    f = models.widened_corpus(sdf)[name]
+    pts, info = sdf.generate(f, step=step, bounds=bounds, verbose=False, return_info=True)
+    rpts, rstats = ref.generate(f, step=step, bounds=bounds)
+    assert (info['skipped'], info['empty'], info['nonempty']) == (rstats['skipped'], rstats['empty'], rstats['nonempty'])
+    rep = compare_soups(pts, rpts)
+    assert rep['count_equal'] and rep['max_vertex_dist'] <= 1e-5, rep
+    assert rep['exact_triangles'] >= 0.999 * rep['n_ref'], rep
 
 
 def test_generate_auto_bounds_matches_reference_goldens(sdf, golden_dir):

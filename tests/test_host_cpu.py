@@ -97,8 +97,13 @@ def test_program_size_limit():
     f = sdf_b200.sphere(0.1)
     for i in range(300):
         f = f | sdf_b200.sphere(0.1).translate((i, 0, 0))
+    prog = ir.lower(f)                                  # a left-leaning chain shares ONE point slot
+    assert prog.pslots == 1 and len(prog.code) > 600
+    g = sdf_b200.sphere(0.1).translate((1, 0, 0))
+    for i in range(20):                                 # right-leaning: every level needs its own slot
+        g = sdf_b200.sphere(0.1).translate((i, 0, 0)) | g.translate((0, 1, 0))
     with pytest.raises(ir.NotLowerableError):
-        ir.lower(f)
+        ir.lower(g)
 
 
 # ------------------------------------------------------------------ lattice / batching
@@ -205,6 +210,25 @@ def test_no_gpu_means_loud_failure_not_cpu_fallback():
     assert ei.value.code == _abi.E_NOGPU and 'no CPU fallback' in str(ei.value)
     with pytest.raises(_abi.SdfB200Error):
         sdf_b200.sphere(1)(np.zeros((1, 3)))
+
+
+def test_runtime_specialisation_compiles_without_a_gpu():
+    """The generated straight-line evaluator of a tree compiles with NVRTC for sm_100a (no GPU needed)."""
+    from sdf_b200 import core
+    ms = models.widened_corpus(sdf_b200)
+    for name, kernel in (('weave', 4), ('pawn', 6), ('slice', 7), ('x_polygon', 0), ('extrude_to', 8)):
+        h, _ = core.program_handle(ms[name])
+        assert h.jit_probe(kernel) > 10000, name
+
+
+def test_large_program_is_accepted_and_small_limits_still_guard():
+    f = sdf_b200.sphere(0.1)
+    for i in range(40):
+        f = f | sdf_b200.sphere(0.1).translate((i, 0, 0)).repeat((50.0, 3.0, 0), padding=1)
+    prog = ir.lower(f)
+    assert len(prog.code) > ir.IMG_MAX_CODE            # too big for the interpreter image ...
+    h = _abi.ProgramHandle(prog)                        # ... but a valid program (runs on the specialised kernels)
+    assert h.jit_probe(6) > 10000
 
 
 def test_program_create_validates():
