@@ -47,11 +47,45 @@ def plan_slabs(sdf, X, Y, Z, batch_size, world, device=None):
     return partition_layers(active, world)
 
 
-def allgather_triangles(local, group=None):
+class _PinnedTorchPool:
+    """Page-locked host buffers for the gathered result, recycled when the arrays handed out die
+    (same contract as sdf_b200._abi.PinnedPool, but torch-owned so that ``copy_(non_blocking=True)``
+    runs at PCIe rate)."""
+
+    def __init__(self, max_free=2):
+        self.free, self.max_free = [], max_free
+
+    def take(self, n_floats):
+        import weakref
+        import torch
+        n = max(int(n_floats), 1024)
+        best = None
+        for i, t in enumerate(self.free):
+            if t.numel() >= n and (best is None or t.numel() < self.free[best].numel()):
+                best = i
+        if best is not None:
+            t = self.free.pop(best)
+        else:
+            t = torch.empty(1 << max(10, (n - 1).bit_length()), dtype=torch.float32, pin_memory=True)
+        arr = t.numpy()
+        weakref.finalize(arr, self._release, t)
+        return t, arr
+
+    def _release(self, t):
+        if len(self.free) < self.max_free:
+            self.free.append(t)
+
+
+_pinned = _PinnedTorchPool()
+
+
+def allgather_triangles(local, group=None, compact=True):
     """Concatenate every rank's (n_r, 9) float32 triangle tensor on every rank.
 
     Counts are gathered first, buffers are padded to the largest count for one
-    ``all_gather_into_tensor`` and compacted afterwards, in rank (= Z-slab) order."""
+    ``all_gather_into_tensor``; ``compact=True`` returns the dense (T, 9) tensor in rank (= Z-slab)
+    order, ``compact=False`` the padded buffer with ``(counts, stride)`` so that the caller can copy
+    the valid segments itself (the host gather does, straight into pinned memory)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -66,6 +100,8 @@ def allgather_triangles(local, group=None):
         padded[:local.shape[0]] = local
     gathered = torch.empty((world * mx, 9), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
+    if not compact:
+        return gathered, counts, mx
     if all(c == mx for c in counts):
         return gathered
     return torch.cat([gathered[r * mx: r * mx + c] for r, c in enumerate(counts)])
@@ -103,6 +139,19 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
                                      stream=torch.cuda.current_stream(dev).cuda_stream)
         local = tri
     info = dict(info, zb=zb, rank=rank, world=world)
+    if gather == 'host' and world > 1 and local.is_cuda:
+        # padded all-gather, then the valid segment of every rank straight into one pinned array
+        gathered, counts, mx = allgather_triangles(local, group, compact=False)
+        total = int(sum(counts))
+        t, arr = _pinned.take(total * 9)
+        off = 0
+        for r, c in enumerate(counts):
+            if c:
+                t[off * 9:(off + c) * 9].copy_(gathered[r * mx:r * mx + c].reshape(-1), non_blocking=True)
+            off += c
+        torch.cuda.current_stream(local.device).synchronize()
+        info['triangles_total'] = total
+        return arr[:total * 9].reshape(-1, 3), info
     if gather == 'none' or world == 1:
         allt = local
     else:

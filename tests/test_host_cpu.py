@@ -223,7 +223,7 @@ def test_runtime_specialisation_compiles_without_a_gpu():
 
 def test_large_program_is_accepted_and_small_limits_still_guard():
     f = sdf_b200.sphere(0.1)
-    for i in range(40):
+    for i in range(12):
         f = f | sdf_b200.sphere(0.1).translate((i, 0, 0)).repeat((50.0, 3.0, 0), padding=1)
     prog = ir.lower(f)
     assert len(prog.code) > ir.IMG_MAX_CODE            # too big for the interpreter image ...
