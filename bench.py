@@ -54,8 +54,66 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+class NvmlSampler:
+    """SM clock + throttle reasons polled through NVML every millisecond during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.ok = index, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        if not self.ok:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def stop(self, t0, t1):
+        if not self.ok:
+            return None
+        self.stop_flag = True
+        self.thread.join(1.0)
+        nv = self.nv
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows
+        if not rows:
+            return None
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8) if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown') else 0x8,
+                 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+        reasons = [k for k, m in names.items() if bits & m]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {'sm_mhz': float(sm[len(sm) // 2]), 'sm_max_mhz': float(mx) if mx else None, 'reasons': reasons,
+                'samples': len(rows), 'source': 'nvml, 1 ms polling during the timed region'}
+
+
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """nvidia-smi clock / throttle-reason samples during the timed region (fallback)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -199,13 +257,15 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         device_step()
-    sampler = ClockSampler(local)
+    sampler = NvmlSampler(local)
+    if not sampler.ok:
+        sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     t0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    fused_ms, prepass_ms, stats_acc, n_tri = [], [], None, 0
+    fused_ms, prepass_ms, kern_ms, stats_acc, n_tri = [], [], [], None, 0
     for k in range(args.steps):
         flush.zero_()                                  # L2 flush between timed iterations (not timed)
         ev[k][0].record()
@@ -213,6 +273,7 @@ def run_ours(args):
         ev[k][1].record()
         fused_ms.append(timings[1])
         prepass_ms.append(timings[0])
+        kern_ms.append((timings[4], timings[5], timings[6]))
         stats_acc = stats
     barrier()
     t1 = time.time()
@@ -221,10 +282,12 @@ def run_ours(args):
     agg = torch.tensor([float(n_tri), float(stats_acc[3]), float(stats_acc[4]), float(stats_acc[5]),
                         float(stats_acc[0]), float(stats_acc[1]), float(stats_acc[2])], dtype=torch.float64, device='cuda')
     fused_t = torch.tensor([sum(fused_ms) / len(fused_ms)], dtype=torch.float64, device='cuda')
+    tile_t = torch.tensor([sum(k[0] for k in kern_ms) / len(kern_ms)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(fused_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tile_t, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
@@ -252,8 +315,13 @@ def run_ours(args):
     if rank == 0:
         tri_total, evaluated, refined, cubes = (float(agg[i].item()) for i in range(4))
         peak, peak_src = peaks()
-        fused_s = float(fused_t.item()) / 1e3
-        achieved = (evaluated / world) * 12.0 / fused_s / 1e9 if fused_s > 0 else 0.0   # per-GPU kernel
+        tile_s = float(tile_t.item()) / 1e3
+        achieved = (evaluated / world) * 12.0 / tile_s / 1e9 if tile_s > 0 else 0.0     # per-GPU kernel
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        if os.path.exists(tpath) and world == 1 and args.grid is None and args.model == 'gearlike':
+            with open(tpath) as fp:
+                traffic = json.load(fp).get('tile_eval_kernel_dram_bytes_per_launch')
         line = {
             'metric': 'Mpoints/s', 'value': n_points / (ms_per_step / 1e3) / 1e6, 'unit': 'Mpoints/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -269,16 +337,21 @@ def run_ours(args):
             'mpoints_evaluated_per_s': evaluated / (ms_per_step / 1e3) / 1e6,
             'batches': {'skipped': int(agg[4].item()), 'empty': int(agg[5].item()), 'nonempty': int(agg[6].item())},
             'samples_evaluated': int(evaluated), 'samples_refined_f64': int(refined), 'active_cubes': int(cubes),
-            'kernel_ms': {'fused_tile_kernel': float(fused_t.item()), 'skip_prepass+setup': sum(prepass_ms) / len(prepass_ms)},
-            'gpu_launches': 3 * args.steps,
+            'kernel_ms': {'tile_pipeline_A+B+C': float(fused_t.item()), 'skip_prepass+setup': sum(prepass_ms) / len(prepass_ms),
+                          'tile_eval_kernel(A)': sum(k[0] for k in kern_ms) / len(kern_ms),
+                          'refine_points_kernel(B)': sum(k[1] for k in kern_ms) / len(kern_ms),
+                          'extract_kernel(C)': sum(k[2] for k in kern_ms) / len(kern_ms)},
+            'gpu_launches': 5 * args.steps,
             'clocks': clocks,
             'e2e': {'value': n_points / e2e_s / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(8 * (len(X) + len(Y) + len(Z))),
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'fused_tile_kernel', 'peak_source': peak_src,
-                         'note': '12 algorithmic B per evaluated sample (north_star float3 stream); the fused kernel '
-                                 'generates samples in registers, so real DRAM traffic is only the triangle output; '
-                                 'the kernel is FP32/MUFU-issue bound, not HBM bound'},
+                         'traffic': traffic, 'kernel': 'tile_eval_body (jit_kernel, 148 x 1024)', 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': (evaluated / world) * 12.0,
+                         'note': 'dominant kernel of the step (tile evaluate + classify); 12 algorithmic B per evaluated '
+                                 'sample (north_star float3 accounting) over its CUDA-event duration; the kernel '
+                                 'generates its samples in registers, so its DRAM traffic (ncu, per launch) is only the '
+                                 'stored tile volumes; it is FP32/MUFU issue bound (ncu: 71 % issue-slot utilisation)'},
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_port(w, args.cpu_seconds)

@@ -92,13 +92,28 @@ int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n, double* d
  *   n_tri        triangles produced (or required, with SDFB200_E_CAPACITY)
  *   stats[6]     skipped, empty, nonempty batches (core.py:135-141), samples evaluated in f32,
  *                samples re-evaluated in f64, active cubes
- *   timings_ms[4] optional: skip pre-pass, fused eval+MC kernel, whole device section, D2H
+ *   timings_ms[7] optional, CUDA events on `stream`: [0] setup + skip pre-pass, [1] tile pipeline (A+B+C),
+ *                [2] whole device section, [3] statistics + result copy, [4] tile_eval kernel (A),
+ *                [5] float64 refinement kernel (B), [6] extraction kernel (C)
  */
 int sdfb200_generate(sdfb200_prog* prog,
                      const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
                      int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
                      float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
-                     double timings_ms[4], int device, void* stream);
+                     double timings_ms[7], int device, void* stream);
+
+/*
+ * Replaces: core.save() for '.stl' paths (sdf/core.py:152-156) = generate() followed by
+ * write_binary_stl's record building (sdf/stl.py:7-20): same as sdfb200_generate, but the result is
+ * the file payload -- tri records of 50 bytes {normal f32x3, 3 vertices f32x3, attr u16 = 0}, the
+ * normal computed on the device operation by operation like numpy (cross, norm, divide in float32).
+ * records_out: host (ideally sdfb200_host_alloc) or device, 50 * tri_capacity bytes.
+ */
+int sdfb200_generate_stl(sdfb200_prog* prog,
+                         const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
+                         int batch_size, int sparse, int precision, double tau,
+                         void* records_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
+                         double timings_ms[7], int device, void* stream);
 
 /*
  * Run-time specialisation check (needs no GPU): generate the straight-line evaluator of `prog` for

@@ -18,7 +18,7 @@ PREC = {'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}
 EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32', 'sdfb200_eval_f32_fast',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
-           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe']
+           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_generate_stl']
 
 
 class SdfB200Error(RuntimeError):
@@ -60,6 +60,8 @@ def lib():
     L.sdfb200_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.sdfb200_host_free.argtypes = [vp]
     L.sdfb200_host_free.restype = None
+    L.sdfb200_generate_stl.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl,
+                                       vp, i64, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
     _lib = L
@@ -167,12 +169,26 @@ class ProgramHandle:
                                         Z.ctypes.data, len(Z), batch_size, flags.ctypes.data, device, stream))
         return flags.reshape(nb)
 
+    def generate_stl(self, X, Y, Z, batch_size, sparse, precision, tau, records_out, capacity, device=0, stream=None):
+        """Like generate(), but fills 50-byte binary-STL records; returns (n_tri, stats[6], timings_ms[4])."""
+        n_tri = ctypes.c_int64(0)
+        stats = np.zeros(6, np.int64)
+        timings = np.zeros(7, np.float64)
+        rc = lib().sdfb200_generate_stl(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y), Z.ctypes.data, len(Z),
+                                        int(batch_size), int(bool(sparse)), PREC[precision], float(tau),
+                                        _ptr(records_out), int(capacity), ctypes.byref(n_tri), stats.ctypes.data,
+                                        timings.ctypes.data, device, stream)
+        if rc == E_CAPACITY:
+            raise CapacityError(rc, lib().sdfb200_last_error().decode(), n_tri.value)
+        _check(rc)
+        return n_tri.value, stats, timings
+
     def generate(self, X, Y, Z, batch_size, sparse, precision, tau, tri_out, capacity,
                  zb=(0, -1), device=0, stream=None):
         """Returns (n_tri, stats[6], timings_ms[4]); raises CapacityError with .needed."""
         n_tri = ctypes.c_int64(0)
         stats = np.zeros(6, np.int64)
-        timings = np.zeros(4, np.float64)
+        timings = np.zeros(7, np.float64)
         rc = lib().sdfb200_generate(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y),
                                     Z.ctypes.data, len(Z), int(batch_size), int(bool(sparse)),
                                     PREC[precision], float(tau), int(zb[0]), int(zb[1]), _ptr(tri_out), int(capacity),

@@ -180,7 +180,8 @@ def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='exa
     info = dict(triangles=n_tri, skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
                 evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]),
                 prepass_ms=float(timings[0]), fused_ms=float(timings[1]), device_ms=float(timings[2]),
-                d2h_ms=float(timings[3]), tau=tau, precision=precision)
+                d2h_ms=float(timings[3]), tile_eval_ms=float(timings[4]), refine_ms=float(timings[5]),
+                extract_ms=float(timings[6]), tau=tau, precision=precision)
     return out[:n_tri], info
 
 
@@ -228,14 +229,57 @@ def generate(
     return points
 
 
+def save_stl(path, sdf, step=None, bounds=None, samples=SAMPLES, workers=WORKERS, batch_size=BATCH_SIZE,
+             verbose=True, sparse=True, *, precision='exact', device=None):
+    """generate() + write_binary_stl() (core.py:152-156, stl.py:4-24) with the 50-byte records built on the
+    device: the file payload comes back in one page-locked copy and is written as is."""
+    import struct
+    start = time.time()
+    bounds, (dx, dy, dz), (X, Y, Z) = make_lattice(sdf, step, bounds, samples)
+    (x0, y0, z0), (x1, y1, z1) = bounds
+    if verbose:
+        print('min %g, %g, %g' % (x0, y0, z0))
+        print('max %g, %g, %g' % (x1, y1, z1))
+        print('step %g, %g, %g' % (dx, dy, dz))
+    (nbx, nby, nbz), num_samples = batch_counts(X, Y, Z, batch_size)
+    if verbose:
+        print('%d samples in %d batches with %d workers' % (num_samples, nbx * nby * nbz, workers))
+    h, key = program_handle(sdf)
+    X = np.ascontiguousarray(X, np.float64)
+    Y = np.ascontiguousarray(Y, np.float64)
+    Z = np.ascontiguousarray(Z, np.float64)
+    tau = mixed_tau(h.program, X, Y, Z)
+    dev = default_device() if device is None else device
+    hint_key = (key, len(X), len(Y), len(Z), batch_size, bool(sparse), (0, -1))
+    cap = _capacity_hint.get(hint_key, default_capacity(X, Y, Z))
+    bar = progress.Bar(nbx * nby * nbz, enabled=verbose)
+    while True:
+        rec = _abi.pinned_pool.take((cap * 50 + 3) // 4)
+        try:
+            n_tri, stats, _ = h.generate_stl(X, Y, Z, batch_size, sparse, precision, tau, rec, cap, device=dev)
+            break
+        except _abi.CapacityError as e:
+            cap = int(e.needed * 1.05) + 1024
+    _capacity_hint[hint_key] = int(n_tri * 1.05) + 1024
+    bar.done()
+    with open(path, 'wb') as fp:
+        fp.write(b'\x00' * 80)
+        fp.write(struct.pack('<I', n_tri))
+        fp.write(memoryview(rec).cast('B')[:n_tri * 50])
+    if verbose:
+        print('%d skipped, %d empty, %d nonempty' % (int(stats[0]), int(stats[1]), int(stats[2])))
+        print('%d triangles in %g seconds' % (n_tri, time.time() - start))
+    return n_tri
+
+
 def save(path, *args, **kwargs):
     """core.py:152-158."""
-    points = generate(*args, **kwargs)
     if path.lower().endswith('.stl'):
-        stl.write_binary_stl(path, points)
-    else:
-        mesh = _mesh(points)
-        mesh.write(path)
+        save_stl(path, *args, **kwargs)
+        return
+    points = generate(*args, **kwargs)
+    mesh = _mesh(points)
+    mesh.write(path)
 
 
 def _mesh(points):

@@ -731,6 +731,45 @@ __device__ __forceinline__ void batch_stats_body(const GridDesc& g, const unsign
 }
 
 // ---------------------------------------------------------------------------------------
+// binary-STL records (sdf/stl.py:4-24): per triangle {normal f32x3, vertices f32x9, attr u16 = 0},
+// 50 bytes, the normal computed in float32 operation by operation like numpy does
+// (np.cross, np.linalg.norm, divide) -- no FMA contraction, so the bytes equal the reference writer's.
+#define STL_THREADS 128
+
+__device__ __forceinline__ void stl_records_body(const float* __restrict__ tris, long long n, unsigned char* __restrict__ out) {
+    __shared__ __align__(16) unsigned short rec[STL_THREADS * 25];
+    const long long t0 = (long long)blockIdx.x * STL_THREADS;
+    const long long t = t0 + threadIdx.x;
+    if (t < n) {
+        float p[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p[k] = tris[t * 9 + k];
+        const float ax = __fsub_rn(p[3], p[0]), ay = __fsub_rn(p[4], p[1]), az = __fsub_rn(p[5], p[2]);
+        const float bx = __fsub_rn(p[6], p[0]), by = __fsub_rn(p[7], p[1]), bz = __fsub_rn(p[8], p[2]);
+        float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+        float ny = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+        float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+        const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+        nx = __fdiv_rn(nx, len); ny = __fdiv_rn(ny, len); nz = __fdiv_rn(nz, len);
+        unsigned short* r = &rec[threadIdx.x * 25];
+        const float v[12] = {nx, ny, nz, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const unsigned int b = __float_as_uint(v[k]);
+            r[2 * k] = (unsigned short)(b & 0xffffu);
+            r[2 * k + 1] = (unsigned short)(b >> 16);
+        }
+        r[24] = 0;
+    }
+    __syncthreads();
+    const long long cnt = min((long long)STL_THREADS, n - t0);
+    if (cnt <= 0) return;
+    const int n16 = (int)cnt * 25;                       // 16-bit units of this block, contiguous in the file
+    unsigned short* dst = reinterpret_cast<unsigned short*>(out + t0 * 50);
+    for (int i = threadIdx.x; i < n16; i += STL_THREADS) dst[i] = rec[i];
+}
+
+// ---------------------------------------------------------------------------------------
 // streamed point evaluation (SDF3.__call__): float3 AoS in HBM -> smem by TMA bulk copy
 
 #define STREAM_THREADS 256

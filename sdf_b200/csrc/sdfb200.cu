@@ -96,6 +96,9 @@ __global__ void batch_stats_kernel(const GridDesc g, const unsigned char* flags,
     batch_stats_body(g, flags, batch_tris, ctr);
 }
 
+__global__ void __launch_bounds__(STL_THREADS)
+stl_records_kernel(const float* tris, long long n, unsigned char* out) { stl_records_body(tris, n, out); }
+
 template <bool FAST>
 __global__ void __launch_bounds__(STREAM_THREADS)
 eval_stream_f32_kernel(const __grid_constant__ ProgramImage img, const float* xyz, long long n, float* out) {
@@ -123,7 +126,7 @@ struct DeviceCtx {
     float* vol = nullptr; size_t slot_cap = 0; uint2* tile_meta = nullptr; size_t meta_cap = 0;
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 enum JitKernel { JK_SKIP = 0, JK_TILE0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_REFINE = 8, JK_COUNT = 9 };
@@ -312,7 +315,7 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c.ctr, sizeof(Counters)));
     CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters)));
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
+    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
     prog->ctxs.reserve(16);
     prog->ctxs.push_back(c);
     *out = &prog->ctxs.back();
@@ -415,7 +418,7 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFree(c.axes); cudaFree(c.flags); cudaFree(c.active); cudaFree(c.batch_tris); cudaFree(c.ctr);
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
-        for (int i = 0; i < 4; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+        for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
     }
     for (auto& e : prog->jit) if (e.lib) cudaLibraryUnload(e.lib);
     delete prog;
@@ -574,10 +577,10 @@ static cudaError_t launch_tile_eval(int grid, cudaStream_t stream, const Program
 
 static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kept per round
 
-extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
-                                const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
-                                int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
-                                int64_t stats[6], double timings_ms[4], int device, void* stream_) {
+static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                         const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
+                         int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
+                         int64_t stats[6], double timings_ms[7], int device, void* stream_, unsigned char* stl_out) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
     if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
@@ -590,6 +593,13 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     // output placement: device pointer -> written in place; pinned host -> either written in place by
     // the kernel over PCIe (zero copy, overlaps the transfer with the computation) or staged + one async
     // copy; pageable host -> staged + copy
+    // STL mode: triangles stay in the device staging area, 50-byte records follow them there
+    unsigned char* drec = nullptr;
+    if (stl_out) {
+        rc = ensure_stage(c, (size_t)tri_capacity * 36 + 256 + (size_t)tri_capacity * 50 + 256); if (rc) return rc;
+        tri_out = (float*)c->stage;
+        drec = (unsigned char*)c->stage + (((size_t)tri_capacity * 36 + 255) & ~(size_t)255);
+    }
     const int out_kind = tri_out ? mem_kind(tri_out) : 1;
     static const bool zero_copy = [] { const char* e = getenv("SDFB200_ZEROCOPY"); return e ? atoi(e) != 0 : false; }();
     bool out_dev = (out_kind == 1) || (out_kind == 2 && zero_copy);
@@ -609,6 +619,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
     const long long lattice = (long long)nx * ny * nz;
     const bool big = lattice >= (1 << 21);
     Counters& h = *c->ctr_host;
+    bool ran_pipeline = false;
     if (total_b > 0) {
         const int pb = (int)((total_b + 127) / 128);
         // ---- skip pre-pass
@@ -636,6 +647,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
         }
         const unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
         if (n_work > 0) {
+            ran_pipeline = true;
             rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
             rc = grow(&c->tile_meta, &c->meta_cap, (size_t)round); if (rc) return rc;
             const size_t est_tiles = sync_free ? std::max<size_t>(256, round / 4) : round;     // most batches are skipped / empty
@@ -664,6 +676,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                     const int grid = (int)std::min<unsigned long long>(std::min<unsigned long long>(n_work, wb + round) - wb, (unsigned long long)c->sms);
                     // ---- (A) evaluate + classify
                     cudaError_t e;
+                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[4], stream));
                     if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
                         const bool f64 = precision == SDFB200_PREC_F64;
                         const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
@@ -687,6 +700,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                     else
                         e = launch_tile_eval<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
                     if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile_eval_kernel launch failed: %s", cudaGetErrorString(e));
+                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[5], stream));
                     // ---- (B) float64 refinement of the queued samples
                     if (precision == SDFB200_PREC_MIXED || precision == SDFB200_PREC_EXACT) {
                         const int rgrid = c->sms * 8;
@@ -700,9 +714,11 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
                             CUDA_TRY(cudaGetLastError());
                         }
                     }
+                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[6], stream));
                     // ---- (C) extraction
                     extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, stream>>>(g, L, c->ctr, c->batch_tris, dtri, cap);
                     CUDA_TRY(cudaGetLastError());
+                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[7], stream));
                 }
                 CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -743,22 +759,50 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
         stats[3] = (int64_t)h.pts_f32; stats[4] = (int64_t)h.pts_f64; stats[5] = (int64_t)h.active_cubes;
     }
     const bool overflow = tri_out && h.tri_cursor > (unsigned long long)tri_capacity;
-    if (tri_out && !out_dev && !overflow && h.tri_cursor > 0) {
+    if (stl_out && !overflow && h.tri_cursor > 0) {
+        const long long nt = (long long)h.tri_cursor;
+        stl_records_kernel<<<(unsigned)((nt + STL_THREADS - 1) / STL_THREADS), STL_THREADS, 0, stream>>>(dtri, nt, drec);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(stl_out, drec, (size_t)nt * 50, cudaMemcpyDefault, stream));
+    } else if (tri_out && !out_dev && !overflow && h.tri_cursor > 0) {
         CUDA_TRY(cudaMemcpyAsync(tri_out, dtri, (size_t)h.tri_cursor * 36, cudaMemcpyDeviceToHost, stream));
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (timings_ms) {
-        float a = 0, b = 0, d = 0;
+        float a = 0, b = 0, d = 0, ta = 0, tb = 0, tc = 0;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+        if (ran_pipeline) {
+            cudaEventElapsedTime(&ta, c->ev[4], c->ev[5]);
+            cudaEventElapsedTime(&tb, c->ev[5], c->ev[6]);
+            cudaEventElapsedTime(&tc, c->ev[6], c->ev[7]);
+        }
         timings_ms[0] = a; timings_ms[1] = b; timings_ms[2] = a + b; timings_ms[3] = d;
+        timings_ms[4] = ta; timings_ms[5] = tb; timings_ms[6] = tc;
     }
     if (overflow)
         return fail(SDFB200_E_CAPACITY, "triangle buffer too small: %lld needed, %lld given", (long long)h.tri_cursor,
                     (long long)tri_capacity);
     return 0;
+}
+
+extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
+                                int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
+                                int64_t stats[6], double timings_ms[7], int device, void* stream) {
+    return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, zb_begin, zb_end, tri_out,
+                         tri_capacity, n_tri, stats, timings_ms, device, stream, nullptr);
+}
+
+extern "C" int sdfb200_generate_stl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                    const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
+                                    void* records_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
+                                    double timings_ms[7], int device, void* stream) {
+    if (!records_out) return fail(SDFB200_E_INVALID, "generate_stl: records_out is NULL");
+    return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, nullptr, tri_capacity,
+                         n_tri, stats, timings_ms, device, stream, (unsigned char*)records_out);
 }
 
 extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {

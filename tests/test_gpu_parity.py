@@ -256,6 +256,26 @@ def test_edge_cases(sdf, ref):
     assert n_tri == ei.value.needed
 
 
+def test_save_stl_bytes_equal_the_reference_writer(sdf, ref, tmp_path):
+    """f.save('x.stl'): records built on the device are byte-identical to write_binary_stl (sdf/stl.py) applied
+    to the same triangles (compared as sets of 50-byte records: batch order is not preserved)."""
+    f = models.cfg_csg(sdf)
+    bounds, step = ((-1, -1, -1), (1, 1, 1)), 2.0 / 64
+    path = tmp_path / 'a.stl'
+    f.save(str(path), step=step, bounds=bounds, verbose=False)
+    raw = path.read_bytes()
+    n = int(np.frombuffer(raw[80:84], '<u4')[0])
+    assert raw[:80] == b'\x00' * 80 and len(raw) == 84 + 50 * n
+    pts = f.generate(step=step, bounds=bounds, verbose=False)
+    assert n * 3 == len(pts)
+    host = tmp_path / 'b.stl'
+    sdf.write_binary_stl(str(host), pts)
+    def sorted_records(buf):
+        rows = np.frombuffer(buf, np.uint8).reshape(-1, 50)
+        return rows[np.lexsort(rows.T[::-1])]
+    assert np.array_equal(sorted_records(raw[84:]), sorted_records(host.read_bytes()[84:]))
+
+
 def test_opaque_closure_is_callable_but_not_meshable(sdf):
     @sdf.sdf3
     def my_sphere(r):
