@@ -242,13 +242,28 @@ def run_ours(args):
     out = torch.empty((cap, 9), dtype=torch.float32, device='cuda')
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device='cuda')   # 768 MB > 126 MB L2
 
+    root_gather = None
+    if world > 1 and args.gather == 'root':
+        needs = torch.tensor([need], dtype=torch.int64, device='cuda')
+        dist.all_reduce(needs)
+        root_gather = multi.RootGather(int(needs.item() * 1.02) + 4096, local)
+
     def device_step():
+        if root_gather is not None:
+            n_loc, stats, timings, total = root_gather.run(h, X, Y, Z, BATCH, True, args.precision, tau, zb, stream=stream)
+            return n_loc, stats, timings, total
         n_tri, stats, timings = h.generate(X, Y, Z, BATCH, True, args.precision, tau, out, cap, zb=zb,
                                            device=local, stream=stream)
         gathered = None
         if world > 1:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
             gathered = multi.allgather_triangles(out[:n_tri])
+            g1.record()
+            gather_events.append((g0, g1))
         return n_tri, stats, timings, gathered
+
+    gather_events = []
 
     def barrier():
         if world > 1:
@@ -278,6 +293,7 @@ def run_ours(args):
     barrier()
     t1 = time.time()
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    gather_ms = [a.elapsed_time(b) for a, b in gather_events[-args.steps:]] if gather_events else []
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
     agg = torch.tensor([float(n_tri), float(stats_acc[3]), float(stats_acc[4]), float(stats_acc[5]),
                         float(stats_acc[0]), float(stats_acc[1]), float(stats_acc[2])], dtype=torch.float64, device='cuda')
@@ -298,7 +314,7 @@ def run_ours(args):
         t = time.perf_counter()
         if world > 1:
             pts, info = multi.generate_distributed(f, step=w['step'], bounds=w['bounds'], precision=args.precision,
-                                                   plan=plan, gather='host')
+                                                   plan=plan, gather=('root' if args.gather == 'root' else 'host'))
         else:
             pts, info = sdf_b200.generate(f, step=w['step'], bounds=w['bounds'], verbose=False,
                                           precision=args.precision, device=local, return_info=True)
@@ -332,7 +348,8 @@ def run_ours(args):
                                    % (w['model'], w['model'], w['n'], w['L']),
                        'points': n_points, 'precision': args.precision,
                        'l2': 'flushed between timed iterations (768 MB memset, outside the per-step events)',
-                       'parallelism': 'z-slab x%d' % world},
+                       'parallelism': 'z-slab x%d' % world,
+                       'gather': (args.gather if world > 1 else None)},
             'mtris_per_s': tri_total / (ms_per_step / 1e3) / 1e6, 'triangles': int(tri_total),
             'mpoints_evaluated_per_s': evaluated / (ms_per_step / 1e3) / 1e6,
             'batches': {'skipped': int(agg[4].item()), 'empty': int(agg[5].item()), 'nonempty': int(agg[6].item())},
@@ -342,6 +359,7 @@ def run_ours(args):
                           'refine_points_kernel(B)': sum(k[1] for k in kern_ms) / len(kern_ms),
                           'extract_kernel(C)': sum(k[2] for k in kern_ms) / len(kern_ms)},
             'gpu_launches': 5 * args.steps,
+            'allgather_ms_rank0': (sum(gather_ms) / len(gather_ms)) if gather_ms else None,
             'clocks': clocks,
             'e2e': {'value': n_points / e2e_s / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(8 * (len(X) + len(Y) + len(Z))),
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6},
@@ -372,6 +390,8 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-batches', type=int, default=4096)
+    ap.add_argument('--gather', default='root', choices=['root', 'allgather'],
+                    help='N>1: fused NVLink peer writes into rank 0 (default) or NCCL send/recv all-gather')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

@@ -116,6 +116,29 @@ int sdfb200_generate_stl(sdfb200_prog* prog,
                          double timings_ms[7], int device, void* stream);
 
 /*
+ * Fused multi-GPU gather (replaces nothing in the reference, which is single process): the ROOT rank
+ * creates one triangle buffer + two cursors in its HBM and hands the 64-byte CUDA-IPC handle to the other
+ * ranks (any transport; sdf_b200/multi.py uses torch.distributed), which map it.  Every rank then runs
+ * sdfb200_generate_shared on its Z-slab: the extraction kernel reserves its output range with a
+ * system-scope atomic on the root's cursor `which` and stores its triangles into the root's buffer over
+ * NVLink as coalesced peer writes -- no collective follows, only a barrier before the root reads the
+ * count.  Cursors ping-pong (`which` = step & 1): the root resets the next step's cursor while the
+ * current step runs.  n_tri_local = triangles this rank contributed.
+ */
+typedef struct sdfb200_shared sdfb200_shared;
+int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_shared** out, unsigned char handle_out[64]);
+int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_capacity, int device, sdfb200_shared** out);
+void sdfb200_shared_free(sdfb200_shared* s);
+void* sdfb200_shared_buffer(sdfb200_shared* s);
+int sdfb200_shared_reset(sdfb200_shared* s, int which, void* stream);
+int sdfb200_shared_count(sdfb200_shared* s, int which, int64_t* n, void* stream);
+int sdfb200_generate_shared(sdfb200_prog* prog,
+                            const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
+                            int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
+                            sdfb200_shared* dst, int which, int64_t* n_tri_local, int64_t stats[6],
+                            double timings_ms[7], int device, void* stream);
+
+/*
  * Run-time specialisation check (needs no GPU): generate the straight-line evaluator of `prog` for
  * kernel id 0 (skip pre-pass), 1..4 (fused tile kernel, precision 0..3), 5/6 (streamed float32
  * evaluator accurate/fast), 7 (streamed float64) and compile it with NVRTC for sm_100a.  The other

@@ -18,7 +18,9 @@ PREC = {'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}
 EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32', 'sdfb200_eval_f32_fast',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
-           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_generate_stl']
+           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_generate_stl',
+           'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
+           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared']
 
 
 class SdfB200Error(RuntimeError):
@@ -62,6 +64,16 @@ def lib():
     L.sdfb200_host_free.restype = None
     L.sdfb200_generate_stl.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl,
                                        vp, i64, ctypes.POINTER(i64), vp, vp, i32, vp]
+    L.sdfb200_shared_create.argtypes = [i64, i32, ctypes.POINTER(vp), vp]
+    L.sdfb200_shared_open.argtypes = [vp, i64, i32, ctypes.POINTER(vp)]
+    L.sdfb200_shared_free.argtypes = [vp]
+    L.sdfb200_shared_free.restype = None
+    L.sdfb200_shared_buffer.argtypes = [vp]
+    L.sdfb200_shared_buffer.restype = vp
+    L.sdfb200_shared_reset.argtypes = [vp, i32, vp]
+    L.sdfb200_shared_count.argtypes = [vp, i32, ctypes.POINTER(i64), vp]
+    L.sdfb200_generate_shared.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
+                                          vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
     _lib = L
@@ -130,6 +142,39 @@ class PinnedPool:
 pinned_pool = PinnedPool()
 
 
+class SharedOutput:
+    """One triangle buffer in the root GPU's memory that every rank's extraction kernel writes into
+    (include/sdfb200.h "fused multi-GPU gather").  ``handle`` (64 bytes) is what the root broadcasts."""
+
+    def __init__(self, capacity, device, handle=None):
+        self._h = ctypes.c_void_p()
+        self.capacity, self.device, self.owner = int(capacity), int(device), handle is None
+        if handle is None:
+            buf = (ctypes.c_ubyte * 64)()
+            _check(lib().sdfb200_shared_create(self.capacity, self.device, ctypes.byref(self._h), buf))
+            self.handle = bytes(buf)
+        else:
+            self.handle = bytes(handle)
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(self.handle)
+            _check(lib().sdfb200_shared_open(buf, self.capacity, self.device, ctypes.byref(self._h)))
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _lib is not None:
+            _lib.sdfb200_shared_free(h)
+
+    def buffer_ptr(self):
+        return lib().sdfb200_shared_buffer(self._h)
+
+    def reset(self, which, stream=None):
+        _check(lib().sdfb200_shared_reset(self._h, which, stream))
+
+    def count(self, which, stream=None):
+        n = ctypes.c_int64(0)
+        _check(lib().sdfb200_shared_count(self._h, which, ctypes.byref(n), stream))
+        return n.value
+
+
 class ProgramHandle:
     """Owns one sdfb200_prog (freed on garbage collection)."""
 
@@ -181,6 +226,18 @@ class ProgramHandle:
         if rc == E_CAPACITY:
             raise CapacityError(rc, lib().sdfb200_last_error().decode(), n_tri.value)
         _check(rc)
+        return n_tri.value, stats, timings
+
+    def generate_shared(self, X, Y, Z, batch_size, sparse, precision, tau, shared, which, zb=(0, -1), device=0,
+                        stream=None):
+        """This rank's slab, written straight into the root's shared buffer; returns (n_local, stats, timings)."""
+        n_tri = ctypes.c_int64(0)
+        stats = np.zeros(6, np.int64)
+        timings = np.zeros(7, np.float64)
+        _check(lib().sdfb200_generate_shared(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y), Z.ctypes.data, len(Z),
+                                             int(batch_size), int(bool(sparse)), PREC[precision], float(tau),
+                                             int(zb[0]), int(zb[1]), shared._h, int(which), ctypes.byref(n_tri),
+                                             stats.ctypes.data, timings.ctypes.data, device, stream))
         return n_tri.value, stats, timings
 
     def generate(self, X, Y, Z, batch_size, sparse, precision, tau, tri_out, capacity,

@@ -612,25 +612,35 @@ __device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc&
 #define EXTRACT_BLOCKS_PER_SM 3      // register cap 85/thread: the fp64 divides are latency bound, occupancy wins
 #endif
 
+#define EXTRACT_STAGE_TRIS 1024        // triangles of one CTA iteration staged in shared memory (36 KB)
+
 struct ExtractSmem {
     McTablesSmem mc;
+    float stage[EXTRACT_STAGE_TRIS * 9];
     unsigned int warp_sums[EXTRACT_THREADS / 32];
     unsigned long long tri_base;
     unsigned int n_active;
 };
 
+// `cursor`: where output ranges are reserved.  Normally &ctr->tri_cursor of this GPU; for the fused
+// multi-GPU gather it is a cursor in the ROOT GPU's memory (mapped through CUDA IPC) and `tri_out` is
+// the root's buffer: ranges are reserved with one system-scope atomic per CTA iteration over NVLink and
+// the triangles leave this GPU as fully coalesced peer stores straight from the staging area -- the
+// transfer overlaps the extraction math, no collective follows.
 template <int TS>
 __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists L, Counters* __restrict__ ctr,
                                              unsigned int* __restrict__ batch_tris, float* __restrict__ tri_out,
-                                             const unsigned long long tri_capacity) {
-    __shared__ ExtractSmem sm;
+                                             const unsigned long long tri_capacity,
+                                             unsigned long long* __restrict__ ext_cursor) {
+    extern __shared__ __align__(16) unsigned char extract_smem_raw[];
+    ExtractSmem& sm = *reinterpret_cast<ExtractSmem*>(extract_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     load_mc_tables(&sm.mc, tid, EXTRACT_THREADS);
     const unsigned int n = min(ctr->n_cubes, L.cube_cap);
     const unsigned int n_up = (n + EXTRACT_THREADS - 1) / EXTRACT_THREADS * EXTRACT_THREADS;
     unsigned int my_active = 0;
+    __syncthreads();
     for (unsigned int i0 = blockIdx.x * EXTRACT_THREADS; i0 < n_up; i0 += gridDim.x * EXTRACT_THREADS) {
-        __syncthreads();
         const unsigned int i = i0 + tid;
         double v[8];
         int tiling = -1;
@@ -672,41 +682,63 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             if (wi < warp) warp_off += s;
             total += s;
         }
-        if (tid == 0) sm.tri_base = total ? atomicAdd(&ctr->tri_cursor, (unsigned long long)total) : 0ull;
+        if (tid == 0) {
+            unsigned long long base = 0ull;
+            if (total) {
+                if (ext_cursor) {
+                    base = atomicAdd_system(ext_cursor, (unsigned long long)total);
+                    atomicAdd(&ctr->tri_cursor, (unsigned long long)total);          // local count (statistics)
+                } else {
+                    base = atomicAdd(&ctr->tri_cursor, (unsigned long long)total);
+                }
+            }
+            sm.tri_base = base;
+        }
         __syncthreads();
         if (nt != 0) atomicAdd(&batch_tris[meta.x], nt);
-        const unsigned long long first = sm.tri_base + warp_off + incl - nt;
-        if (nt != 0 && tri_out != nullptr && first + nt <= tri_capacity) {   // else: count only / overflow
-        // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
-        const double scx = __dsub_rn(g.xs[min(t.bx0 + 1, g.nx - 1)], g.xs[t.bx0]), ofx = g.xs[t.bx0];
-        const double scy = __dsub_rn(g.ys[min(t.by0 + 1, g.ny - 1)], g.ys[t.by0]), ofy = g.ys[t.by0];
-        const double scz = __dsub_rn(g.zs[min(t.bz0 + 1, g.nz - 1)], g.zs[t.bz0]), ofz = g.zs[t.bz0];
-        const int lx = t.oz + cz, ly = t.oy + cy, lz = t.ox + cx;             // Lewiner x,y,z (batch-local)
-        const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling]];
-        float* dst = tri_out + first * 9ull;
-        // every edge vertex of the cube is computed once (a cube with nt triangles touches about
-        // nt + 2 edges, not 3 nt) and already world-mapped; triangles then only copy
-        float ev[13][3];
-        unsigned int have = 0;
-        for (unsigned int tri = 0; tri < nt; ++tri, dst += 9, ed += 3) {
+        const unsigned int local_first = warp_off + incl - nt;
+        const unsigned long long gbase = sm.tri_base;
+        const bool writable = tri_out != nullptr && gbase + total <= tri_capacity;      // else: count only / overflow
+        const bool staged = total <= EXTRACT_STAGE_TRIS;
+        if (nt != 0 && writable) {
+            // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
+            const double scx = __dsub_rn(g.xs[min(t.bx0 + 1, g.nx - 1)], g.xs[t.bx0]), ofx = g.xs[t.bx0];
+            const double scy = __dsub_rn(g.ys[min(t.by0 + 1, g.ny - 1)], g.ys[t.by0]), ofy = g.ys[t.by0];
+            const double scz = __dsub_rn(g.zs[min(t.bz0 + 1, g.nz - 1)], g.zs[t.bz0]), ofz = g.zs[t.bz0];
+            const int lx = t.oz + cz, ly = t.oy + cy, lz = t.ox + cx;             // Lewiner x,y,z (batch-local)
+            const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling]];
+            float* dst = staged ? &sm.stage[local_first * 9u] : tri_out + (gbase + local_first) * 9ull;
+            // every edge vertex of the cube is computed once (a cube with nt triangles touches about
+            // nt + 2 edges, not 3 nt) and already world-mapped; triangles then only copy
+            float ev[13][3];
+            unsigned int have = 0;
+            for (unsigned int tri = 0; tri < nt; ++tri, dst += 9, ed += 3) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int e = ed[k];
-                if (!((have >> e) & 1u)) {
-                    float q[3];
-                    if (e < 12) mc_edge_vertex_fast(v, e, lx, ly, lz, q);
-                    else mc_edge_vertex(v, e, lx, ly, lz, q);
-                    // verts flipped to array-axis order (z,y,x)_L, then core.py:58-60
-                    ev[e][0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
-                    ev[e][1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
-                    ev[e][2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
-                    have |= 1u << e;
+                for (int k = 0; k < 3; ++k) {
+                    const int ee = ed[k];
+                    if (!((have >> ee) & 1u)) {
+                        float q[3];
+                        if (ee < 12) mc_edge_vertex_fast(v, ee, lx, ly, lz, q);
+                        else mc_edge_vertex(v, ee, lx, ly, lz, q);
+                        // verts flipped to array-axis order (z,y,x)_L, then core.py:58-60
+                        ev[ee][0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
+                        ev[ee][1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
+                        ev[ee][2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
+                        have |= 1u << ee;
+                    }
+                    float* o = dst + (2 - k) * 3;            // faces flipped (a,b,c) -> (c,b,a)
+                    o[0] = ev[ee][0]; o[1] = ev[ee][1]; o[2] = ev[ee][2];
                 }
-                float* o = dst + (2 - k) * 3;            // faces flipped (a,b,c) -> (c,b,a)
-                o[0] = ev[e][0]; o[1] = ev[e][1]; o[2] = ev[e][2];
             }
         }
+        __syncthreads();
+        if (writable && staged && total) {
+            // the CTA's triangles leave as one contiguous, fully coalesced run (local HBM or a peer over NVLink)
+            float* gdst = tri_out + gbase * 9ull;
+            const unsigned int nfl = total * 9u;
+            for (unsigned int k = tid; k < nfl; k += EXTRACT_THREADS) gdst[k] = sm.stage[k];
         }
+        __syncthreads();
     }
     // statistics
 #pragma unroll
@@ -718,8 +750,10 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
     }
 }
 
+// skipped / empty / nonempty exactly as core.generate counts them (core.py:135-141): "nonempty" = a
+// non-skipped batch that produced at least one triangle
 __device__ __forceinline__ void batch_stats_body(const GridDesc& g, const unsigned char* __restrict__ flags,
-                                   const unsigned int* __restrict__ batch_tris, Counters* __restrict__ ctr) {
+                                                 const unsigned int* __restrict__ batch_tris, Counters* __restrict__ ctr) {
     const int nzl = g.zb1 - g.zb0;
     const int total = g.nbx * g.nby * nzl;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -87,8 +87,8 @@ refine_points_kernel(const __grid_constant__ ProgramImage img, const GridDesc g,
 template <int TS>
 __global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_BLOCKS_PER_SM)
 extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
-               const unsigned long long tri_capacity) {
-    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity);
+               const unsigned long long tri_capacity, unsigned long long* ext_cursor) {
+    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor);
 }
 
 __global__ void batch_stats_kernel(const GridDesc g, const unsigned char* flags, const unsigned int* batch_tris,
@@ -580,7 +580,8 @@ static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kep
 static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                          const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
                          int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
-                         int64_t stats[6], double timings_ms[7], int device, void* stream_, unsigned char* stl_out) {
+                         int64_t stats[6], double timings_ms[7], int device, void* stream_, unsigned char* stl_out,
+                         unsigned long long* ext_cursor = nullptr) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
     if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
@@ -716,7 +717,15 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     }
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[6], stream));
                     // ---- (C) extraction
-                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, stream>>>(g, L, c->ctr, c->batch_tris, dtri, cap);
+                    {
+                        static bool attr_set[64] = {false};
+                        if (!attr_set[device]) {
+                            CUDA_TRY(cudaFuncSetAttribute(extract_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExtractSmem)));
+                            attr_set[device] = true;
+                        }
+                    }
+                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, sizeof(ExtractSmem), stream>>>(
+                        g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor);
                     CUDA_TRY(cudaGetLastError());
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[7], stream));
                 }
@@ -758,7 +767,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         stats[0] = h.skipped; stats[1] = h.empty; stats[2] = h.nonempty;
         stats[3] = (int64_t)h.pts_f32; stats[4] = (int64_t)h.pts_f64; stats[5] = (int64_t)h.active_cubes;
     }
-    const bool overflow = tri_out && h.tri_cursor > (unsigned long long)tri_capacity;
+    const bool overflow = tri_out && !ext_cursor && h.tri_cursor > (unsigned long long)tri_capacity;
     if (stl_out && !overflow && h.tri_cursor > 0) {
         const long long nt = (long long)h.tri_cursor;
         stl_records_kernel<<<(unsigned)((nt + STL_THREADS - 1) / STL_THREADS), STL_THREADS, 0, stream>>>(dtri, nt, drec);
@@ -803,6 +812,85 @@ extern "C" int sdfb200_generate_stl(sdfb200_prog* prog, const double* xs, int64_
     if (!records_out) return fail(SDFB200_E_INVALID, "generate_stl: records_out is NULL");
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, nullptr, tri_capacity,
                          n_tri, stats, timings_ms, device, stream, (unsigned char*)records_out);
+}
+
+// ---------------------------------------------------------------------------------------
+// shared output: one triangle buffer + cursors in the ROOT GPU's memory, mapped into the other ranks'
+// address spaces with CUDA IPC, written by their extraction kernels over NVLink (sdfb200_generate_shared)
+
+struct sdfb200_shared {
+    unsigned char* base = nullptr;      // [0,256): two cursors (ping-pong); [256, ...): triangles
+    int64_t capacity = 0;
+    int device = -1;
+    bool owner = false;
+};
+
+extern "C" int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_shared** out, unsigned char handle_out[64]) {
+    if (!out || !handle_out || tri_capacity <= 0) return fail(SDFB200_E_INVALID, "shared_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(device));
+    sdfb200_shared* s = new (std::nothrow) sdfb200_shared();
+    if (!s) return fail(SDFB200_E_INVALID, "out of host memory");
+    CUDA_TRY(cudaMalloc(&s->base, 256 + (size_t)tri_capacity * 36));
+    CUDA_TRY(cudaMemset(s->base, 0, 256));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->base));
+    memcpy(handle_out, &h, 64);
+    s->capacity = tri_capacity; s->device = device; s->owner = true;
+    *out = s;
+    return 0;
+}
+
+extern "C" int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_capacity, int device, sdfb200_shared** out) {
+    if (!out || !handle || tri_capacity <= 0) return fail(SDFB200_E_INVALID, "shared_open: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    sdfb200_shared* s = new (std::nothrow) sdfb200_shared();
+    if (!s) return fail(SDFB200_E_INVALID, "out of host memory");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->base = (unsigned char*)p; s->capacity = tri_capacity; s->device = device; s->owner = false;
+    *out = s;
+    return 0;
+}
+
+extern "C" void sdfb200_shared_free(sdfb200_shared* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->owner) cudaFree(s->base); else cudaIpcCloseMemHandle(s->base);
+    delete s;
+}
+
+extern "C" void* sdfb200_shared_buffer(sdfb200_shared* s) { return s ? (void*)(s->base + 256) : nullptr; }
+
+// owner only: zero cursor `which` (0/1) for a coming step
+extern "C" int sdfb200_shared_reset(sdfb200_shared* s, int which, void* stream) {
+    if (!s || !s->owner || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "shared_reset: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaMemsetAsync(s->base + 8 * which, 0, 8, (cudaStream_t)stream));
+    return 0;
+}
+
+// owner only: triangles accumulated under cursor `which` (synchronises `stream`)
+extern "C" int sdfb200_shared_count(sdfb200_shared* s, int which, int64_t* n, void* stream) {
+    if (!s || !s->owner || !n || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "shared_count: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, s->base + 8 * which, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *n = (int64_t)v;
+    return 0;
+}
+
+extern "C" int sdfb200_generate_shared(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                       const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
+                                       int zb_begin, int zb_end, sdfb200_shared* dst, int which, int64_t* n_tri_local,
+                                       int64_t stats[6], double timings_ms[7], int device, void* stream) {
+    if (!dst || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "generate_shared: bad argument");
+    return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, zb_begin, zb_end,
+                         (float*)(dst->base + 256), dst->capacity, n_tri_local, stats, timings_ms, device, stream, nullptr,
+                         (unsigned long long*)(dst->base + 8 * which));
 }
 
 extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {

@@ -80,19 +80,41 @@ _pinned = _PinnedTorchPool()
 
 
 def allgather_triangles(local, group=None, compact=True):
-    """Concatenate every rank's (n_r, 9) float32 triangle tensor on every rank.
+    """Concatenate every rank's (n_r, 9) float32 triangle tensor on every rank, in rank (= Z-slab) order.
 
-    Counts are gathered first, buffers are padded to the largest count for one
-    ``all_gather_into_tensor``; ``compact=True`` returns the dense (T, 9) tensor in rank (= Z-slab)
-    order, ``compact=False`` the padded buffer with ``(counts, stride)`` so that the caller can copy
-    the valid segments itself (the host gather does, straight into pinned memory)."""
+    Counts are exchanged first (one tiny all-gather); on CUDA every rank then sends its slab to every
+    peer and receives each peer's slab directly at its final offset of the dense output (one grouped
+    NCCL send/recv batch: no padding to the largest slab, no compaction copy afterwards).  On CPU
+    (gloo, the tests) the padded ``all_gather_into_tensor`` + compaction form is used."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
     counts = torch.empty(world, dtype=torch.int64, device=local.device)
     dist.all_gather_into_tensor(counts, n, group=group)
     counts = counts.cpu().tolist()
+    if local.is_cuda:
+        total = int(sum(counts))
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        out = torch.empty((total, 9), dtype=local.dtype, device=local.device)
+        local = local.contiguous()
+        ops = []
+        for r in range(world):
+            if r == rank:
+                continue
+            if counts[rank]:
+                ops.append(dist.P2POp(dist.isend, local, r, group))
+            if counts[r]:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r, group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if counts[rank]:
+            out[offs[rank]:offs[rank + 1]].copy_(local)
+        for q in reqs:
+            q.wait()
+        return out if compact else (out, counts, None)
     mx = max(max(counts), 1)
     padded = local
     if local.shape[0] != mx:
@@ -100,11 +122,59 @@ def allgather_triangles(local, group=None, compact=True):
         padded[:local.shape[0]] = local
     gathered = torch.empty((world * mx, 9), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded.contiguous(), group=group)
-    if not compact:
-        return gathered, counts, mx
     if all(c == mx for c in counts):
         return gathered
     return torch.cat([gathered[r * mx: r * mx + c] for r, c in enumerate(counts)])
+
+
+class RootGather:
+    """Fused gather to rank 0 (the B200 path): the extraction kernels of all ranks write into one buffer
+    in rank 0's HBM over NVLink (CUDA-IPC mapped, system-scope atomic cursor); no collective moves
+    triangles.  Per step: ``run()`` on every rank, then ONE barrier; rank 0 then owns ``total`` triangles
+    at ``view()``.  Two cursors ping-pong so that the reset of the next step's cursor is off the path."""
+
+    def __init__(self, capacity, device, group=None):
+        import torch.distributed as dist
+        from . import _abi
+        self.group, self.device = group, device
+        self.rank = dist.get_rank(group)
+        self.capacity = int(capacity)
+        box = [None]
+        if self.rank == 0:
+            self.shared = _abi.SharedOutput(self.capacity, device)
+            box[0] = self.shared.handle
+        dist.broadcast_object_list(box, src=0, group=group)
+        if self.rank != 0:
+            self.shared = _abi.SharedOutput(self.capacity, device, handle=box[0])
+        self.step = 0
+        if self.rank == 0:
+            self.shared.reset(0)
+            self.shared.reset(1)
+        dist.barrier(group)
+
+    def run(self, handle, X, Y, Z, batch_size, sparse, precision, tau, zb, stream=None):
+        """One step on this rank; returns (n_local, stats, timings, total) -- total only on rank 0."""
+        import torch
+        import torch.distributed as dist
+        which = self.step & 1
+        if self.rank == 0:
+            self.shared.reset(which ^ 1, stream)          # next step's cursor: nobody touches it now
+        n_local, stats, timings = handle.generate_shared(X, Y, Z, batch_size, sparse, precision, tau, self.shared,
+                                                         which, zb=zb, device=self.device, stream=stream)
+        dist.barrier(self.group)                          # every peer's kernel (and its NVLink stores) has retired
+        total = self.shared.count(which, stream) if self.rank == 0 else None
+        self.step += 1
+        if total is not None and total > self.capacity:
+            raise RuntimeError('shared triangle buffer too small: %d needed, %d given' % (total, self.capacity))
+        return n_local, stats, timings, total
+
+    def view(self, total):
+        """(total, 9) float32 CUDA tensor over the root's buffer (rank 0 only)."""
+        import torch
+        ptr = self.shared.buffer_ptr()
+        iface = {'shape': (int(total), 9), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+        holder = type('CudaView', (), {'__cuda_array_interface__': iface})()
+        return torch.as_tensor(holder, device=torch.device('cuda', self.device))
 
 
 def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batch_size=core.BATCH_SIZE,
@@ -128,6 +198,25 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
         else:
             plan = plan_slabs(sdf, X, Y, Z, batch_size, world, device=device)
     zb = plan[rank]
+    if gather == 'root' and compute is None and world > 1:
+        # fused gather: every rank's extraction kernel writes into rank 0's buffer over NVLink
+        dev = core.default_device() if device is None else device
+        h, key = core.program_handle(sdf)
+        Xc, Yc, Zc = (np.ascontiguousarray(a, np.float64) for a in (X, Y, Z))
+        tau = core.mixed_tau(h.program, Xc, Yc, Zc)
+        need, _ = _count(sdf, Xc, Yc, Zc, batch_size, sparse, precision, zb, dev)
+        rg = _root_gather(need, dev, group)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n_local, stats, timings, total = rg.run(h, Xc, Yc, Zc, batch_size, sparse, precision, tau, zb, stream=stream)
+        info = dict(triangles=n_local, skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
+                    evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]), zb=zb, rank=rank,
+                    world=world, triangles_total=total)
+        if rank != 0:
+            return np.zeros((0, 3), np.float32), info
+        t, arr = _pinned.take(total * 9)
+        t[:total * 9].copy_(rg.view(total).reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return arr[:total * 9].reshape(-1, 3), info
     if compute is not None:
         tris, info = compute(zb)
         local = torch.as_tensor(np.ascontiguousarray(tris, np.float32).reshape(-1, 9))
@@ -140,15 +229,11 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
         local = tri
     info = dict(info, zb=zb, rank=rank, world=world)
     if gather == 'host' and world > 1 and local.is_cuda:
-        # padded all-gather, then the valid segment of every rank straight into one pinned array
-        gathered, counts, mx = allgather_triangles(local, group, compact=False)
-        total = int(sum(counts))
+        # dense gather on the device, then one copy into a pinned (pooled) host array
+        allt = allgather_triangles(local, group)
+        total = int(allt.shape[0])
         t, arr = _pinned.take(total * 9)
-        off = 0
-        for r, c in enumerate(counts):
-            if c:
-                t[off * 9:(off + c) * 9].copy_(gathered[r * mx:r * mx + c].reshape(-1), non_blocking=True)
-            off += c
+        t[:total * 9].copy_(allt.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(local.device).synchronize()
         info['triangles_total'] = total
         return arr[:total * 9].reshape(-1, 3), info
@@ -160,6 +245,22 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
     if gather == 'device':
         return allt, info
     return allt.cpu().numpy().reshape(-1, 3), info
+
+
+_root_gathers = {}
+
+
+def _root_gather(local_need, dev, group):
+    """RootGather sized for the sum of the ranks' needs (cached: creating one maps IPC memory)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(local_need)], dtype=torch.int64, device=torch.device('cuda', dev))
+    dist.all_reduce(t, group=group)
+    cap = 1 << max(16, (int(t.item()) - 1).bit_length())
+    key = (cap, dev, id(group))
+    if key not in _root_gathers:
+        _root_gathers[key] = RootGather(cap, dev, group)
+    return _root_gathers[key]
 
 
 _count_cache = {}

@@ -31,6 +31,13 @@ def main():
         ok = ok and good
         print('rank %d %s: slab %s local %d total %d single %d identical=%s' % (
             rank, name, info['zb'], info['triangles'], info['triangles_total'], info1['triangles'], good), flush=True)
+        # fused gather to rank 0 (NVLink peer writes from the extraction kernels)
+        rpts, rinfo = multi.generate_distributed(f, step=step, bounds=bounds, gather='root', device=local)
+        if rank == 0:
+            rrep = compare_soups(rpts, one)
+            rgood = rrep['count_equal'] and rrep['exact_triangles'] == rrep['n_ref']
+            ok = ok and rgood
+            print('rank 0 %s: ROOT gather total %d identical=%s' % (name, rinfo['triangles_total'], rgood), flush=True)
     t = torch.tensor([1 if ok else 0], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
