@@ -1,7 +1,4 @@
-"""Constants re-exported to user scripts (reference sdf/util.py:1-6)."""
-import math
+"""Names that user scripts pick up through ``from sdf import *`` (reference sdf/util.py:1-6)."""
+from math import degrees, pi, radians  # noqa: F401
 
-pi = math.pi
-
-degrees = math.degrees
-radians = math.radians
+__all__ = ['pi', 'degrees', 'radians']
