@@ -148,6 +148,19 @@ int sdfb200_generate_shared(sdfb200_prog* prog,
 int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes);
 
 /*
+ * Diagnostic (needs no GPU): how the specialised tile kernel of `precision` (0..3) groups its samples.
+ * A thread evaluates `samples_per_thread` consecutive lattice samples along axis `share_axis`
+ * (0 = x, 1 = y, 2 = z; -1 = flat mapping), which share the other two coordinates, so every
+ * sub-expression of the tree that does not depend on that axis -- a cylinder along it, an extruded
+ * 2-D profile, a circular array around it -- is evaluated once per group.  `invariant_fraction` is the
+ * estimated share of the evaluation work that does not depend on the best axis.  The grouping only
+ * affects speed, never results.  Replaces nothing in the reference (its numpy closures evaluate every
+ * node at every point of the batch, sdf/core.py:49-50).
+ */
+int sdfb200_jit_plan(sdfb200_prog* prog, int precision, int* share_axis, int* samples_per_thread,
+                     double* invariant_fraction);
+
+/*
  * Replaces: nothing in the reference (diagnostic / load balancing): the skip
  * flags of every batch (1 = skipped), X-major / Z-fastest batch order of
  * core.py:119.  flags: host pointer, nbx*nby*nbz bytes.

@@ -18,7 +18,7 @@ PREC = {'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}
 EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32', 'sdfb200_eval_f32_fast',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
-           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_generate_stl',
+           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
            'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
            'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared']
 
@@ -75,6 +75,7 @@ def lib():
     L.sdfb200_generate_shared.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
                                           vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
+    L.sdfb200_jit_plan.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(dbl)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
     _lib = L
     return L
@@ -200,6 +201,12 @@ class ProgramHandle:
         n = ctypes.c_int64(0)
         _check(lib().sdfb200_jit_probe(self._h, kernel, ctypes.byref(n)))
         return n.value
+
+    def jit_plan(self, precision=3):
+        """(share axis, samples per thread, invariant fraction) of the specialised tile kernel (no GPU needed)."""
+        ax, n, fr = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
+        _check(lib().sdfb200_jit_plan(self._h, precision, ctypes.byref(ax), ctypes.byref(n), ctypes.byref(fr)))
+        return ax.value, n.value, fr.value
 
     def eval_f32_fast(self, xyz, out, n, device=0, stream=None):
         _check(lib().sdfb200_eval_f32_fast(self._h, _ptr(xyz), n, _ptr(out), device, stream))

@@ -426,22 +426,73 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
             }
         } else {
             constexpr int N = EV::kN;
-            for (int base = 0; base < npts; base += THREADS * N) {
-                float x[N], y[N], z[N], d[N];
+            constexpr int SH = EV::kShare;
+            if (SH < 0) {
+                for (int base = 0; base < npts; base += THREADS * N) {
+                    float x[N], y[N], z[N], d[N];
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    int idx = base + k * THREADS + tid;
-                    if (idx >= npts) idx = npts - 1;
-                    const unsigned int ix = dpyz.div(idx), rem = idx - ix * pyz, iy = dpz.div(rem), iz = rem - iy * pz;
-                    x[k] = sm.axf[0][ix]; y[k] = sm.axf[1][iy]; z[k] = sm.axf[2][iz];
+                    for (int k = 0; k < N; ++k) {
+                        int idx = base + k * THREADS + tid;
+                        if (idx >= npts) idx = npts - 1;
+                        const unsigned int ix = dpyz.div(idx), rem = idx - ix * pyz, iy = dpz.div(rem), iz = rem - iy * pz;
+                        x[k] = sm.axf[0][ix]; y[k] = sm.axf[1][iy]; z[k] = sm.axf[2][iz];
+                    }
+                    ev.template run<float, N, EXACT>(x, y, z, d);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const int idx = base + k * THREADS + tid;
+                        if (idx < npts) {
+                            sm.tile[idx] = d[k];
+                            vmin = fminf(vmin, d[k]); vmax = fmaxf(vmax, d[k]);
+                        }
+                    }
                 }
-                ev.template run<float, N, EXACT>(x, y, z, d);
+            } else {
+                // Axis sharing: a thread's N samples are consecutive along lattice axis SH and share the
+                // other two coordinates -- literally the same registers -- so that in the generated
+                // straight-line evaluator every sub-expression that does not depend on axis SH (a
+                // cylinder along it, an extruded 2-D profile, a circular array around it ...) is
+                // computed ONCE for the N samples by the compiler's common-subexpression elimination.
+                // The host picks SH from a dependency analysis of the program (sdfb200.cu: share_axis).
+                const int pa = SH == 0 ? px : (SH == 1 ? py : pz);
+                const int nrest = SH == 0 ? (int)pyz : (SH == 1 ? px * pz : px * py);
+                const int ngroups = ((pa + N - 1) / N) * nrest;
+                const int astride = SH == 0 ? (int)pyz : (SH == 1 ? pz : 1);
+                FastDiv drest, dfast;
+                drest.init((unsigned int)nrest);
+                dfast.init((unsigned int)(SH == 2 ? py : pz));
+                for (int gb = 0; gb < ngroups; gb += THREADS) {
+                    int gi = gb + tid;
+                    const bool on = gi < ngroups;
+                    if (!on) gi = ngroups - 1;
+                    const unsigned int ga = drest.div(gi), rest = gi - ga * nrest;
+                    const unsigned int hi = dfast.div(rest), lo = rest - hi * dfast.d;
+                    const int ia0 = (int)ga * N;
+                    float x[N], y[N], z[N], d[N];
+                    int idx0;
+                    if (SH == 2) {                    // rest = ix * py + iy
+                        const float xv = sm.axf[0][hi], yv = sm.axf[1][lo];
+                        idx0 = (int)rest * pz + ia0;
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const int idx = base + k * THREADS + tid;
-                    if (idx < npts) {
-                        sm.tile[idx] = d[k];
-                        vmin = fminf(vmin, d[k]); vmax = fmaxf(vmax, d[k]);
+                        for (int k = 0; k < N; ++k) { x[k] = xv; y[k] = yv; z[k] = sm.axf[2][min(ia0 + k, pz - 1)]; }
+                    } else if (SH == 1) {             // rest = ix * pz + iz
+                        const float xv = sm.axf[0][hi], zv = sm.axf[2][lo];
+                        idx0 = (int)(hi * pyz) + ia0 * pz + (int)lo;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) { x[k] = xv; z[k] = zv; y[k] = sm.axf[1][min(ia0 + k, py - 1)]; }
+                    } else {                          // rest = iy * pz + iz
+                        const float yv = sm.axf[1][hi], zv = sm.axf[2][lo];
+                        idx0 = ia0 * (int)pyz + (int)rest;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) { y[k] = yv; z[k] = zv; x[k] = sm.axf[0][min(ia0 + k, px - 1)]; }
+                    }
+                    ev.template run<float, N, EXACT>(x, y, z, d);
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        if (on && ia0 + k < pa) {
+                            sm.tile[idx0 + k * astride] = d[k];
+                            vmin = fminf(vmin, d[k]); vmax = fmaxf(vmax, d[k]);
+                        }
                     }
                 }
             }

@@ -107,7 +107,8 @@ template <> struct MathP<float, true> {
     static __device__ __forceinline__ T atan2_(T y, T x) {
         const T ax = fabsf(x), ay = fabsf(y);
         const T mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-        const T t = (mx > 0.0f) ? __fdividef(mn, mx) : 0.0f;
+        const T tq = __fdividef(mn, mx);                   // unconditional: keeps the function branch-free, so that
+        const T t = (mx > 0.0f) ? tq : 0.0f;               // identical calls merge (tile kernel, axis sharing)
         const T q = t * t;
         // near-minimax fit of atan(t)/t in q = t*t on [0,1], max error 8.9e-8
         T p = -4.7804095924e-03f;
@@ -174,6 +175,25 @@ struct SdfOps {
     static __device__ __forceinline__ T m_len2(T u, T v) { return M::sqrt_(u * u + v * v); }
     static __device__ __forceinline__ T m_len3(T u, T v, T w) { return M::sqrt_(u * u + v * v + w * w); }
     static __device__ __forceinline__ T m_div(T u, T v) { return M::div(u, v); }
+    // u*a + v*b + w*c.  In the generated float32 throughput code (FAST, constants are literals) a term
+    // whose coefficient is zero relative to `scale` (below 2^-28 of it: 1/16 ulp of the sum) is left
+    // out, so that the result does not depend on that input at all -- what lets the tile kernel's
+    // axis sharing see through axis-aligned rotations and planes (cos(pi/2) = 6e-17 is not 0.0).
+    // Everything that can reach the output is re-evaluated without this shortcut.
+    static __device__ __forceinline__ T dot3z(T u, T v, T w, T a, T b, T c, T scale) {
+#ifdef __CUDACC_RTC__
+        if (FAST) {
+            const T eps = scale * T(3.7252902984619141e-09);
+            const bool ka = m_abs(a) > eps, kb = m_abs(b) > eps, kc = m_abs(c) > eps;
+            T acc = T(0);
+            if (ka) acc = u * a;
+            if (kb) acc = ka ? acc + v * b : v * b;
+            if (kc) acc = (ka || kb) ? acc + w * c : w * c;
+            return acc;
+        }
+#endif
+        return u * a + v * b + w * c;
+    }
 
     static __device__ __forceinline__ void SPHERE(State& st, const T* c, const int a) {
         SDF_BIND_STATE;                               // d3.py:94-95
@@ -184,7 +204,8 @@ struct SdfOps {
     static __device__ __forceinline__ void PLANE(State& st, const T* c, const int a) {
         SDF_BIND_STATE;                                // d3.py:101-102
         const T nx = c[0], ny = c[1], nz = c[2], px = c[3], py = c[4], pz = c[5];
-        SDF_FOR_N d[i] = (px - x[i]) * nx + (py - y[i]) * ny + (pz - z[i]) * nz;
+        const T sc = m_max(m_abs(nx), m_max(m_abs(ny), m_abs(nz)));
+        SDF_FOR_N d[i] = dot3z(px - x[i], py - y[i], pz - z[i], nx, ny, nz, sc);
         }
 
     static __device__ __forceinline__ void BOX(State& st, const T* c, const int a) {
@@ -392,11 +413,13 @@ struct SdfOps {
         SDF_BIND_STATE;                               // d3.py:358-359  (p @ M)
         const T m00 = c[0], m01 = c[1], m02 = c[2], m10 = c[3], m11 = c[4], m12 = c[5],
                 m20 = c[6], m21 = c[7], m22 = c[8];
+        const T sc = m_max(m_max(m_max(m_abs(m00), m_abs(m01)), m_max(m_abs(m02), m_abs(m10))),
+                           m_max(m_max(m_abs(m11), m_abs(m12)), m_max(m_abs(m20), m_max(m_abs(m21), m_abs(m22)))));
         SDF_FOR_N {
             const T px = x[i], py = y[i], pz = z[i];
-            x[i] = px * m00 + py * m10 + pz * m20;
-            y[i] = px * m01 + py * m11 + pz * m21;
-            z[i] = px * m02 + py * m12 + pz * m22;
+            x[i] = dot3z(px, py, pz, m00, m10, m20, sc);
+            y[i] = dot3z(px, py, pz, m01, m11, m21, sc);
+            z[i] = dot3z(px, py, pz, m02, m12, m22, sc);
         }
         }
 
@@ -613,9 +636,10 @@ struct SdfOps {
         const T k = m_sqrt(T(3));
         SDF_FOR_N {
             T px = m_abs(x[i]) - T(1), py = y[i] + m_div(T(1), k);
-            if (px + k * py > T(0)) {
+            {   // both candidates computed, then selected: no branch, so identical calls can merge (axis sharing)
                 const T qx = m_div(px - k * py, T(2)), qy = m_div(-k * px - py, T(2));
-                px = qx; py = qy;
+                const bool fold = px + k * py > T(0);
+                px = fold ? qx : px; py = fold ? qy : py;
             }
             px = px - m_min(m_max(px, T(-2)), T(0));
             d[i] = -m_len2(px, py) * m_sign(py);
@@ -670,7 +694,8 @@ struct SdfOps {
         const T b = m_sqrt(r * r - dd * dd);
         SDF_FOR_N {
             const T px = m_abs(x[i]), py = m_abs(y[i]);
-            d[i] = ((py - b) * dd > px * b) ? m_len2(px, py - b) : m_len2(px + dd, py) - r;
+            const T va = m_len2(px, py - b), vb = m_len2(px + dd, py) - r;      // both arms, then a select (no branch)
+            d[i] = ((py - b) * dd > px * b) ? va : vb;
         }
     }
     // ------------------------------------------------------------------ 2-D <-> 3-D
@@ -837,6 +862,7 @@ __device__ __forceinline__ void sdf_interp(const ProgramImage& img, T (&x)[N], T
 // run-time-generated evaluator (struct SpecEval in the JIT translation unit) has the same shape.
 struct InterpEval {
     static constexpr int kN = 2;             // samples per thread in the tile kernel
+    static constexpr int kShare = -1;        // no axis sharing: nothing to gain without straight-line code
     const ProgramImage* img;
     template <typename T, int N, bool FAST>
     __device__ __forceinline__ void run(T (&x)[N], T (&y)[N], T (&z)[N], T (&d)[N]) const {

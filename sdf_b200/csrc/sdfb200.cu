@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <math.h>
 #include <new>
 #include <mutex>
@@ -113,6 +115,8 @@ eval_stream_f64_kernel(const __grid_constant__ ProgramImage img, const double* x
 // ---------------------------------------------------------------------------------------
 // host side
 
+static constexpr int kMaxPipe = 16;
+
 struct DeviceCtx {
     int device = -1;
     int sms = 0;
@@ -127,7 +131,18 @@ struct DeviceCtx {
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // pipelined host output: the triangles of round k travel over PCIe while round k+1 computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pev[kMaxPipe] = {};
 };
+
+// Rounds the work list is cut into when the triangles go to HOST memory (env SDFB200_PIPE, 1 = one
+// round + one copy at the end).  Read on every call so tests can switch it.
+static int pipe_rounds() {
+    const char* e = getenv("SDFB200_PIPE");
+    const int v = e ? atoi(e) : 4;
+    return v < 1 ? 1 : (v > kMaxPipe ? kMaxPipe : v);
+}
 
 enum JitKernel { JK_SKIP = 0, JK_TILE0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_REFINE = 8, JK_COUNT = 9 };
 
@@ -147,6 +162,7 @@ struct sdfb200_prog {
     std::mutex lock;
     std::vector<DeviceCtx> ctxs;
     JitEntry jit[JK_COUNT];
+    int plan_share[JK_COUNT] = {}, plan_n[JK_COUNT] = {};      // grouping the last compile of each kernel chose
     std::string jit_log;        // last NVRTC failure, if any
 };
 
@@ -206,11 +222,139 @@ static std::string csrc_dir() {
     return "csrc";
 }
 
+// Which lattice axis the tile kernel's per-thread sample group should run along (tile_eval_body, "axis
+// sharing").  A dependency mask over the lattice axes (bit 0 = x, 1 = y, 2 = z) is pushed through the
+// program for every machine register; an operation whose inputs do not depend on axis A is computed
+// once per group when the group runs along A.  Costs are rough instruction counts of the float32
+// throughput path -- the choice only affects speed, never results.  Returns -1 when no axis would save
+// a worthwhile share of the work.
+static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr) {
+    struct Masks {
+        unsigned x = 1, y = 2, z = 4, d = 0, s0 = 0;
+        unsigned r[SDF_MAX_PSLOTS][3] = {};
+        unsigned vs[SDF_MAX_VSTACK + 1] = {};
+    } m;
+    double inv[3] = {0, 0, 0}, total = 0;
+    auto piece = [&](double cost, unsigned mask) {
+        total += cost;
+        for (int ax = 0; ax < 3; ++ax) if (!((mask >> ax) & 1u)) inv[ax] += cost;
+    };
+    auto push = [&](int a) { if (a > 0) m.vs[a - 1] = m.s0; };
+    auto pop = [&](int a) { if (a > 0) m.s0 = m.vs[a - 1]; };
+    const double kZero = 3.7252902984619141e-09;        // 2^-28: coefficients the FAST path drops (sdf_ops.cuh: dot3z)
+    for (size_t i = 0; i < p->code.size(); ++i) {
+        const uint32_t w = p->code[i];
+        const int op = (int)(w & 0xff), a = (int)((w >> 8) & 0xff);
+        const double* c = p->consts.data() + (w >> 16);
+        const unsigned xyz = m.x | m.y | m.z, xy = m.x | m.y;
+        auto nz = [&](double v, double scale) { return fabs(v) > kZero * scale; };
+        switch (op) {
+            case OP_SPHERE: piece(8, xyz); m.d = xyz; break;
+            case OP_PLANE: {
+                const double sc = std::max(fabs(c[0]), std::max(fabs(c[1]), fabs(c[2])));
+                const unsigned mk = (nz(c[0], sc) ? m.x : 0u) | (nz(c[1], sc) ? m.y : 0u) | (nz(c[2], sc) ? m.z : 0u);
+                piece(3, mk); m.d = mk; break;
+            }
+            case OP_BOX: case OP_ROUNDED_BOX:
+                piece(2, m.x); piece(2, m.y); piece(2, m.z); piece(12, xyz); m.d = xyz; break;
+            case OP_WIREFRAME_BOX: piece(5, m.x); piece(5, m.y); piece(5, m.z); piece(40, xyz); m.d = xyz; break;
+            case OP_TORUS: piece(5, xy); piece(5, xyz); m.d = xyz; break;
+            case OP_CAPSULE: piece(22, xyz); m.d = xyz; break;
+            case OP_CYLINDER: piece(5, xy); m.d = xy; break;
+            case OP_CAPPED_CYLINDER: piece(35, xyz); m.d = xyz; break;
+            case OP_ROUNDED_CYLINDER: piece(5, xy); piece(2, m.z); piece(12, xyz); m.d = xyz; break;
+            case OP_CAPPED_CONE: piece(45, xyz); m.d = xyz; break;
+            case OP_ROUNDED_CONE: piece(5, xy); piece(20, xyz); m.d = xyz; break;
+            case OP_ELLIPSOID: piece(5, m.x); piece(5, m.y); piece(5, m.z); piece(14, xyz); m.d = xyz; break;
+            case OP_PYRAMID: piece(3, xy); piece(40, xyz); m.d = xyz; break;
+            case OP_TETRAHEDRON: piece(4, xy); piece(5, xyz); m.d = xyz; break;
+            case OP_OCTAHEDRON: piece(1, m.x); piece(1, m.y); piece(1, m.z); piece(3, xyz); m.d = xyz; break;
+            case OP_DODECAHEDRON: case OP_ICOSAHEDRON:
+                piece(3, m.x); piece(3, m.y); piece(3, m.z); piece(14, xyz); m.d = xyz; break;
+            case OP_TRANSLATE: piece(1, m.x); piece(1, m.y); piece(1, m.z); break;
+            case OP_SCALE_P: piece(2, m.x); piece(2, m.y); piece(2, m.z); break;
+            case OP_ROTATE: {
+                double sc = 0;
+                for (int k = 0; k < 9; ++k) sc = std::max(sc, fabs(c[k]));
+                unsigned out[3];
+                for (int col = 0; col < 3; ++col) {        // p @ M: out[col] = sum_row p[row] * M[row][col]
+                    const unsigned in[3] = {m.x, m.y, m.z};
+                    unsigned mk = 0; int terms = 0;
+                    for (int row = 0; row < 3; ++row) if (nz(c[3 * row + col], sc)) { mk |= in[row]; ++terms; }
+                    piece(terms, mk); out[col] = mk;
+                }
+                m.x = out[0]; m.y = out[1]; m.z = out[2]; break;
+            }
+            case OP_TWIST: piece(10, m.z); piece(4, xyz); m.x = m.y = xyz; break;
+            case OP_BEND: piece(10, m.x); piece(4, xy); m.x = m.y = xy; break;
+            case OP_ELONGATE: push(a); piece(3, m.x); piece(3, m.y); piece(3, m.z); piece(3, xyz); m.s0 = xyz; break;
+            case OP_CIRCULAR_PRE:
+                piece(55, xy);
+                m.r[a][0] = xy; m.r[a][1] = xy; m.r[a][2] = m.z;
+                m.x = m.y = xy; break;
+            case OP_REPEAT_CELL: piece(5, m.x); piece(5, m.y); piece(5, m.z); break;
+            case OP_MULC: case OP_NEGATE: case OP_ADDC: piece(1, m.d); break;
+            case OP_SHELL: piece(2, m.d); break;
+            case OP_ADD_POP: case OP_UNION: case OP_DIFFERENCE: case OP_INTERSECTION:
+                piece(1, m.d | m.s0); m.d |= m.s0; pop(a); break;
+            case OP_BLEND: piece(3, m.d | m.s0); m.d |= m.s0; pop(a); break;
+            case OP_UNION_K: case OP_DIFFERENCE_K: case OP_INTERSECTION_K:
+                piece(12, m.d | m.s0); m.d |= m.s0; pop(a); break;
+            case OP_CIRCLE: piece(6, xy); m.d = xy; break;
+            case OP_LINE2: piece(2, xy); m.d = xy; break;
+            case OP_RECTANGLE: piece(2, m.x); piece(2, m.y); piece(8, xy); m.d = xy; break;
+            case OP_ROUNDED_RECTANGLE: piece(16, xy); m.d = xy; break;
+            case OP_EQUILATERAL_TRIANGLE: case OP_HEXAGON: piece(20, xy); m.d = xy; break;
+            case OP_ROUNDED_X: piece(10, xy); m.d = xy; break;
+            case OP_POLYGON: piece(14.0 * a + 6, xy); m.d = xy; break;
+            case OP_VESICA: piece(14, xy); m.d = xy; break;
+            case OP_REVOLVE: piece(5, xy); m.x = xy; m.y = m.z; break;
+            case OP_EXTRUDE_PRE: push(a); piece(2, m.z); m.s0 = m.z; break;
+            case OP_EXTRUDE_POST: piece(10, m.d | m.s0); m.d |= m.s0; pop(a); break;
+            case OP_SLICE_PRE: m.z = 0; break;
+            case OP_SLICE_SELECT: piece(2, m.d | m.s0); m.d |= m.s0; pop(a); break;
+            case OP_TPARAM_LINEAR: piece(8, xyz); m.d = xyz; break;
+            case OP_TPARAM_RADIAL: piece(8, xy); m.d = xy; break;
+            case OP_TPARAM_Z: piece(4, m.z); m.d = m.z; break;
+            case OP_EASE: if (a) piece(10, m.d); break;
+            case OP_DISPLACE: piece(3, xyz | m.d); m.x |= m.d; m.y |= m.d; m.z |= m.d; break;
+            case OP_LERP_POP2: case OP_MIX_POP2:
+                piece(3, m.d | m.s0 | m.vs[a]); m.d |= m.s0 | m.vs[a]; pop(a); break;
+            case OP_WRAP_PRE: piece(35, xy); m.d = xy; m.y = xy; break;
+            case OP_WRAP_POST: piece(1, m.d); m.x = m.d; break;
+            case OP_PUSH: push(a); m.s0 = m.d; break;
+            case OP_SAVEP: m.r[a][0] = m.x; m.r[a][1] = m.y; m.r[a][2] = m.z; break;
+            case OP_LOADP: m.x = m.r[a][0]; m.y = m.r[a][1]; m.z = m.r[a][2]; break;
+            default: piece(10, 7u); break;
+        }
+    }
+    int best = 2;                                       // ties go to z: conflict-free tile stores, the usual extrusion axis
+    if (inv[1] > inv[best]) best = 1;
+    if (inv[0] > inv[best]) best = 0;
+    const double frac = total > 0 ? inv[best] / total : 0.0;
+    if (saved_fraction) *saved_fraction = frac;
+    return frac >= 0.15 ? best : -1;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 // The generated evaluator: one SdfOps call per program word, constants as literals.
-static std::string jit_source(const sdfb200_prog* p, int kernel) {
+// `share` / `kn`: the tile kernels' sample grouping (tile_eval_body); ignored by the other kernels.
+static std::string jit_source(const sdfb200_prog* p, int kernel, int share, int kn) {
     std::ostringstream o;
     o << "#define SDF_JIT_KERNEL " << kernel << "\n#include \"sdf_kernels.cuh\"\n";
-    o << "struct SpecEval {\n  static constexpr int kN = 4;\n  template <typename T, int N, bool FAST>\n"
+    if (kernel >= 1 && kernel <= 4) {
+        double frac = 0;
+        const int ax = share_axis(p, &frac);
+        char note[96];
+        snprintf(note, sizeof(note), "// share_axis: %d (%.3f of the estimated work does not depend on it)\n", ax, frac);
+        o << note;
+    }
+    o << "struct SpecEval {\n  static constexpr int kN = " << kn << ";\n  static constexpr int kShare = " << share
+      << ";\n  template <typename T, int N, bool FAST>\n"
          "  __device__ __forceinline__ void run(T (&x)[N], T (&y)[N], T (&z)[N], T (&d)[N]) const {\n"
          "    typedef SdfOps<T, N, FAST> O;\n    typename O::State st(x, y, z, d);\n";
     o << "    const T C[" << (p->n_consts > 0 ? p->n_consts : 1) << "] = {";
@@ -231,35 +375,172 @@ static std::string jit_source(const sdfb200_prog* p, int kernel) {
     return o.str();
 }
 
-// NVRTC: source -> cubin for sm_100a.  Needs no GPU.
-static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_out) {
+// Disk cache of the specialised kernels: <dir>/<128-bit key>.cubin, the key covering the generated
+// source, every header it includes, the compile options and the NVRTC version.  Directory: env
+// SDFB200_JIT_CACHE (empty string = no cache), default `.jitcache` next to libsdfb200.so; a directory
+// that cannot be written is simply not used.  A script that meshes the same tree twice pays the
+// NVRTC compile (seconds) once.
+static uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+    const unsigned char* b = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+static const char* const kJitOptions[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--extra-device-vectorization",
+                                          "--ptxas-options=-v"};
+
+static void jit_env_hash(uint64_t h[2]) {
+    static uint64_t cached[2] = {0, 0};
+    static std::once_flag once;
+    std::call_once(once, [] {
+        uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
+        const char* files[] = {"sdf_kernels.cuh", "sdf_ops.cuh", "sdf_opcodes.h", "sdf_jit_entry.cuh", "mc_tables.inc"};
+        for (const char* f : files) {
+            const std::string path = csrc_dir() + "/" + f;
+            if (FILE* fp = fopen(path.c_str(), "rb")) {
+                char buf[65536];
+                size_t n;
+                while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) { a = fnv1a(buf, n, a); b = fnv1a(buf, n, b); }
+                fclose(fp);
+            }
+        }
+        for (const char* o : kJitOptions) { a = fnv1a(o, strlen(o), a); b = fnv1a(o, strlen(o), b); }
+        int ver[2] = {0, 0};
+        if (nvrtc_api().h)
+            if (auto fn = (int (*)(int*, int*))dlsym(nvrtc_api().h, "nvrtcVersion")) fn(&ver[0], &ver[1]);
+        a = fnv1a(ver, sizeof(ver), a); b = fnv1a(ver, sizeof(ver), b);
+        cached[0] = a; cached[1] = b;
+    });
+    h[0] = cached[0]; h[1] = cached[1];
+}
+
+static std::string jit_cache_path(const std::string& src) {
+    std::string dir;
+    if (const char* e = getenv("SDFB200_JIT_CACHE")) { if (!*e) return std::string(); dir = e; }
+    else { dir = csrc_dir(); dir = dir.substr(0, dir.size() - 5) + "/.jitcache"; }      // strip "/csrc"
+    uint64_t h[2];
+    jit_env_hash(h);
+    h[0] = fnv1a(src.data(), src.size(), h[0]);
+    h[1] = fnv1a(src.data(), src.size(), h[1]);
+    char name[64];
+    snprintf(name, sizeof(name), "/%016llx%016llx.cubin", (unsigned long long)h[0], (unsigned long long)h[1]);
+    return dir + name;
+}
+
+static bool jit_cache_load(const std::string& path, std::vector<char>* out) {
+    if (path.empty()) return false;
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END);
+    const long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    bool ok = sz > 64;
+    if (ok) { out->resize((size_t)sz); ok = fread(out->data(), 1, (size_t)sz, fp) == (size_t)sz; }
+    fclose(fp);
+    ok = ok && memcmp(out->data(), "\x7f" "ELF", 4) == 0;          // a cubin is an ELF image
+    if (!ok) out->clear();
+    return ok;
+}
+
+static void jit_cache_store(const std::string& path, const std::vector<char>& cubin) {
+    if (path.empty()) return;
+    const size_t k = path.rfind('/');
+    if (k != std::string::npos) mkdir(path.substr(0, k).c_str(), 0777);          // fails when it exists: fine
+    const std::string tmp = path + "." + std::to_string((long long)getpid()) + ".tmp";
+    FILE* fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return;
+    const bool ok = fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
+    fclose(fp);
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+// NVRTC: source -> cubin for sm_100a (or the cached cubin of the same source).  Needs no GPU.
+// *spill = bytes of register spill stores ptxas reported for the kernel.
+static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& src, std::vector<char>* cubin_out, long* spill) {
+    const std::string cpath = jit_cache_path(src);
+    *spill = 0;
+    if (jit_cache_load(cpath, cubin_out)) {
+        if (FILE* f = fopen((cpath + ".spill").c_str(), "r")) { if (fscanf(f, "%ld", spill) != 1) *spill = 0; fclose(f); }
+        return true;
+    }
     NvrtcApi& rt = nvrtc_api();
     if (!rt.ok) { p->jit_log = "NVRTC (libnvrtc.so.12) not available"; return false; }
-    const std::string src = jit_source(p, kernel);
     void* prog = nullptr;
     if (rt.CreateProgram(&prog, src.c_str(), "sdfb200_jit.cu", 0, nullptr, nullptr) != 0) { p->jit_log = "nvrtcCreateProgram failed"; return false; }
     const std::string inc = "-I" + csrc_dir();
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", inc.c_str(), "-lineinfo", "--extra-device-vectorization"};
-    const int rc = rt.CompileProgram(prog, 5, opts);
+    const char* opts[] = {kJitOptions[0], kJitOptions[1], kJitOptions[2], kJitOptions[3], kJitOptions[4], inc.c_str()};
+    const int rc = rt.CompileProgram(prog, 6, opts);
+    size_t n = 0;
+    rt.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) rt.GetProgramLog(prog, &log[0]);
     if (rc != 0) {
-        size_t n = 0;
-        rt.GetProgramLogSize(prog, &n);
-        std::string log(n, '\0');
-        if (n) rt.GetProgramLog(prog, &log[0]);
         p->jit_log = "NVRTC compile failed (kernel " + std::to_string(kernel) + "): " + log;
         if (getenv("SDFB200_JIT_VERBOSE")) fprintf(stderr, "%s\n", p->jit_log.c_str());
         rt.DestroyProgram(&prog);
         return false;
     }
+    // "ptxas info : ... N bytes spill stores, M bytes spill loads" (one line per entry point; this unit has one)
+    for (size_t at = log.find("bytes spill stores"); at != std::string::npos; at = log.find("bytes spill stores", at + 1)) {
+        size_t b = at;
+        while (b > 0 && log[b - 1] == ' ') --b;
+        size_t a = b;
+        while (a > 0 && isdigit((unsigned char)log[a - 1])) --a;
+        if (a < b) *spill = std::max(*spill, atol(log.substr(a, b - a).c_str()));
+    }
+    if (getenv("SDFB200_JIT_VERBOSE")) fprintf(stderr, "[sdfb200 jit] kernel %d: %s", kernel, log.c_str());
     size_t sz = 0;
     rt.GetCUBINSize(prog, &sz);
     cubin_out->resize(sz);
     rt.GetCUBIN(prog, cubin_out->data());
     rt.DestroyProgram(&prog);
+    jit_cache_store(cpath, *cubin_out);
+    if (*spill > 0 && !cpath.empty())
+        if (FILE* f = fopen((cpath + ".spill").c_str(), "w")) { fprintf(f, "%ld\n", *spill); fclose(f); }
+    return true;
+}
+
+// Source generation + compilation of one kernel.  The tile kernels (1..4) choose their sample grouping
+// here: groups of 11 samples along the axis share_axis() names (three groups per 33-sample line),
+// backing off to 6, 4 and finally the flat 4-sample mapping when ptxas had to spill registers.
+// SDFB200_JIT_SHARE (-1 = flat, 0..2) / SDFB200_JIT_N force a grouping (experiments, A/B timing).
+static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_out) {
+    const bool tile = kernel >= JK_TILE0 && kernel < JK_TILE0 + 4;
+    int cand[4][2];
+    int n_cand = 0;
+    const int env_share = env_int("SDFB200_JIT_SHARE", -2), env_n = env_int("SDFB200_JIT_N", 0);
+    // no axis saves evaluation work: still group along z -- a group of samples shares its index
+    // arithmetic and two of its three coordinate loads, and z-columns store without bank conflicts
+    int share = -1;
+    if (tile) {
+        if (env_share >= -1 && env_share <= 2) share = env_share;
+        else { share = share_axis(p); if (share < 0) share = 2; }
+    }
+    if (env_n >= 1 && env_n <= 16) { cand[0][0] = share; cand[0][1] = env_n; n_cand = 1; }
+    else if (share < 0) { cand[0][0] = -1; cand[0][1] = 4; n_cand = 1; }
+    else {
+        const int ns[3] = {11, 6, 4};
+        for (int k = 0; k < 3; ++k) { cand[k][0] = share; cand[k][1] = ns[k]; }
+        cand[3][0] = -1; cand[3][1] = 4;
+        n_cand = 4;
+    }
+    long best_spill = -1;
+    std::string best_src;
+    std::vector<char> cubin;
+    for (int k = 0; k < n_cand; ++k) {
+        const std::string src = jit_source(p, kernel, cand[k][0], cand[k][1]);
+        long spill = 0;
+        if (!jit_compile_source(p, kernel, src, &cubin, &spill)) return false;
+        if (best_spill < 0 || spill < best_spill) {
+            best_spill = spill; best_src = src; cubin_out->swap(cubin);
+            p->plan_share[kernel] = cand[k][0]; p->plan_n[kernel] = cand[k][1];
+        }
+        if (spill == 0) break;
+    }
     if (const char* dump = getenv("SDFB200_JIT_DUMP")) {       // debugging aid: keep source + cubin
         const std::string base = std::string(dump) + "/jit_k" + std::to_string(kernel);
-        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fputs(src.c_str(), f); fclose(f); }
-        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin_out->data(), 1, sz, f); fclose(f); }
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fputs(best_src.c_str(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin_out->data(), 1, cubin_out->size(), f); fclose(f); }
     }
     return true;
 }
@@ -314,8 +595,10 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     c.device = device;
     CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c.ctr, sizeof(Counters)));
-    CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters)));
+    CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters) * (1 + kMaxPipe)));     // [0] final, [1 + k] after round k
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
+    for (int i = 0; i < kMaxPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.pev[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     prog->ctxs.reserve(16);
     prog->ctxs.push_back(c);
     *out = &prog->ctxs.back();
@@ -419,6 +702,8 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
         for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+        for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
+        if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     }
     for (auto& e : prog->jit) if (e.lib) cudaLibraryUnload(e.lib);
     delete prog;
@@ -621,6 +906,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
     const bool big = lattice >= (1 << 21);
     Counters& h = *c->ctr_host;
     bool ran_pipeline = false;
+    unsigned long long copied = 0;      // triangles already on their way to tri_out (pipelined host output)
     if (total_b > 0) {
         const int pb = (int)((total_b + 127) / 128);
         // ---- skip pre-pass
@@ -639,14 +925,24 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         // synchronises in the middle; otherwise the host reads it and runs rounds of `max_round` tiles.
         const unsigned long long max_round = std::max<unsigned long long>(1ull, kVolBudgetBytes / ((size_t)VOL_STRIDE * 4));
         const unsigned long long upper = (unsigned long long)total_b * g.sub * g.sub * g.sub;
-        const bool sync_free = upper <= max_round;
+        // Host output: cut the work list into a few rounds so that the triangles of round k cross PCIe
+        // while round k+1 is computed (the copy is the longer leg: 36 B per triangle at PCIe speed).
+        int pipe = (tri_out && !out_dev && !stl_out && !ext_cursor && big) ? pipe_rounds() : 1;
+        const bool sync_free = upper <= max_round && pipe == 1;
         unsigned long long n_work = upper;
         if (!sync_free) {
             CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
         }
-        const unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
+        unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
+        if (pipe > 1) {
+            // whole waves of the persistent tile kernel (one tile per SM) per round; a job of less than
+            // two waves has nothing to overlap
+            const unsigned long long per = ((n_work + pipe - 1) / pipe + c->sms - 1) / c->sms * c->sms;
+            if (n_work < 2ull * c->sms || n_work > max_round) pipe = 1;
+            else round = (unsigned int)std::min<unsigned long long>(per, max_round);
+        }
         if (n_work > 0) {
             ran_pipeline = true;
             rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
@@ -655,6 +951,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, est_tiles * 3072)));
             size_t want_pts = std::max<size_t>(c->pt_cap, precision == SDFB200_PREC_EXACT ? want_cubes * 3 : want_cubes);
             for (int attempt = 0; attempt < 3; ++attempt) {
+                int n_rounds = 0;
                 rc = grow(&c->cubes, &c->cube_cap, want_cubes); if (rc) return rc;
                 rc = grow(&c->pts, &c->pt_cap, want_pts); if (rc) return rc;
                 TileLists L;
@@ -662,6 +959,8 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 L.slot_cap = round; L.cube_cap = (unsigned int)std::min<size_t>(c->cube_cap, 0xffffffffu);
                 L.pt_cap = (unsigned int)std::min<size_t>(c->pt_cap, 0xffffffffu);
                 if (attempt > 0) {      // redo from a clean slate (the pre-pass results stay valid)
+                    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+                    copied = 0;
                     const size_t nb = (size_t)g.nbx * g.nby * g.nbz;
                     CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->tri_cursor, 0, 4 * sizeof(unsigned long long), stream));
@@ -728,6 +1027,23 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor);
                     CUDA_TRY(cudaGetLastError());
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[7], stream));
+                    if (pipe > 1 && n_rounds < kMaxPipe) {
+                        CUDA_TRY(cudaMemcpyAsync(c->ctr_host + 1 + n_rounds, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                        CUDA_TRY(cudaEventRecord(c->pev[n_rounds], stream));
+                        ++n_rounds;
+                    }
+                }
+                // every round is queued; follow them and send each round's triangles as soon as it is done
+                for (int k = 0; k < n_rounds; ++k) {
+                    CUDA_TRY(cudaEventSynchronize(c->pev[k]));
+                    const Counters& hk = c->ctr_host[1 + k];
+                    if (hk.max_cubes > L.cube_cap || hk.max_pts > L.pt_cap) break;       // lists overflowed: retried below
+                    const unsigned long long upto = std::min<unsigned long long>(hk.tri_cursor, cap);
+                    if (upto > copied) {
+                        CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(upto - copied) * 36,
+                                                 cudaMemcpyDeviceToHost, c->copy_stream));
+                        copied = upto;
+                    }
                 }
                 CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -773,9 +1089,11 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         stl_records_kernel<<<(unsigned)((nt + STL_THREADS - 1) / STL_THREADS), STL_THREADS, 0, stream>>>(dtri, nt, drec);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(stl_out, drec, (size_t)nt * 50, cudaMemcpyDefault, stream));
-    } else if (tri_out && !out_dev && !overflow && h.tri_cursor > 0) {
-        CUDA_TRY(cudaMemcpyAsync(tri_out, dtri, (size_t)h.tri_cursor * 36, cudaMemcpyDeviceToHost, stream));
+    } else if (tri_out && !out_dev && !overflow && h.tri_cursor > copied) {
+        CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(h.tri_cursor - copied) * 36,
+                                 cudaMemcpyDeviceToHost, stream));
     }
+    if (copied > 0) CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(cudaEventRecord(c->ev[3], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (timings_ms) {
@@ -899,6 +1217,19 @@ extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_
     std::vector<char> cubin;
     if (!jit_compile(prog, kernel, &cubin)) return fail(SDFB200_E_INVALID, "%s", prog->jit_log.c_str());
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return 0;
+}
+
+extern "C" int sdfb200_jit_plan(sdfb200_prog* prog, int precision, int* share_axis_out, int* samples_per_thread,
+                                double* invariant_fraction) {
+    if (!prog || precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "jit_plan: bad argument");
+    std::lock_guard<std::mutex> guard(prog->lock);
+    std::vector<char> cubin;
+    const int kernel = JK_TILE0 + precision;
+    if (!jit_compile(prog, kernel, &cubin)) return fail(SDFB200_E_INVALID, "%s", prog->jit_log.c_str());
+    if (share_axis_out) *share_axis_out = prog->plan_share[kernel];
+    if (samples_per_thread) *samples_per_thread = prog->plan_n[kernel];
+    if (invariant_fraction) share_axis(prog, invariant_fraction);
     return 0;
 }
 

@@ -221,6 +221,60 @@ def test_runtime_specialisation_compiles_without_a_gpu():
         assert h.jit_probe(kernel) > 10000, name
 
 
+def test_sample_grouping_plan_follows_the_tree_structure():
+    """sdfb200_jit_plan: the tile kernel groups samples along the axis most of the tree does not depend on."""
+    from sdf_b200 import core
+    S = sdf_b200
+    cases = {
+        'gearlike': (models.CONFIGS['gearlike'](S), 2),                       # cylinders + circular array about Z
+        'cyl_x': (S.cylinder(1).orient(S.X) & S.sphere(2), 0),                # rotate_to's cos(pi/2) is 6e-17, not 0
+        'cyl_y': (S.cylinder(1).orient(S.Y) & S.sphere(2), 1),
+        'extrusion': (S.hexagon(1).extrude(2) - S.circle(0.4).extrude(3), 2),
+        'sphere': (S.sphere(1), 2),                                           # nothing to share: z columns anyway
+    }
+    for name, (f, axis) in cases.items():
+        h, _ = core.program_handle(f)
+        got_axis, group, frac = h.jit_plan(3)
+        assert got_axis == axis, (name, got_axis)
+        assert group in (11, 6, 4), (name, group)
+        assert (frac > 0.3) == (name != 'sphere'), (name, frac)
+    # a deep tree needs more registers per sample: the group shrinks until ptxas stops spilling
+    h, _ = core.program_handle(models.widened_corpus(S)['weave'])
+    assert h.jit_plan(3)[1] < 11
+    # forced grouping (A/B timing, tests)
+    import os
+    os.environ['SDFB200_JIT_SHARE'] = '-1'; os.environ['SDFB200_JIT_N'] = '4'
+    try:
+        assert _abi.ProgramHandle(ir.lower(cases['gearlike'][0])).jit_plan(3)[:2] == (-1, 4)
+    finally:
+        os.environ.pop('SDFB200_JIT_SHARE'); os.environ.pop('SDFB200_JIT_N')
+
+
+def test_specialised_kernels_are_cached_on_disk(tmp_path):
+    import os, time
+    old = os.environ.get('SDFB200_JIT_CACHE')
+    os.environ['SDFB200_JIT_CACHE'] = str(tmp_path / 'jit')
+    try:
+        prog = ir.lower(sdf_b200.torus(1, 0.25).twist(0.5) | sdf_b200.box(0.7))
+        t0 = time.time(); a = _abi.ProgramHandle(prog).jit_probe(4); t1 = time.time()
+        files = sorted(os.listdir(tmp_path / 'jit'))
+        assert len(files) == 1 and files[0].endswith('.cubin')
+        b = _abi.ProgramHandle(prog).jit_probe(4); t2 = time.time()
+        assert a == b and sorted(os.listdir(tmp_path / 'jit')) == files
+        assert (t2 - t1) < 0.5 * (t1 - t0)                   # a file read instead of an NVRTC compile
+        # a damaged entry is ignored and replaced
+        with open(tmp_path / 'jit' / files[0], 'wb') as fh:
+            fh.write(b'garbage')
+        assert _abi.ProgramHandle(prog).jit_probe(4) == a
+        os.environ['SDFB200_JIT_CACHE'] = ''                 # empty: no cache
+        assert _abi.ProgramHandle(prog).jit_probe(4) == a
+    finally:
+        if old is None:
+            os.environ.pop('SDFB200_JIT_CACHE', None)
+        else:
+            os.environ['SDFB200_JIT_CACHE'] = old
+
+
 def test_large_program_is_accepted_and_small_limits_still_guard():
     f = sdf_b200.sphere(0.1)
     for i in range(12):
