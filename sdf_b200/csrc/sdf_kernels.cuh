@@ -413,8 +413,12 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
         __syncthreads();
 
         // ---------------------------------------------------------------- evaluation
+        // A tile that is one sample thick along some axis holds no cube (the reference still evaluates
+        // it, skimage raises, the batch counts as empty: core.py:53-56): nothing to evaluate.
+        const bool thin = !valid || px < 2 || py < 2 || pz < 2;
         float vmin = FLT_MAX, vmax = -FLT_MAX;
-        if (F64) {
+        if (thin) {
+        } else if (F64) {
             for (int idx = tid; idx < npts; idx += THREADS) {
                 const unsigned int ix = dpyz.div(idx), rem = idx - ix * pyz, iy = dpz.div(rem), iz = rem - iy * pz;
                 double x[1] = {sm.axd[0][F64 ? ix : 0]}, y[1] = {sm.axd[F64 ? 1 : 0][F64 ? iy : 0]},
@@ -497,7 +501,7 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
                 }
             }
         }
-        if (tid == 0 && valid) my_pts += (unsigned long long)npts;
+        if (tid == 0 && !thin) my_pts += (unsigned long long)npts;
         // warp-shuffle min/max reduction, one shared atomic per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -140,7 +140,7 @@ struct DeviceCtx {
 // round + one copy at the end).  Read on every call so tests can switch it.
 static int pipe_rounds() {
     const char* e = getenv("SDFB200_PIPE");
-    const int v = e ? atoi(e) : 4;
+    const int v = e ? atoi(e) : 8;      // measured (profiles/): 8 rounds <= 4 rounds < 2 < 1 on every configuration
     return v < 1 ? 1 : (v > kMaxPipe ? kMaxPipe : v);
 }
 
@@ -226,8 +226,9 @@ static std::string csrc_dir() {
 // sharing").  A dependency mask over the lattice axes (bit 0 = x, 1 = y, 2 = z) is pushed through the
 // program for every machine register; an operation whose inputs do not depend on axis A is computed
 // once per group when the group runs along A.  Costs are rough instruction counts of the float32
-// throughput path -- the choice only affects speed, never results.  Returns -1 when no axis would save
-// a worthwhile share of the work.
+// throughput path -- the choice only affects speed, never results.  Returns the best axis (z when no
+// axis saves anything: z-columns store into the tile without bank conflicts) and, through
+// `saved_fraction`, the estimated share of the work that does not depend on it.
 static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr) {
     struct Masks {
         unsigned x = 1, y = 2, z = 4, d = 0, s0 = 0;
@@ -333,8 +334,12 @@ static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr) {
     if (inv[0] > inv[best]) best = 0;
     const double frac = total > 0 ? inv[best] / total : 0.0;
     if (saved_fraction) *saved_fraction = frac;
-    return frac >= 0.15 ? best : -1;
+    return best;
 }
+
+// Column groups pay off when they save evaluation work; below this invariant fraction the flat
+// 4-sample mapping is used (A/B timings: profiles/).
+static constexpr double kColumnMinFraction = 0.0;
 
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -509,12 +514,14 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
     int cand[4][2];
     int n_cand = 0;
     const int env_share = env_int("SDFB200_JIT_SHARE", -2), env_n = env_int("SDFB200_JIT_N", 0);
-    // no axis saves evaluation work: still group along z -- a group of samples shares its index
-    // arithmetic and two of its three coordinate loads, and z-columns store without bank conflicts
     int share = -1;
     if (tile) {
         if (env_share >= -1 && env_share <= 2) share = env_share;
-        else { share = share_axis(p); if (share < 0) share = 2; }
+        else {
+            double frac = 0;
+            share = share_axis(p, &frac);
+            if (frac < kColumnMinFraction) share = -1;
+        }
     }
     if (env_n >= 1 && env_n <= 16) { cand[0][0] = share; cand[0][1] = env_n; n_cand = 1; }
     else if (share < 0) { cand[0][0] = -1; cand[0][1] = 4; n_cand = 1; }
