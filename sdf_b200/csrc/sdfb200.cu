@@ -229,7 +229,7 @@ static std::string csrc_dir() {
 // throughput path -- the choice only affects speed, never results.  Returns the best axis (z when no
 // axis saves anything: z-columns store into the tile without bank conflicts) and, through
 // `saved_fraction`, the estimated share of the work that does not depend on it.
-static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr) {
+static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr, double* saved_cost = nullptr) {
     struct Masks {
         unsigned x = 1, y = 2, z = 4, d = 0, s0 = 0;
         unsigned r[SDF_MAX_PSLOTS][3] = {};
@@ -334,12 +334,16 @@ static int share_axis(const sdfb200_prog* p, double* saved_fraction = nullptr) {
     if (inv[0] > inv[best]) best = 0;
     const double frac = total > 0 ? inv[best] / total : 0.0;
     if (saved_fraction) *saved_fraction = frac;
+    if (saved_cost) *saved_cost = inv[best];
     return best;
 }
 
-// Column groups pay off when they save evaluation work; below this invariant fraction the flat
-// 4-sample mapping is used (A/B timings: profiles/).
-static constexpr double kColumnMinFraction = 0.0;
+// Column groups are used when they save at least this much estimated evaluation work per sample (in
+// share_axis()'s instruction units); below it the flat 4-sample mapping is faster.  Measured on B200
+// (profiles/r1_ab_grouping.jsonl): a column tile costs ~4 us more than a flat one outside the
+// evaluation, a saved instruction per sample is worth ~0.2 us per tile -> gearlike (75 saved, tile
+// kernel -27 %) and knurling (56, -4 %) use columns; csg (15: +6 % with columns), blobby, sphere stay flat.
+static constexpr double kColumnMinSavedCost = 30.0;
 
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -518,9 +522,9 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
     if (tile) {
         if (env_share >= -1 && env_share <= 2) share = env_share;
         else {
-            double frac = 0;
-            share = share_axis(p, &frac);
-            if (frac < kColumnMinFraction) share = -1;
+            double saved = 0;
+            share = share_axis(p, nullptr, &saved);
+            if (saved < kColumnMinSavedCost) share = -1;
         }
     }
     if (env_n >= 1 && env_n <= 16) { cand[0][0] = share; cand[0][1] = env_n; n_cand = 1; }
