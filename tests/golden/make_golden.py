@@ -106,6 +106,14 @@ def main():
         print('auto', name, r['skipped'], r['empty'], r['nonempty'], r['active'], r['dims'], step)
     np.savez_compressed(os.path.join(HERE, 'engine.npz'), **eng)
 
+    # random compositions (tests/models.py: random_trees) evaluated by the real reference
+    Pr = models.random_points(512, seed=4321)
+    rt = {'points': Pr}
+    for i, f in enumerate(models.random_trees(ref)):
+        rt['d_%03d' % i] = f(Pr).reshape(-1)
+    np.savez_compressed(os.path.join(HERE, 'random_trees.npz'), **rt)
+    print('random_trees.npz: %d trees x %d points' % (len(rt) - 1, len(Pr)))
+
 
 if __name__ == '__main__':
     main()

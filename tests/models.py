@@ -207,3 +207,49 @@ def random_points(n, seed=0, L=3.0):
     # exact lattice-like coordinates and zeros exercise the branch points (atan2(0,0), |x| = 0, ...)
     p[:8] = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0.5, 0.5, 0.5), (2, 0, 0), (0, -2, 0)]
     return p
+
+
+def random_tree(S, rng, depth):
+    """A seeded random composition of primitives, transforms and folds (S = our package or the reference)."""
+    u = lambda lo, hi: float(rng.uniform(lo, hi))
+    v3 = lambda lo, hi: tuple(float(t) for t in rng.uniform(lo, hi, 3))
+    if depth == 0 or rng.random() < 0.15:
+        k = rng.integers(0, 12)
+        if k == 0: return S.sphere(u(0.3, 1.2), v3(-0.5, 0.5))
+        if k == 1: return S.box(v3(0.4, 1.5))
+        if k == 2: return S.rounded_box(v3(0.6, 1.5), u(0.05, 0.2))
+        if k == 3: return S.torus(u(0.6, 1.2), u(0.1, 0.3))
+        if k == 4: return S.capsule(v3(-1, 0), v3(0, 1), u(0.1, 0.4))
+        if k == 5: return S.cylinder(u(0.2, 0.8))
+        if k == 6: return S.capped_cylinder(v3(-1, 0), v3(0, 1), u(0.2, 0.5))
+        if k == 7: return S.ellipsoid(v3(0.4, 1.3))
+        if k == 8: return S.hexagon(u(0.4, 1.0)).extrude(u(0.3, 1.5))
+        if k == 9: return S.circle(u(0.2, 0.6)).translate((u(0.7, 1.2), 0)).revolve()
+        if k == 10: return S.rectangle((u(0.5, 1.2), u(0.3, 0.9))).extrude_to(S.circle(u(0.3, 0.8)), u(0.5, 1.5))
+        return S.octahedron(u(0.5, 1.2))
+    k = rng.integers(0, 16)
+    a = random_tree(S, rng, depth - 1)
+    if k == 0: return a.translate(v3(-1, 1))
+    if k == 1: return a.scale(u(0.5, 1.8))
+    if k == 2: return a.rotate(u(-3, 3), v3(-1, 1))
+    if k == 3: return a.orient(v3(-1, 1))
+    if k == 4: return a.twist(u(-1, 1))
+    if k == 5: return a.elongate(v3(0, 0.5))
+    if k == 6: return a.circular_array(int(rng.integers(2, 9)), u(0, 1.5))
+    if k == 7: return a.repeat(v3(2.5, 4.0), count=(1, 1, 0), padding=int(rng.integers(0, 2)))
+    if k == 8: return a.shell(u(0.05, 0.2))
+    if k == 9: return a.dilate(u(0.02, 0.2))
+    if k == 10: return a.bend_linear(v3(-1, 0), v3(0, 1), v3(-0.3, 0.3))
+    b = random_tree(S, rng, depth - 1)
+    kk = None if rng.random() < 0.5 else u(0.05, 0.4)
+    if k == 11: return a.union(b, random_tree(S, rng, depth - 1), k=kk)
+    if k == 12: return a.difference(b, k=kk)
+    if k == 13: return a.intersection(b, k=kk)
+    if k == 14: return a.blend(b, k=u(0.1, 0.9))
+    return a.transition_linear(b, v3(-1, 0), v3(0, 1))
+
+
+def random_trees(S, count=120, seed=424242):
+    """The fixed list of random trees behind tests/golden/random_trees.npz."""
+    rng = np.random.default_rng(seed)
+    return [random_tree(S, rng, int(rng.integers(1, 5))) for _ in range(count)]

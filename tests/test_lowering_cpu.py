@@ -41,53 +41,13 @@ def test_late_k_and_shared_subtrees_lower_correctly():
         assert np.max(np.abs(got - ref)) < 1e-12
 
 
-def _random_tree(rng, depth):
-    S = sdf_b200
-    u = lambda lo, hi: float(rng.uniform(lo, hi))
-    v3 = lambda lo, hi: tuple(float(t) for t in rng.uniform(lo, hi, 3))
-    if depth == 0 or rng.random() < 0.15:
-        k = rng.integers(0, 12)
-        if k == 0: return S.sphere(u(0.3, 1.2), v3(-0.5, 0.5))
-        if k == 1: return S.box(v3(0.4, 1.5))
-        if k == 2: return S.rounded_box(v3(0.6, 1.5), u(0.05, 0.2))
-        if k == 3: return S.torus(u(0.6, 1.2), u(0.1, 0.3))
-        if k == 4: return S.capsule(v3(-1, 0), v3(0, 1), u(0.1, 0.4))
-        if k == 5: return S.cylinder(u(0.2, 0.8))
-        if k == 6: return S.capped_cylinder(v3(-1, 0), v3(0, 1), u(0.2, 0.5))
-        if k == 7: return S.ellipsoid(v3(0.4, 1.3))
-        if k == 8: return S.hexagon(u(0.4, 1.0)).extrude(u(0.3, 1.5))
-        if k == 9: return S.circle(u(0.2, 0.6)).translate((u(0.7, 1.2), 0)).revolve()
-        if k == 10: return S.rectangle((u(0.5, 1.2), u(0.3, 0.9))).extrude_to(S.circle(u(0.3, 0.8)), u(0.5, 1.5))
-        return S.octahedron(u(0.5, 1.2))
-    k = rng.integers(0, 16)
-    a = _random_tree(rng, depth - 1)
-    if k == 0: return a.translate(v3(-1, 1))
-    if k == 1: return a.scale(u(0.5, 1.8))
-    if k == 2: return a.rotate(u(-3, 3), v3(-1, 1))
-    if k == 3: return a.orient(v3(-1, 1))
-    if k == 4: return a.twist(u(-1, 1))
-    if k == 5: return a.elongate(v3(0, 0.5))
-    if k == 6: return a.circular_array(int(rng.integers(2, 9)), u(0, 1.5))
-    if k == 7: return a.repeat(v3(2.5, 4.0), count=(1, 1, 0), padding=int(rng.integers(0, 2)))
-    if k == 8: return a.shell(u(0.05, 0.2))
-    if k == 9: return a.dilate(u(0.02, 0.2))
-    if k == 10: return a.bend_linear(v3(-1, 0), v3(0, 1), v3(-0.3, 0.3))
-    b = _random_tree(rng, depth - 1)
-    kk = None if rng.random() < 0.5 else u(0.05, 0.4)
-    if k == 11: return a.union(b, _random_tree(rng, depth - 1), k=kk)
-    if k == 12: return a.difference(b, k=kk)
-    if k == 13: return a.intersection(b, k=kk)
-    if k == 14: return a.blend(b, k=u(0.1, 0.9))
-    return a.transition_linear(b, v3(-1, 0), v3(0, 1))
-
-
 def test_random_trees_lower_correctly():
     """300 seeded random trees (depth <= 4) through lower() + simulator vs the oracle's tree walk."""
     rng = np.random.default_rng(20260922)
     P = models.random_points(600, seed=8)
     deepest = 0
     for i in range(300):
-        f = _random_tree(rng, int(rng.integers(1, 5)))
+        f = models.random_tree(sdf_b200, rng, int(rng.integers(1, 5)))
         try:
             prog = ir.lower(f)
         except ir.NotLowerableError:
@@ -102,6 +62,18 @@ def test_random_trees_lower_correctly():
     assert deepest > 100
 
 
+def test_random_tree_goldens_through_the_simulator(golden_dir):
+    """The trees of tests/golden/random_trees.npz (values from the REAL reference): lower() + simulator."""
+    g = np.load(golden_dir + '/random_trees.npz')
+    P = g['points']
+    for i, f in enumerate(models.random_trees(sdf_b200)):
+        got = prog_sim.run(ir.lower(f), P)
+        r = g['d_%03d' % i]
+        assert np.array_equal(np.isnan(got), np.isnan(r)), i
+        ok = np.isfinite(r)
+        assert np.max(np.abs(got[ok] - r[ok]) / np.maximum(1.0, np.abs(r[ok]))) < 1e-12, i
+
+
 def test_random_trees_specialise_with_nvrtc():
     """The generated straight-line evaluator of random trees compiles for sm_100a (no GPU needed), in the
     float64 streamed kernel and in the fused tile kernel with whatever sample grouping the plan picks."""
@@ -109,7 +81,7 @@ def test_random_trees_specialise_with_nvrtc():
     rng = np.random.default_rng(7)
     done = 0
     while done < 8:
-        f = _random_tree(rng, 4)
+        f = models.random_tree(sdf_b200, rng, 4)
         try:
             prog = ir.lower(f)
         except ir.NotLowerableError:

@@ -24,6 +24,19 @@ def test_node_evaluation_bit_identical_to_reference(corpus, golden_dir):
         assert np.array_equal(d, g['d_' + name], equal_nan=True), name
 
 
+def test_random_compositions_bit_identical_to_reference(golden_dir):
+    """120 seeded random trees (depth <= 4: transforms, warps, arrays, smooth folds, 2-D -> 3-D) evaluated
+    by the REAL reference (tests/golden/random_trees.npz): the restatement reproduces every value."""
+    g = np.load(golden_dir + '/random_trees.npz')
+    P = g['points']
+    trees = models.random_trees(sdf_b200)
+    assert len(trees) == 120
+    for i, f in enumerate(trees):
+        with np.errstate(all='ignore'):
+            d = sdf_ref.evaluate(f, P).reshape(-1)
+        assert np.array_equal(d, g['d_%03d' % i], equal_nan=True), i
+
+
 def test_known_answers():
     # SURVEY.md section 8c golden vectors
     s = sdf_b200.sphere(1)
