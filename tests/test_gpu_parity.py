@@ -69,21 +69,6 @@ def test_eval_f64_matches_reference_goldens(sdf, corpus, golden_dir):
     assert not bad, bad
 
 
-def test_eval_f64_random_trees_match_reference_goldens(sdf, evaluator_front_end, golden_dir):
-    """120 seeded random compositions (tests/models.py: random_trees) against the REAL reference's values."""
-    g = np.load(golden_dir + '/random_trees.npz')
-    P = g['points']
-    trees = models.random_trees(sdf)
-    step = 1 if evaluator_front_end == 'interp' else 6           # one NVRTC compile per tree on the specialised path
-    for i in range(0, len(trees), step):
-        d = trees[i](P).reshape(-1)
-        r = g['d_%03d' % i]
-        assert np.array_equal(np.isnan(d), np.isnan(r)), i
-        ok = np.isfinite(r)
-        err = np.max(np.abs(d[ok] - r[ok]) / np.maximum(1.0, np.abs(r[ok]))) if ok.any() else 0.0
-        assert err <= 1e-11, (i, err)
-
-
 def test_eval_f32_stream_matches_oracle(sdf, ref, corpus):
     """The streamed float32 evaluator (TMA-staged float3 points) against the float64 oracle."""
     import torch

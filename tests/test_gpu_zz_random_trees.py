@@ -1,0 +1,46 @@
+"""SDF3.__call__ on the GPU (float64) for 120 seeded random compositions against values produced by the
+REAL reference (tests/golden/random_trees.npz).  Needs a B200: -m gpu.  (Named to run last.)
+
+Known difference, found by this test on the B200 and reproduced on the CPU by giving the lowering
+simulator IEEE minNum/maxNum semantics: the device's fmin/fmax drop a NaN operand, numpy's
+minimum/maximum (dn.py:14,29,44) propagate it.  The only NaN source in these trees is the exact centre of
+an `ellipsoid` (0/0, d3.py:255-258); where a fold combines it with another shape the reference returns
+NaN and the device returns the other operand: trees 43 and 116 at the point (0,0,0).  Meshes are not
+affected (`NaN > 0` is false: the sample counts as inside, as its neighbours do).  DESIGN.md section 8.
+"""
+import numpy as np
+import pytest
+
+import models
+
+pytestmark = pytest.mark.gpu
+
+KNOWN_NAN_DROPPED = {(43, 0), (116, 0)}          # (tree, point): reference NaN, device finite
+
+
+@pytest.mark.parametrize('front', ['interp', 'jit'])
+def test_eval_f64_random_trees_match_reference_goldens(front, golden_dir):
+    import os
+    import sdf_b200 as sdf
+    old = os.environ.get('SDFB200_JIT')
+    os.environ['SDFB200_JIT'] = '0' if front == 'interp' else '2'
+    try:
+        g = np.load(golden_dir + '/random_trees.npz')
+        P = g['points']
+        trees = models.random_trees(sdf)
+        step = 1 if front == 'interp' else 6         # one NVRTC compile per tree on the specialised path
+        dropped = set()
+        for i in range(0, len(trees), step):
+            d = trees[i](P).reshape(-1)
+            r = g['d_%03d' % i]
+            assert not np.any(np.isnan(d) & ~np.isnan(r)), i          # never NaN where the reference is finite
+            dropped |= {(i, int(k)) for k in np.nonzero(np.isnan(r) & ~np.isnan(d))[0]}
+            ok = np.isfinite(r) & np.isfinite(d)
+            err = np.max(np.abs(d[ok] - r[ok]) / np.maximum(1.0, np.abs(r[ok]))) if ok.any() else 0.0
+            assert err <= 1e-11, (i, err)
+        assert dropped <= KNOWN_NAN_DROPPED, dropped
+    finally:
+        if old is None:
+            os.environ.pop('SDFB200_JIT', None)
+        else:
+            os.environ['SDFB200_JIT'] = old
