@@ -11,6 +11,14 @@ from .d2 import *              # noqa: F401,F403
 
 from .d3 import *              # noqa: F401,F403
 
+from .texture import (         # noqa: F401  (names only: out of scope, raise on use)
+    Mesh,
+    image,
+    measure_image,
+    measure_text,
+    text,
+)
+
 from .core import (            # noqa: F401
     generate,
     save,
