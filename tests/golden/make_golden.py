@@ -70,9 +70,26 @@ def classify(ref, f, bounds, step, batch_size=32, sparse=True):
                 dims=(len(X), len(Y), len(Z)), flags=np.array(flags, np.uint8))
 
 
+def natural_grids(ref, ref_models):
+    """`samples = N^3` with the reference's own bounds estimate.
+    Slow (minutes: the real reference evaluates every non-skipped batch): `make_golden.py --natural`."""
+    out = {}
+    for name, n in (('gearlike', 512), ('blobby', 768), ('knurling', 1024)):
+        f = ref_models['cfg_' + name]
+        lo, hi = (np.array(v, np.float64) for v in ref.core._estimate_bounds(f))
+        step = (float(np.prod(hi - lo)) / n ** 3) ** (1 / 3)
+        r = classify(ref, f, (tuple(lo), tuple(hi)), step)
+        out['auto_%s' % name] = np.array([r['skipped'], r['empty'], r['nonempty'], r['active'], *r['dims']], np.int64)
+        out['autostep_%s' % name] = np.array([step])
+        print('auto', name, r['skipped'], r['empty'], r['nonempty'], r['active'], r['dims'], step, flush=True)
+        np.savez_compressed(os.path.join(HERE, 'natural.npz'), **out)
+
+
 def main():
     ref = import_reference()
     ref_models = models.build(ref)
+    if '--natural' in sys.argv:
+        return natural_grids(ref, ref_models)
     P = models.random_points(4096, seed=1234)
     out = {'points': P}
     for name, f in ref_models.items():

@@ -44,3 +44,19 @@ def test_eval_f64_random_trees_match_reference_goldens(front, golden_dir):
             os.environ.pop('SDFB200_JIT', None)
         else:
             os.environ['SDFB200_JIT'] = old
+
+
+@pytest.mark.parametrize('name,n', [('gearlike', 512), ('blobby', 768), ('knurling', 1024)])
+def test_natural_grids_match_the_reference_classification(name, n, golden_dir):
+    """SURVEY.md section 8(c) table, rows 3-5, at FULL size: `samples = N^3` with the bounds estimate on the
+    GPU evaluator; lattice dimensions, skipped / empty / nonempty batches and the number of active cubes
+    equal what the REAL reference computes (tests/golden/natural.npz, `make_golden.py --natural`)."""
+    import sdf_b200 as sdf
+    g = np.load(golden_dir + '/natural.npz')
+    f = models.CONFIGS[name](sdf)
+    pts, info = sdf.generate(f, samples=n ** 3, verbose=False, return_info=True)
+    gold = g['auto_' + name]
+    assert info['dims'] == tuple(gold[4:7]), (info['dims'], gold)
+    assert (info['skipped'], info['empty'], info['nonempty']) == tuple(gold[:3]), (info, gold)
+    assert info['active_cubes'] == gold[3], (info['active_cubes'], gold[3])
+    assert len(pts) == 3 * info['triangles'] and info['triangles'] >= info['active_cubes']
