@@ -560,15 +560,34 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
                     c64 |= (u0 | (u0 >> 1)) | (u1 | (u1 >> 1)) | (u2 | (u2 >> 1)) | (u3 | (u3 >> 1));
                 }
                 W = (unsigned int)c64 & (czn >= 32 ? 0xffffffffu : ((1u << czn) - 1u));
+#ifndef SDF_EXP_REFM_GATHER
                 if (EXACT && W) {
                     const unsigned long long zm = (unsigned long long)W | ((unsigned long long)W << 1);
                     atomicOr(&sm.refm[l00], zm); atomicOr(&sm.refm[l01], zm);
                     atomicOr(&sm.refm[l10], zm); atomicOr(&sm.refm[l11], zm);
                 }
+#endif
             }
             sm.cand[col] = W;
         }
         __syncthreads();
+#ifdef SDF_EXP_REFM_GATHER
+        // EXPERIMENT: every z-line collects the candidate words of its (up to) four
+        // adjacent cube columns instead of the columns scattering 64-bit shared-memory atomics (which
+        // compile to CAS spin loops) into the lines.
+        if (EXACT) {
+            for (int ln = tid; ln < nlines; ln += THREADS) {
+                const int ix = ln / py, iy = ln - ix * py;
+                unsigned int Wl = 0u;
+                if (ix < TS && iy < TS) Wl |= sm.cand[(ix << 5) | iy];
+                if (ix < TS && iy > 0) Wl |= sm.cand[(ix << 5) | (iy - 1)];
+                if (ix > 0 && iy < TS) Wl |= sm.cand[((ix - 1) << 5) | iy];
+                if (ix > 0 && iy > 0) Wl |= sm.cand[((ix - 1) << 5) | (iy - 1)];
+                sm.refm[ln] |= (unsigned long long)Wl | ((unsigned long long)Wl << 1);
+            }
+        }
+        __syncthreads();
+#endif
         // ---------------------------------------------- compaction of the two bitmaps
         // one prefix sum over the per-thread popcounts (cubes in the low, samples in the high half
         // word), ONE pair of global atomics per tile, then every thread writes its own entries

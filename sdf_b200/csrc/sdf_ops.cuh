@@ -37,6 +37,13 @@ struct ProgramImage {
 };
 
 namespace sdfm {
+// EXPERIMENT (off unless the translation unit defines SDF_EXP_NUMPY_MINMAX): numpy's
+// minimum / maximum return NaN when either operand is NaN, fmin / fmax return the other operand.
+#ifdef SDF_EXP_NUMPY_MINMAX
+#define SDF_MINMAX(T, F, a, b) (((a) != (a) || (b) != (b)) ? ((a) + (b)) : F((a), (b)))
+#else
+#define SDF_MINMAX(T, F, a, b) F((a), (b))
+#endif
 // ----------------------------------------------------------------------------------------------
 // Math policies.  MathP<double, *> and MathP<float, false> use IEEE-rounded division / square
 // root and the accurate libdevice transcendentals.  MathP<float, true> is the throughput path:
@@ -50,8 +57,8 @@ template <bool FAST> struct MathP<double, FAST> {
     static __device__ __forceinline__ T sqrt_(T x) { return sqrt(x); }
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
     static __device__ __forceinline__ T abs_(T x) { return fabs(x); }
-    static __device__ __forceinline__ T min_(T a, T b) { return fmin(a, b); }
-    static __device__ __forceinline__ T max_(T a, T b) { return fmax(a, b); }
+    static __device__ __forceinline__ T min_(T a, T b) { return SDF_MINMAX(T, fmin, a, b); }
+    static __device__ __forceinline__ T max_(T a, T b) { return SDF_MINMAX(T, fmax, a, b); }
     static __device__ __forceinline__ void sincos_(T a, T* s, T* c) { sincos(a, s, c); }
     static __device__ __forceinline__ T atan2_(T y, T x) { return atan2(y, x); }
     static __device__ __forceinline__ T hypot_(T x, T y) { return hypot(x, y); }
@@ -71,8 +78,8 @@ template <> struct MathP<float, false> {
     static __device__ __forceinline__ T sqrt_(T x) { return sqrtf(x); }
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
     static __device__ __forceinline__ T abs_(T x) { return fabsf(x); }
-    static __device__ __forceinline__ T min_(T a, T b) { return fminf(a, b); }
-    static __device__ __forceinline__ T max_(T a, T b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ T min_(T a, T b) { return SDF_MINMAX(T, fminf, a, b); }
+    static __device__ __forceinline__ T max_(T a, T b) { return SDF_MINMAX(T, fmaxf, a, b); }
     static __device__ __forceinline__ void sincos_(T a, T* s, T* c) { sincosf(a, s, c); }
     static __device__ __forceinline__ T atan2_(T y, T x) { return atan2f(y, x); }
     static __device__ __forceinline__ T hypot_(T x, T y) { return sqrtf(x * x + y * y); }

@@ -354,6 +354,16 @@ static int env_int(const char* name, int dflt) {
 // `share` / `kn`: the tile kernels' sample grouping (tile_eval_body); ignored by the other kernels.
 static std::string jit_source(const sdfb200_prog* p, int kernel, int share, int kn) {
     std::ostringstream o;
+    // experiments: SDFB200_JIT_DEFINES="NAME[=V] NAME2 ..." become #defines of the translation unit
+    // (part of the source, hence of the cache key); unset in normal operation
+    if (const char* defs = getenv("SDFB200_JIT_DEFINES")) {
+        std::istringstream in(defs);
+        std::string tok;
+        while (in >> tok) {
+            const size_t eq = tok.find('=');
+            o << "#define " << (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) << "\n";
+        }
+    }
     o << "#define SDF_JIT_KERNEL " << kernel << "\n#include \"sdf_kernels.cuh\"\n";
     if (kernel >= 1 && kernel <= 4) {
         double frac = 0;
@@ -588,7 +598,20 @@ static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true)
                         "specialisation is unavailable: %s", (prog)->code.size(), (prog)->jit_log.c_str());  \
     } while (0)
 
+// EXPERIMENT: SDFB200_EXP_CARVEOUT=1 asks for the maximum shared-memory
+// carve-out on every kernel of the step, so that the SMs are not reconfigured between the pre-pass (no
+// shared memory) and the 144 KB tile kernel.  Off unless the variable is set.
+static bool exp_carveout() {
+    const char* e = getenv("SDFB200_EXP_CARVEOUT");
+    return e && atoi(e) != 0;
+}
+
 static cudaError_t jit_launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
+    if (exp_carveout()) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaKernelSetAttributeForDevice(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared, dev);
+    }
     return cudaLaunchKernel((const void*)k, grid, block, args, smem, stream);
 }
 
@@ -1033,6 +1056,10 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                             CUDA_TRY(cudaFuncSetAttribute(extract_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExtractSmem)));
                             attr_set[device] = true;
                         }
+                    }
+                    if (exp_carveout()) {
+                        cudaFuncSetAttribute(extract_kernel<kTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                        cudaFuncSetAttribute(batch_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                     }
                     extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, sizeof(ExtractSmem), stream>>>(
                         g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor);

@@ -270,6 +270,22 @@ def test_sample_grouping_plan_follows_the_tree_structure():
         os.environ.pop('SDFB200_JIT_SHARE'); os.environ.pop('SDFB200_JIT_N')
 
 
+def test_experiment_switches_compile():
+    """The opt-in experiments of DESIGN.md section 8 (SDFB200_JIT_DEFINES) keep compiling; unset, they
+    leave the generated source untouched."""
+    import os
+    prog = ir.lower(models.CONFIGS['gearlike'](sdf_b200))
+    base = _abi.ProgramHandle(prog).jit_probe(4)
+    os.environ['SDFB200_JIT_DEFINES'] = 'SDF_EXP_REFM_GATHER SDF_EXP_NUMPY_MINMAX=1'
+    try:
+        h = _abi.ProgramHandle(prog)
+        sizes = [h.jit_probe(k) for k in (0, 4, 7, 8)]
+    finally:
+        os.environ.pop('SDFB200_JIT_DEFINES')
+    assert all(sz > 10000 for sz in sizes) and sizes[1] != base
+    assert _abi.ProgramHandle(prog).jit_probe(4) == base
+
+
 def test_specialised_kernels_are_cached_on_disk(tmp_path):
     import os, time
     old = os.environ.get('SDFB200_JIT_CACHE')

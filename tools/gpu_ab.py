@@ -38,6 +38,11 @@ def main():
     ap.add_argument('--models', default='gearlike,knurling,csg,blobby,sphere')
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--grid', type=int, default=0)
+    ap.add_argument('--variants', default='flat4,auto',
+                    help='comma list of: flat4, auto, col11 (z columns of 11 whatever the plan says), gather '
+                         '(SDF_EXP_REFM_GATHER), minmax (SDF_EXP_NUMPY_MINMAX), carveout (SDFB200_EXP_CARVEOUT), '
+                         'and combinations joined with + (e.g. auto+gather+carveout)')
+    ap.add_argument('--no-host-output', action='store_true')
     args = ap.parse_args()
     os.environ['SDFB200_JIT'] = '2'
     import torch
@@ -59,8 +64,12 @@ def main():
         prog = lower(f)
         tau = core.mixed_tau(prog, X, Y, Z)
         out = None
-        for label, share, group in (('flat4', '-1', '4'), ('auto', None, None)):
-            for k, v in (('SDFB200_JIT_SHARE', share), ('SDFB200_JIT_N', group)):
+        for label in args.variants.split(','):
+            parts = label.split('+')
+            share, group = ('-1', '4') if 'flat4' in parts else (('2', '11') if 'col11' in parts else (None, None))
+            defines = ' '.join(d for d, key in (('SDF_EXP_REFM_GATHER', 'gather'), ('SDF_EXP_NUMPY_MINMAX', 'minmax')) if key in parts)
+            for k, v in (('SDFB200_JIT_SHARE', share), ('SDFB200_JIT_N', group), ('SDFB200_JIT_DEFINES', defines or None),
+                         ('SDFB200_EXP_CARVEOUT', '1' if 'carveout' in parts else None)):
                 if v is None:
                     os.environ.pop(k, None)
                 else:
@@ -89,9 +98,9 @@ def main():
                                   extract_ms=round(float(med[4]), 4), tile_eval_min_ms=round(float(a[:, 2].min()), 4))), flush=True)
             del h
         # pipelined host output through the public API (automatic grouping)
-        os.environ.pop('SDFB200_JIT_SHARE', None)
-        os.environ.pop('SDFB200_JIT_N', None)
-        for rounds in ('1', '2', '4', '8'):
+        for k in ('SDFB200_JIT_SHARE', 'SDFB200_JIT_N', 'SDFB200_JIT_DEFINES', 'SDFB200_EXP_CARVEOUT'):
+            os.environ.pop(k, None)
+        for rounds in (() if args.no_host_output else ('1', '2', '4', '8')):
             os.environ['SDFB200_PIPE'] = rounds
             ts = []
             for it in range(2 + reps):
