@@ -339,3 +339,27 @@ def test_product_never_imports_the_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle|oracle/|oracle\.|libmc_oracle|sdf_ref', src, re.M), fn
+
+
+def test_integration_md_stub_binds_the_library():
+    """The minimal ctypes stub printed in INTEGRATION.md is executed as written: it loads the library,
+    creates a program and reaches sdfb200_generate (which, without a GPU, reports "no CPU fallback")."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    block = re.search(r"```python\n# sdf/_b200\.py\n(.*?)```", text, re.S).group(1)
+    block = block.replace("ctypes.CDLL('libsdfb200.so')", "ctypes.CDLL(%r)" % os.path.join(root, 'sdf_b200', 'libsdfb200.so'))
+    ns = {}
+    exec(compile(block, 'INTEGRATION.md', 'exec'), ns)
+    prog = ir.lower(sdf_b200.sphere(1))
+    h = ns['program'](np.ascontiguousarray(prog.code, np.uint32), np.ascontiguousarray(prog.consts, np.float64))
+    assert h.value
+    X = np.arange(-1.5, 1.5, 0.1)
+    if _abi.device_count() > 0:
+        pts, stats = ns['generate'](h, X, X, X, capacity=1 << 16)
+        assert len(pts) > 0 and len(pts) % 3 == 0
+    else:
+        with pytest.raises(RuntimeError) as ei:
+            ns['generate'](h, X, X, X, capacity=1 << 10)
+        assert 'no CPU fallback' in str(ei.value)
