@@ -29,6 +29,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <math.h>
+#include <memory>
 #include <new>
 #include <mutex>
 #include <sstream>
@@ -1185,29 +1186,33 @@ extern "C" int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_s
     if (!out || !handle_out || tri_capacity <= 0) return fail(SDFB200_E_INVALID, "shared_create: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     CUDA_TRY(cudaSetDevice(device));
-    sdfb200_shared* s = new (std::nothrow) sdfb200_shared();
+    std::unique_ptr<sdfb200_shared> s(new (std::nothrow) sdfb200_shared());
     if (!s) return fail(SDFB200_E_INVALID, "out of host memory");
     CUDA_TRY(cudaMalloc(&s->base, 256 + (size_t)tri_capacity * 36));
-    CUDA_TRY(cudaMemset(s->base, 0, 256));
     cudaIpcMemHandle_t h;
-    CUDA_TRY(cudaIpcGetMemHandle(&h, s->base));
+    cudaError_t e = cudaMemset(s->base, 0, 256);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, s->base);
+    if (e != cudaSuccess) {
+        cudaFree(s->base);
+        return fail(SDFB200_E_CUDA, "shared_create: %s", cudaGetErrorString(e));
+    }
     memcpy(handle_out, &h, 64);
     s->capacity = tri_capacity; s->device = device; s->owner = true;
-    *out = s;
+    *out = s.release();
     return 0;
 }
 
 extern "C" int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_capacity, int device, sdfb200_shared** out) {
     if (!out || !handle || tri_capacity <= 0) return fail(SDFB200_E_INVALID, "shared_open: bad argument");
     CUDA_TRY(cudaSetDevice(device));
-    sdfb200_shared* s = new (std::nothrow) sdfb200_shared();
+    std::unique_ptr<sdfb200_shared> s(new (std::nothrow) sdfb200_shared());
     if (!s) return fail(SDFB200_E_INVALID, "out of host memory");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->base = (unsigned char*)p; s->capacity = tri_capacity; s->device = device; s->owner = false;
-    *out = s;
+    *out = s.release();
     return 0;
 }
 
