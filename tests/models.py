@@ -59,6 +59,11 @@ CONFIG_GRIDS = {'sphere': (64, 1.25), 'csg': (256, 1.0), 'gearlike': (512, 2.5),
                 'blobby': (768, 4.5), 'knurling': (1024, 2.75)}
 
 
+# Triangle counts of the ORACLE (numpy evaluation + C Lewiner restatement, tests/test_oracle_cpu.py) on the
+# reference-natural grids of configs 3-5 (samples = N^3, reference bounds); the GPU path must reproduce them.
+NATURAL_TRIANGLES = {'gearlike': 2550892, 'blobby': 2278232, 'knurling': 18721558}
+
+
 def node_corpus(ns):
     """One model per node of the 3-D library (d3.py:92-433, dn.py:7-114) that is lowered."""
     X, Y, Z = ns.X, ns.Y, ns.Z

@@ -60,3 +60,5 @@ def test_natural_grids_match_the_reference_classification(name, n, golden_dir):
     assert (info['skipped'], info['empty'], info['nonempty']) == tuple(gold[:3]), (info, gold)
     assert info['active_cubes'] == gold[3], (info['active_cubes'], gold[3])
     assert len(pts) == 3 * info['triangles'] and info['triangles'] >= info['active_cubes']
+    if name in models.NATURAL_TRIANGLES:                      # identical triangle count (north_star's bar) with the oracle
+        assert info['triangles'] == models.NATURAL_TRIANGLES[name], (info['triangles'], models.NATURAL_TRIANGLES[name])

@@ -37,6 +37,20 @@ def test_random_compositions_bit_identical_to_reference(golden_dir):
         assert np.array_equal(d, g['d_%03d' % i], equal_nan=True), i
 
 
+def test_natural_grid_classification_matches_reference(golden_dir):
+    """SURVEY.md section 8(c) table row 3 at FULL size (gearlike, samples = 512^3, the reference's own bounds:
+    732 x 732 x 251 samples, 4,232 batches): the oracle's skipped / empty / nonempty equal the real
+    reference's (tests/golden/natural.npz).  ~20 s on 8 threads."""
+    e, g = np.load(golden_dir + '/engine.npz'), np.load(golden_dir + '/natural.npz')
+    f = models.CONFIGS['gearlike'](sdf_b200)
+    lo, hi = e['bounds_gearlike']
+    pts, st = sdf_ref.generate(f, step=float(g['autostep_gearlike'][0]), bounds=(tuple(lo), tuple(hi)), workers=8)
+    gold = g['auto_gearlike']
+    assert st['dims'] == tuple(gold[4:7])
+    assert (st['skipped'], st['empty'], st['nonempty']) == tuple(gold[:3])
+    assert st['triangles'] == models.NATURAL_TRIANGLES['gearlike'] and len(pts) == 3 * st['triangles']
+
+
 def test_known_answers():
     # SURVEY.md section 8c golden vectors
     s = sdf_b200.sphere(1)
