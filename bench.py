@@ -46,6 +46,12 @@ def workload(n_gpus, grid=None, model='gearlike'):
     return dict(model=model, n=grid, L=L, step=2.0 * L / grid, bounds=((-L, -L, -L), (L, L, L)))
 
 
+def workload_name(w):
+    """The same string in both arms (ours and --impl reference)."""
+    return '%s tree (reference examples/%s.py), %d^3 lattice, bounds +-%g, sparse skip on, batch 32' % (
+        w['model'], w['model'], w['n'], w['L'])
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -204,7 +210,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'Mpoints/s', 'value': val, 'unit': 'Mpoints/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '%s tree, %d^3 lattice, sparse skip on, batch 32' % (w['model'], w['n'])},
+            'config': {'workload': workload_name(w), 'points': w['n'] ** 3, 'precision': 'f64 (the reference arithmetic)'},
             'cpu_baseline': {'value': val, 'unit': 'Mpoints/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d of %d batches per step (seeded); reference numpy closures + ThreadPool(%d) '
                                        'restated in oracle/, MC by the C restatement (skimage unavailable)' % (m, total, cores)},
@@ -344,8 +350,7 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'mixed': 'f32 (+f64 re-evaluation of |d|<tau samples)', 'f32': 'f32', 'f64': 'f64', 'exact': 'f32 classification + f64 for every sample that reaches the output'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': '%s tree (reference examples/%s.py), %d^3 lattice, bounds +-%g, sparse skip on, batch 32'
-                                   % (w['model'], w['model'], w['n'], w['L']),
+            'config': {'workload': workload_name(w),
                        'points': n_points, 'precision': args.precision,
                        'l2': 'flushed between timed iterations (768 MB memset, outside the per-step events)',
                        'parallelism': 'z-slab x%d' % world,
