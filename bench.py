@@ -357,7 +357,7 @@ def run_ours(args):
                        'gather': (args.gather if world > 1 else None),
                        'sample_grouping': dict(zip(('share_axis', 'samples_per_thread', 'invariant_fraction'),
                                                    h.jit_plan({'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}[args.precision]))),
-                       'host_output_rounds': int(os.environ.get('SDFB200_PIPE', 4))},
+                       'host_output_rounds': int(os.environ.get('SDFB200_PIPE', 8))},
             'mtris_per_s': tri_total / (ms_per_step / 1e3) / 1e6, 'triangles': int(tri_total),
             'mpoints_evaluated_per_s': evaluated / (ms_per_step / 1e3) / 1e6,
             'batches': {'skipped': int(agg[4].item()), 'empty': int(agg[5].item()), 'nonempty': int(agg[6].item())},
