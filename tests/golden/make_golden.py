@@ -121,6 +121,14 @@ def main():
         eng['auto_%s' % name] = np.array([r['skipped'], r['empty'], r['nonempty'], r['active'], *r['dims']], np.int64)
         eng['autostep_%s' % name] = np.array([step])
         print('auto', name, r['skipped'], r['empty'], r['nonempty'], r['active'], r['dims'], step)
+    # sample_slice (core.py:202-232): values, extent and axis names of the three orientations
+    f = ref_models['cfg_csg']
+    sb = ((-1.0, -0.9, -0.8), (1.1, 1.0, 0.7))
+    for key, kw in (('x', dict(x=0.13)), ('y', dict(y=-0.2)), ('z', dict(z=0.31))):
+        a, extent, axes = ref.core.sample_slice(f, w=24, h=17, bounds=sb, **kw)
+        eng['slice_' + key] = a
+        eng['slice_extent_' + key] = np.array(extent, np.float64)
+        eng['slice_axes_' + key] = np.array([ord(c) for c in axes], np.int64)
     np.savez_compressed(os.path.join(HERE, 'engine.npz'), **eng)
 
     # random compositions (tests/models.py: random_trees) evaluated by the real reference

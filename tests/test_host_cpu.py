@@ -363,3 +363,22 @@ def test_integration_md_stub_binds_the_library():
         with pytest.raises(RuntimeError) as ei:
             ns['generate'](h, X, X, X, capacity=1 << 10)
         assert 'no CPU fallback' in str(ei.value)
+
+
+def test_sample_slice_host_logic_matches_reference(golden_dir):
+    """core.sample_slice (core.py:202-232): point order, reshape, extent and axis names -- the evaluator is
+    replaced by the oracle here (any callable works once bounds are given), the vectors come from the
+    REAL reference."""
+    from oracle import sdf_ref
+    from sdf_b200 import core
+    g = np.load(golden_dir + '/engine.npz')
+    f = models.CONFIGS['csg'](sdf_b200)
+    cpu = lambda P: sdf_ref.evaluate(f, P)
+    sb = ((-1.0, -0.9, -0.8), (1.1, 1.0, 0.7))
+    for key, kw in (('x', dict(x=0.13)), ('y', dict(y=-0.2)), ('z', dict(z=0.31))):
+        a, extent, axes = core.sample_slice(cpu, w=24, h=17, bounds=sb, **kw)
+        assert a.shape == (24, 17) and np.array_equal(a, g['slice_' + key])
+        assert np.array_equal(np.array(extent, np.float64), g['slice_extent_' + key])
+        assert axes == ''.join(chr(c) for c in g['slice_axes_' + key])
+    with pytest.raises(Exception):
+        core.sample_slice(cpu, bounds=sb)
