@@ -129,6 +129,16 @@ def main():
         eng['slice_' + key] = a
         eng['slice_extent_' + key] = np.array(extent, np.float64)
         eng['slice_axes_' + key] = np.array([ord(c) for c in axes], np.int64)
+    # write_binary_stl (stl.py:4-24) on a seeded soup with one degenerate triangle (0/0 normal)
+    import tempfile
+    rs = np.random.default_rng(77)
+    soup = rs.uniform(-3, 3, (60 * 3, 3))
+    soup[30:33] = soup[30]                                     # zero-area triangle
+    with tempfile.TemporaryDirectory() as td:
+        with np.errstate(all='ignore'):
+            ref.write_binary_stl(os.path.join(td, 'a.stl'), soup)
+        eng['stl_points'] = soup
+        eng['stl_bytes'] = np.frombuffer(open(os.path.join(td, 'a.stl'), 'rb').read(), np.uint8)
     np.savez_compressed(os.path.join(HERE, 'engine.npz'), **eng)
 
     # random compositions (tests/models.py: random_trees) evaluated by the real reference

@@ -382,3 +382,16 @@ def test_sample_slice_host_logic_matches_reference(golden_dir):
         assert axes == ''.join(chr(c) for c in g['slice_axes_' + key])
     with pytest.raises(Exception):
         core.sample_slice(cpu, bounds=sb)
+
+
+def test_binary_stl_bytes_equal_the_reference_writer(golden_dir, tmp_path):
+    """stl.write_binary_stl against the file the REAL reference wrote for the same soup (float32 normals
+    computed operation by operation like numpy, a zero-area triangle's NaN normal included)."""
+    g = np.load(golden_dir + '/engine.npz')
+    path = tmp_path / 'a.stl'
+    with np.errstate(all='ignore'):
+        stl.write_binary_stl(str(path), g['stl_points'])
+    assert path.read_bytes() == g['stl_bytes'].tobytes()
+    with np.errstate(all='ignore'):
+        stl.write_binary_stl(str(path), g['stl_points'].astype(np.float32).reshape(-1, 3))     # what generate() returns
+    assert path.read_bytes() == g['stl_bytes'].tobytes()
