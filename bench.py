@@ -338,12 +338,23 @@ def run_ours(args):
         tri_total, evaluated, refined, cubes = (float(agg[i].item()) for i in range(4))
         peak, peak_src = peaks()
         tile_s = float(tile_t.item()) / 1e3
+        tile_kernel_name = ('tile_sign_body (jit_kernel, <= 592 x 256)' if args.precision == 'exact' else 'tile_eval_body (jit_kernel, 148 x 1024)')
         achieved = (evaluated / world) * 12.0 / tile_s / 1e9 if tile_s > 0 else 0.0     # per-GPU kernel
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
-        if os.path.exists(tpath) and world == 1 and args.grid is None and args.model == 'gearlike':
+        # DRAM traffic of the dominant kernel: an ncu figure (profiles/r2_traffic.json, written from the committed
+        # capture of THIS kernel on THIS workload); reported only when that capture's kernel time agrees with the
+        # time measured in this run -- a stale capture (another kernel version) prints null instead of a number
+        traffic, traffic_note = None, 'no ncu capture for this configuration'
+        tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+        if os.path.exists(tpath) and world == 1 and args.grid is None:
             with open(tpath) as fp:
-                traffic = json.load(fp).get('tile_eval_kernel_dram_bytes_per_launch')
+                rec = json.load(fp).get(args.model + ':' + args.precision)
+            if rec:
+                t_ncu, t_now = float(rec['kernel_us']), tile_s * 1e6
+                if abs(t_ncu - t_now) <= 0.35 * t_now:
+                    traffic = int(rec['dram_bytes_per_launch'])
+                    traffic_note = 'ncu %s (%s): %.1f us per launch under ncu, %.1f us here' % (rec['capture'], rec['kernel'], t_ncu, t_now)
+                else:
+                    traffic_note = 'capture %s is stale: %.1f us under ncu vs %.1f us measured here' % (rec['capture'], t_ncu, t_now)
         line = {
             'metric': 'Mpoints/s', 'value': n_points / (ms_per_step / 1e3) / 1e6, 'unit': 'Mpoints/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -372,13 +383,13 @@ def run_ours(args):
             'e2e': {'value': n_points / e2e_s / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(8 * (len(X) + len(Y) + len(Z))),
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'kernel': 'tile_eval_body (jit_kernel, 148 x 1024)', 'peak_source': peak_src,
+                         'traffic': traffic, 'traffic_source': traffic_note,
+                         'kernel': tile_kernel_name, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': (evaluated / world) * 12.0,
                          'note': 'dominant kernel of the step (tile evaluate + classify); 12 algorithmic B per evaluated '
-                                 'sample (north_star float3 accounting) over its CUDA-event duration; the kernel '
-                                 'generates its samples in registers, so its DRAM traffic (ncu, per launch) is only the '
-                                 'stored tile volumes; it is FP32/MUFU issue bound (ncu of the flat-mapping version: 71 % issue-slot '
-                                 'utilisation; the axis-shared grouping in config.sample_grouping cut its time by 27 %)'},
+                                 'sample (north_star float3 accounting) over its CUDA-event duration, measured live in this '
+                                 'run; the kernel generates its samples in registers from the three lattice axes, so its real '
+                                 'DRAM traffic is far below the algorithmic bytes and it is FP32/MUFU issue bound'},
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_port(w, args.cpu_seconds)

@@ -33,7 +33,7 @@ typedef unsigned long long uintptr_t;
 #define SDFB200_PREC_EXACT 3
 #endif
 
-#define MC_TABLE_QUAL __device__ const
+#define MC_TABLE_QUAL __device__ __align__(16) const
 #include "mc_tables.inc"
 
 // ---------------------------------------------------------------------------------------
@@ -88,16 +88,6 @@ __constant__ int c_interior_edge[12][8] = {
     {4, 5, 7, 6, 3, 2, 0, 1}, {5, 6, 4, 7, 0, 3, 1, 2}, {6, 7, 5, 4, 1, 0, 2, 3}, {7, 4, 6, 5, 2, 1, 3, 0},
     {0, 4, 3, 7, 2, 6, 1, 5}, {1, 5, 0, 4, 3, 7, 2, 6}, {2, 6, 1, 5, 0, 4, 3, 7}, {3, 7, 2, 6, 1, 5, 0, 4}};
 
-// skimage test_face (asymptotic decider with the FLT_EPSILON dead band)
-__device__ __forceinline__ bool mc_test_face(const double* v, int face) {
-    const int af = face < 0 ? -face : face;
-    const double A = v[c_face_corners[af][0]], B = v[c_face_corners[af][1]];
-    const double C = v[c_face_corners[af][2]], D = v[c_face_corners[af][3]];
-    const double acbd = xsub(xmul(A, C), xmul(B, D));
-    if (acbd > -(double)FLT_EPSILON && acbd < (double)FLT_EPSILON) return face >= 0;
-    return xmul(xmul((double)face, A), acbd) >= 0;
-}
-
 // skimage test_internal; mode 12 = cases 4/10, 0..11 = reference edge
 __device__ __forceinline__ bool mc_test_interior(const double* v, int mode, int s) {
     double t, At = 0, Bt = 0, Ct = 0, Dt = 0;
@@ -144,7 +134,7 @@ __device__ __forceinline__ bool mc_test_interior(const double* v, int mode, int 
 // ---------------------------------------------------------------------------------------
 // shared-memory copies of the decision tables ("edge table in shared memory")
 
-struct McTablesSmem {
+struct __align__(16) McTablesSmem {
     unsigned short sub_base[256];
     unsigned short tile_off[MC_TILE_OFF_LEN];
     short sub_true[MC_SUB_TRUE_LEN];
@@ -156,82 +146,25 @@ struct McTablesSmem {
     unsigned char tile_data[MC_TILE_DATA_LEN];
 };
 
+// every table is a multiple of 4 bytes long and 16-byte aligned (MC_TABLE_QUAL): copied as 32-bit words
+__device__ __forceinline__ void copy_table(void* dst, const void* src, int bytes, int tid, int nthreads) {
+    unsigned int* d = reinterpret_cast<unsigned int*>(dst);
+    const unsigned int* s = reinterpret_cast<const unsigned int*>(src);
+    for (int i = tid; i < bytes / 4; i += nthreads) d[i] = s[i];
+}
+
 __device__ __forceinline__ void load_mc_tables(McTablesSmem* t, int tid, int nthreads) {
-    for (int i = tid; i < 256; i += nthreads) { t->sub_base[i] = MC_SUB_BASE[i]; t->nface[i] = MC_NFACE[i]; }
-    for (int i = tid; i < 256 * 6; i += nthreads) t->faces[i] = MC_FACES[i];
-    for (int i = tid; i < MC_TILE_OFF_LEN; i += nthreads) { t->tile_off[i] = MC_TILE_OFF[i]; t->tile_ntri[i] = MC_TILE_NTRI[i]; }
-    for (int i = tid; i < MC_SUB_TRUE_LEN; i += nthreads) {
-        t->sub_true[i] = MC_SUB_TRUE[i]; t->sub_false[i] = MC_SUB_FALSE[i]; t->sub_interior[i] = MC_SUB_INTERIOR[i];
-    }
-    for (int i = tid; i < MC_TILE_DATA_LEN; i += nthreads) t->tile_data[i] = MC_TILE_DATA[i];
-}
-
-__device__ __forceinline__ int mc_select_tiling(const McTablesSmem* t, int index, const double* v) {
-    const int nf = t->nface[index];
-    const int sgn = (__popc(index) <= 4) ? 1 : -1;
-    int mask = 0;
-    for (int j = 0; j < nf; ++j)
-        if (mc_test_face(v, sgn * (int)t->faces[index * 6 + j])) mask |= 1 << j;
-    const int sub = t->sub_base[index] + mask;
-    const int mode = t->sub_interior[sub];
-    if (mode < 0) return t->sub_true[sub];
-    return mc_test_interior(v, mode, 7 * sgn) ? t->sub_true[sub] : t->sub_false[sub];
-}
-
-// Vertex on a cube edge e < 12, same rounding as mc_edge_vertex(): with w = 1/(eps+|v|) per corner,
-// the coordinate along the edge is x + w_far/(w0+w1); across the edge both corners share the
-// coordinate c, where the generic form gives (c*w0 + c*w1)/(w0+w1) = 0 or exactly 1.
-__device__ __forceinline__ void mc_edge_vertex_fast(const double* v, int e, int x, int y, int z, float* out) {
-    const double eps = (double)FLT_EPSILON;
-    const int k0 = edge_corner(e, 0), k1 = edge_corner(e, 1);
-    double v0 = v[0], v1 = v[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) { v0 = (k0 == j) ? v[j] : v0; v1 = (k1 == j) ? v[j] : v1; }
-    const double w0 = xdiv(1.0, xadd(eps, fabs(v0)));
-    const double w1 = xdiv(1.0, xadd(eps, fabs(v1)));
-    const double ff = xadd(w0, w1);
-    const int dx = corner_x(k0) ^ corner_x(k1), dy = corner_y(k0) ^ corner_y(k1);
-    // the corner that sits at coordinate 1 along the edge contributes its weight
-    const int far_is_k1 = dx ? corner_x(k1) : (dy ? corner_y(k1) : corner_z(k1));
-    const double q = xdiv(far_is_k1 ? w1 : w0, ff);
-    const double fx = dx ? q : (double)corner_x(k0);
-    const double fy = dx ? (double)corner_y(k0) : (dy ? q : (double)corner_y(k0));
-    const double fz = (dx | dy) ? (double)corner_z(k0) : q;
-    out[0] = (float)xadd((double)x, fx);
-    out[1] = (float)xadd((double)y, fy);
-    out[2] = (float)xadd((double)z, fz);
-}
-
-// vertex on edge e (12 = centre), Lewiner cube-local coordinates added to (x,y,z)
-__device__ __forceinline__ void mc_edge_vertex(const double* v, int e, int x, int y, int z, float* out) {
-    double fx = 0, fy = 0, fz = 0, ff = 0;
-    const double eps = (double)FLT_EPSILON;
-    if (e == 12) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const double w = xdiv(1.0, xadd(eps, fabs(v[k])));
-            fx = xadd(fx, xmul((double)corner_x(k), w));
-            fy = xadd(fy, xmul((double)corner_y(k), w));
-            fz = xadd(fz, xmul((double)corner_z(k), w));
-            ff = xadd(ff, w);
-        }
-    } else {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int k = edge_corner(e, s);
-            double vk = v[0];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) vk = (k == j) ? v[j] : vk;      // keeps v[] in registers
-            const double w = xdiv(1.0, xadd(eps, fabs(vk)));
-            fx = xadd(fx, xmul((double)corner_x(k), w));
-            fy = xadd(fy, xmul((double)corner_y(k), w));
-            fz = xadd(fz, xmul((double)corner_z(k), w));
-            ff = xadd(ff, w);
-        }
-    }
-    out[0] = (float)xadd((double)x, xdiv(fx, ff));
-    out[1] = (float)xadd((double)y, xdiv(fy, ff));
-    out[2] = (float)xadd((double)z, xdiv(fz, ff));
+    static_assert(MC_TILE_OFF_LEN % 4 == 0 && MC_SUB_TRUE_LEN % 4 == 0 && MC_TILE_DATA_LEN % 4 == 0 &&
+                  MC_SUB_INTERIOR_LEN % 4 == 0 && MC_TILE_NTRI_LEN % 4 == 0, "table lengths");
+    copy_table(t->sub_base, MC_SUB_BASE, sizeof(t->sub_base), tid, nthreads);
+    copy_table(t->tile_off, MC_TILE_OFF, sizeof(t->tile_off), tid, nthreads);
+    copy_table(t->sub_true, MC_SUB_TRUE, sizeof(t->sub_true), tid, nthreads);
+    copy_table(t->sub_false, MC_SUB_FALSE, sizeof(t->sub_false), tid, nthreads);
+    copy_table(t->sub_interior, MC_SUB_INTERIOR, sizeof(t->sub_interior), tid, nthreads);
+    copy_table(t->nface, MC_NFACE, sizeof(t->nface), tid, nthreads);
+    copy_table(t->faces, MC_FACES, sizeof(t->faces), tid, nthreads);
+    copy_table(t->tile_ntri, MC_TILE_NTRI, sizeof(t->tile_ntri), tid, nthreads);
+    copy_table(t->tile_data, MC_TILE_DATA, sizeof(t->tile_data), tid, nthreads);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -244,6 +177,12 @@ __device__ __forceinline__ double eval1_f64(const EV& ev, double px, double py, 
     return d[0];
 }
 
+// One batch = 16 consecutive lanes (two batches per warp): lane 0 evaluates the centre, lanes 1..8 the
+// corners in itertools.product((x0,x1),(y0,y1),(z0,z1)) order, lanes 9..15 idle.  The reference evaluates
+// the corners only when |centre| > half diagonal and stops at the first sign mismatch -- the flag is the
+// same when all nine are evaluated side by side (the field is a pure function), and the pre-pass then
+// costs ONE float64 evaluation of latency instead of nine.
+#define PREPASS_LANES 16
 template <class EV>
 __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc& g, int sparse,
                                                   unsigned char* __restrict__ flags,
@@ -252,34 +191,40 @@ __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc&
                                                   Counters* __restrict__ ctr) {
     const int nzl = g.zb1 - g.zb0;
     const int total = g.nbx * g.nby * nzl;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tb = gt / PREPASS_LANES, k = gt % PREPASS_LANES;
+    const bool in = tb < total;
+    const int t = in ? tb : 0;
     const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
     const int bz = g.zb0 + bzl;
     const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + bz);
     bool skipped = false;
-    if (sparse) {
+    if (sparse) {                                               // (uniform: every lane reaches the shuffles)
         const int ix0 = bx * g.bs, iy0 = by * g.bs, iz0 = bz * g.bs;
         const int ix1 = min(ix0 + g.bs, g.nx - 1), iy1 = min(iy0 + g.bs, g.ny - 1), iz1 = min(iz0 + g.bs, g.nz - 1);
         const double x0 = g.xs[ix0], x1 = g.xs[ix1], y0 = g.ys[iy0], y1 = g.ys[iy1], z0 = g.zs[iz0], z1 = g.zs[iz1];
         const double x = __ddiv_rn(__dadd_rn(x0, x1), 2.0), y = __ddiv_rn(__dadd_rn(y0, y1), 2.0),
                      z = __ddiv_rn(__dadd_rn(z0, z1), 2.0);
-        const double r = fabs(eval1_f64(img, x, y, z));
+        double v = 0.0;
+        if (in && k < 9) {
+            const int c = k - 1;                                // corner id: bit 2 -> x, bit 1 -> y, bit 0 -> z
+            const double px = k == 0 ? x : ((c & 4) ? x1 : x0), py = k == 0 ? y : ((c & 2) ? y1 : y0),
+                         pz = k == 0 ? z : ((c & 1) ? z1 : z0);
+            v = eval1_f64(img, px, py, pz);
+        }
+        const int base = (int)(threadIdx.x & 31u) & ~(PREPASS_LANES - 1);      // lane 0 of this batch inside the warp
+        const double vc = __shfl_sync(0xffffffffu, v, base);
+        const double v0 = __shfl_sync(0xffffffffu, v, base + 1);
+        const bool pos = v0 > 0;                                // values[0] decides the sign (core.py:41-42)
+        const bool mine = (k >= 1 && k <= 8) ? (pos ? (v > 0) : (v < 0)) : true;
+        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+        const bool same = ((bal >> base) & 0xffffu) == 0xffffu;
+        const double r = fabs(vc);
         const double ex = __dsub_rn(x, x0), ey = __dsub_rn(y, y0), ez = __dsub_rn(z, z0);
         const double dd = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
-        if (!(r <= dd)) {
-            // corners in itertools.product((x0,x1),(y0,y1),(z0,z1)) order; values[0] decides the sign
-            const double v0 = eval1_f64(img, x0, y0, z0);
-            const bool pos = v0 > 0;
-            bool same = pos ? (v0 > 0) : (v0 < 0);
-#pragma unroll 1
-            for (int k = 1; k < 8 && same; ++k) {
-                const double v = eval1_f64(img, (k & 4) ? x1 : x0, (k & 2) ? y1 : y0, (k & 1) ? z1 : z0);
-                same = pos ? (v > 0) : (v < 0);
-            }
-            skipped = same;
-        }
+        skipped = !(r <= dd) && same;
     }
+    if (!in || k != 0) return;
     flags[bid] = skipped ? 1 : 0;
     batch_tris[bid] = 0u;
     if (!skipped) {
@@ -298,9 +243,18 @@ __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc&
 
 #define VOL_STRIDE 35968            // floats per stored tile: 33^3 = 35937 rounded up to a multiple of 32
 
+// Geometry of a stored tile, written once by the kernel that allots the slot, so that the flat kernels
+// over the compacted lists (B, C) do not redo tile_geom()'s integer divisions per sample / per cube.
+struct TileMeta {
+    int bx0, by0, bz0;              // lattice index of the batch origin (world mapping of core.py:58-59)
+    unsigned int bid;               // batch id (batch_tris flag)
+    int ox, oy, oz;                 // sub-tile offset inside the batch (samples)
+    unsigned int ext;               // px | py << 8 | pz << 16: sub-tile extent (samples, <= 33)
+};
+
 struct TileLists {
     float* vol;                     // [slot][VOL_STRIDE] float32 tile volumes (tile-local linearisation)
-    uint2* tile_meta;               // [slot] {batch id, sub-tile index}
+    TileMeta* tile_meta;            // [slot]
     uint2* cubes;                   // candidate cubes {slot, tile-local cube id}
     uint2* pts;                     // samples to re-evaluate in float64 {slot, tile-local sample id}
     unsigned int slot_cap, cube_cap, pt_cap;
@@ -311,6 +265,21 @@ struct TileGeom {
     int ox, oy, oz;                 // sub-tile offset inside the batch (samples)
     int px, py, pz;                 // sub-tile extent (samples)
 };
+
+__device__ __forceinline__ TileMeta make_tile_meta(const TileGeom& t, unsigned int bid) {
+    TileMeta m;
+    m.bx0 = t.bx0; m.by0 = t.by0; m.bz0 = t.bz0; m.bid = bid;
+    m.ox = t.ox; m.oy = t.oy; m.oz = t.oz;
+    m.ext = (unsigned int)t.px | ((unsigned int)t.py << 8) | ((unsigned int)t.pz << 16);
+    return m;
+}
+__device__ __forceinline__ TileMeta load_tile_meta(const TileMeta* p) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p)), b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    TileMeta m;
+    m.bx0 = a.x; m.by0 = a.y; m.bz0 = a.z; m.bid = (unsigned int)a.w;
+    m.ox = b.x; m.oy = b.y; m.oz = b.z; m.ext = (unsigned int)b.w;
+    return m;
+}
 
 // batch id + sub-tile index -> extents (core.py:115-117: slices [i, i+s+1) clipped to the axis)
 template <int TS>
@@ -359,12 +328,13 @@ __device__ __forceinline__ int float_to_ordered(float f) {
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
 
-// (A) one CTA per tile: evaluate the lattice samples into shared memory, classify every cube, queue the
-// candidate cubes and the samples float64 must confirm, store the tile volume.
+// (A) for the precisions that keep float32 values: one CTA per tile evaluates the lattice samples into shared
+// memory, classifies every cube, queues the candidate cubes and the samples float64 must confirm, stores
+// the tile volume.
 //   PREC_F32   accurate float32; candidates = cubes with mixed `v > 0` corners
 //   PREC_MIXED accurate float32; samples with |d| < tau are uncertain -> queued for float64
 //   PREC_F64   float64 evaluation of every sample
-//   PREC_EXACT fast float32; uncertain samples AND every corner of a candidate cube queued for float64
+//   (PREC_EXACT -- the default -- needs no values at all: tile_sign_body below)
 template <int TS, int PREC, int THREADS, class EV>
 __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, const float tau,
                                                const unsigned int* __restrict__ active_list,
@@ -373,7 +343,8 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool F64 = (PREC == SDFB200_PREC_F64);
     constexpr bool REFINE = (PREC == SDFB200_PREC_MIXED || PREC == SDFB200_PREC_EXACT);
-    constexpr bool EXACT = (PREC == SDFB200_PREC_EXACT);
+    static_assert(PREC != SDFB200_PREC_EXACT, "precision `exact` runs tile_sign_body (no value tile)");
+    constexpr bool EXACT = false;
     using S = TileSmem<TS, F64>;
     S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -560,34 +531,10 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
                     c64 |= (u0 | (u0 >> 1)) | (u1 | (u1 >> 1)) | (u2 | (u2 >> 1)) | (u3 | (u3 >> 1));
                 }
                 W = (unsigned int)c64 & (czn >= 32 ? 0xffffffffu : ((1u << czn) - 1u));
-#ifndef SDF_EXP_REFM_GATHER
-                if (EXACT && W) {
-                    const unsigned long long zm = (unsigned long long)W | ((unsigned long long)W << 1);
-                    atomicOr(&sm.refm[l00], zm); atomicOr(&sm.refm[l01], zm);
-                    atomicOr(&sm.refm[l10], zm); atomicOr(&sm.refm[l11], zm);
-                }
-#endif
             }
             sm.cand[col] = W;
         }
         __syncthreads();
-#ifdef SDF_EXP_REFM_GATHER
-        // EXPERIMENT: every z-line collects the candidate words of its (up to) four
-        // adjacent cube columns instead of the columns scattering 64-bit shared-memory atomics (which
-        // compile to CAS spin loops) into the lines.
-        if (EXACT) {
-            for (int ln = tid; ln < nlines; ln += THREADS) {
-                const int ix = ln / py, iy = ln - ix * py;
-                unsigned int Wl = 0u;
-                if (ix < TS && iy < TS) Wl |= sm.cand[(ix << 5) | iy];
-                if (ix < TS && iy > 0) Wl |= sm.cand[(ix << 5) | (iy - 1)];
-                if (ix > 0 && iy < TS) Wl |= sm.cand[((ix - 1) << 5) | iy];
-                if (ix > 0 && iy > 0) Wl |= sm.cand[((ix - 1) << 5) | (iy - 1)];
-                sm.refm[ln] |= (unsigned long long)Wl | ((unsigned long long)Wl << 1);
-            }
-        }
-        __syncthreads();
-#endif
         // ---------------------------------------------- compaction of the two bitmaps
         // one prefix sum over the per-thread popcounts (cubes in the low, samples in the high half
         // word), ONE pair of global atomics per tile, then every thread writes its own entries
@@ -645,7 +592,7 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
         if (live && sm.any_cand) {
             float* dst = L.vol + (size_t)slot * VOL_STRIDE;
             for (int i = tid; i < npts; i += THREADS) dst[i] = sm.tile[i];
-            if (tid == 0) L.tile_meta[slot] = make_uint2(bid, (unsigned int)sidx);
+            if (tid == 0) L.tile_meta[slot] = make_tile_meta(t, bid);
         }
         __syncthreads();                                      // everyone is done with this tile's state
         if (tid == 0) {
@@ -659,6 +606,251 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
     if (tid == 0) atomicAdd(&ctr->pts_f32, my_pts);
 }
 
+// ---------------------------------------------------------------------------------------
+// (A') PREC_EXACT: evaluate + classify WITHOUT a value tile.
+//
+// In `exact` mode every float32 value that could reach the output is re-evaluated in float64 by (B), so
+// the fast pass only has to answer two questions per sample: "is it > 0" and "is |d| < tau".  Both are
+// single predicate bits, and with the lanes of a warp laid along one lattice axis a __ballot_sync turns
+// 32 samples into one mask word while they are produced -- no 144 KB shared-memory value tile, no
+// per-sample index division, no serial mask loop, no shared atomics, no min/max reduction (a tile
+// whose masks hold no mixed cube simply yields no candidates: skimage's "level within data range"
+// check, core.py:53-56), no tile store.
+//
+// Work item = (tile, chunk of SIGN_PW planes along the tile's W axis); CTAs are small (256 threads,
+// several per SM) and take items from one global cursor, so the sparse, uneven work balances at a
+// granularity of 1/7 tile.  A thread evaluates N consecutive samples along the share axis S (they
+// share their other two coordinates, i.e. registers: the axis-sharing of the generated evaluator),
+// its lane is the coordinate along the lane axis U.  Lanes 0..31 cover samples 0..31 of a U-line; the
+// 33rd sample of every line (the plane shared with the next tile) is evaluated by separate
+// thread-runs that write one byte per line.  Masks go to a per-tile scratch block in global memory
+// (10 KB, L2 resident); the CTA that completes a tile's last chunk (device-scope counter) classifies
+// the tile's 32^3 cubes with 64-bit word operations, compacts the candidate cubes and the samples
+// float64 must confirm, and allots the tile's volume slot.
+#define SIGN_TP 33
+#define SIGN_LINES (SIGN_TP * SIGN_TP)
+#define SIGN_PW 5                                               // W planes per work item
+#define SIGN_NCH ((SIGN_TP + SIGN_PW - 1) / SIGN_PW)            // work items per tile (7)
+#define SIGN_STRIDE 9856                                        // bytes of scratch per tile: 1089 x {u32, u32} + 1089 u8, padded
+#define SIGN_THREADS 256
+#define SIGN_BLOCKS_PER_SM 4
+
+struct SignSmem {
+    float ax[3][SIGN_TP + 3];
+    unsigned int cand[32 * 32];                                 // per (cs, cw): bit cu <=> cube is a candidate
+    unsigned long long refm[SIGN_LINES];                        // per (is, iw) line: bit iu <=> sample queued for float64
+    unsigned int warp_sums[SIGN_THREADS / 32];
+    unsigned int item, last, slot, cube_gbase, pt_gbase;
+};
+
+template <int TS, int THREADS, class EV>
+__device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, const float tau,
+                                               const unsigned int* __restrict__ active_list,
+                                               const unsigned int work_begin, const unsigned int work_end_arg,
+                                               const TileLists L, Counters* __restrict__ ctr,
+                                               unsigned char* __restrict__ scratch, unsigned int* __restrict__ tile_done) {
+    static_assert(TS == 32 && THREADS == SIGN_THREADS, "one mask word per line; SignSmem is sized for SIGN_THREADS");
+    constexpr int TP = SIGN_TP;
+    constexpr int N = EV::kN;
+    constexpr int AS = EV::kShare < 0 ? 2 : EV::kShare;        // share axis (thread-run), lane axis, chunk axis
+    constexpr int AU = AS == 2 ? 1 : 2;
+    constexpr int AW = AS == 0 ? 1 : 0;
+    constexpr int NW = THREADS / 32;
+    __shared__ SignSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
+    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
+    const unsigned int n_items = (work_end > work_begin ? work_end - work_begin : 0u) * SIGN_NCH;
+
+    if (tid == 0) sm.item = atomicAdd(&ctr->work_cursor, 1u);
+    __syncthreads();
+    for (;;) {
+        const unsigned int q = sm.item;
+        if (q >= n_items) break;
+        const unsigned int tw = q / SIGN_NCH;
+        const int ch = (int)(q - tw * SIGN_NCH);
+        const unsigned int w = work_begin + tw;
+        const unsigned int bid = active_list[w / subs3];
+        const int sidx = (int)(w % subs3);
+        TileGeom t;
+        const bool valid = tile_geom<TS>(g, bid, sidx, t);
+        // a tile that is one sample thick along some axis holds no cube (the reference still evaluates it,
+        // skimage raises, the batch counts as empty: core.py:53-56): nothing to evaluate
+        const bool thin = !valid || t.px < 2 || t.py < 2 || t.pz < 2;
+        const int ext[3] = {thin ? 0 : t.px, thin ? 0 : t.py, thin ? 0 : t.pz};
+        const int pu = ext[AU], ps = ext[AS], pw = ext[AW];
+        for (int i = tid; i < 3 * TP; i += THREADS) {
+            const int a = i / TP, j = i - a * TP;
+            const double* ap = a == 0 ? g.xs + (t.bx0 + t.ox) : (a == 1 ? g.ys + (t.by0 + t.oy) : g.zs + (t.bz0 + t.oz));
+            const int ea = a == 0 ? ext[0] : (a == 1 ? ext[1] : ext[2]);
+            if (j < ea) sm.ax[a][j] = (float)ap[j];
+        }
+        __syncthreads();
+        unsigned int next_item = 0;
+        if (tid == 0) next_item = atomicAdd(&ctr->work_cursor, 1u);       // consumed at the bottom of the loop
+
+        uint2* const masks = reinterpret_cast<uint2*>(scratch + (size_t)tw * SIGN_STRIDE);      // per line {pos, unc}, bits 0..31
+        unsigned char* const hi = reinterpret_cast<unsigned char*>(masks + SIGN_LINES);       // per line bit 32: pos | unc << 1
+
+        // ---------------------------------------------------------------- evaluation
+        const int w0 = ch * SIGN_PW;
+        const int pwi = max(0, min(SIGN_PW, pw - w0));
+        const int runs_s = (ps + N - 1) / N;
+        const int r_main = pwi * runs_s;
+        const int r_extra = (pu == TP) ? (r_main + 31) / 32 : 0;
+        const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
+        for (int r = warp; r < r_main + r_extra; r += NW) {
+            const bool main_run = r < r_main;                         // warp uniform
+            int rr = main_run ? r : (r - r_main) * 32 + lane;
+            const bool on = rr < r_main;
+            if (!on) rr = 0;
+            const int wi = rr / runs_s, sr = rr - wi * runs_s;
+            const int iw = w0 + wi, is0 = sr * N;
+            const int iu = main_run ? min(lane, pu - 1) : TP - 1;
+            const float cu = sm.ax[AU][iu], cw = sm.ax[AW][iw];
+            float c[3][N], d[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                c[AU][k] = cu; c[AW][k] = cw;
+                c[AS][k] = sm.ax[AS][min(is0 + k, ps - 1)];
+            }
+            ev.template run<float, N, true>(c[0], c[1], c[2], d);
+            if (main_run) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
+                    const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
+                    if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
+                }
+            } else if (on) {
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                    if (is0 + k < ps)
+                        hi[(is0 + k) * TP + iw] = (unsigned char)((d[k] > 0.0f ? 1u : 0u) | (fabsf(d[k]) < tau ? 2u : 0u));
+            }
+        }
+        // ------------------------------------------------- who completes the tile classifies it
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int old = atomicAdd(&tile_done[tw], 1u);
+            const unsigned int last = (old == SIGN_NCH - 1) ? 1u : 0u;
+            if (last) tile_done[tw] = 0u;                               // ready for the next launch
+            sm.last = last;
+        }
+        __syncthreads();
+        if (sm.last && !thin) {                                          // CTA uniform
+            __threadfence();
+            // (1) one thread per (cs, cw) column of cubes: 32 cubes along U classified with word operations.
+            //     A cube is a candidate when its corners are not all > 0 and not all <= 0, or one is uncertain.
+            const bool has_hi = (pu == TP);
+            const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
+            for (int col = tid; col < TS * TS; col += THREADS) {
+                const int cs = col >> 5, cw = col & 31;
+                unsigned int W = 0u;
+                if (cs < ps - 1 && cw < pw - 1) {
+                    const int l00 = cs * TP + cw;
+                    const int ls[4] = {l00, l00 + 1, l00 + TP, l00 + TP + 1};
+                    unsigned long long allp = ~0ull, anyp = 0ull, anyu = 0ull;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ls[j]) : 0u;
+                        const uint2 mk = __ldcg(masks + ls[j]);
+                        const unsigned long long p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
+                        const unsigned long long u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
+                        allp &= p & (p >> 1); anyp |= p | (p >> 1); anyu |= u | (u >> 1);
+                    }
+                    W = (unsigned int)((anyp & ~allp) | anyu) & cumask;
+                }
+                sm.cand[col] = W;
+            }
+            __syncthreads();
+            // (2) one thread per line: queue every corner of a candidate cube (and every uncertain sample)
+            for (int ln = tid; ln < SIGN_LINES; ln += THREADS) {
+                const int is = ln / TP, iw = ln - is * TP;
+                unsigned long long ref = 0ull;
+                if (is < ps && iw < pw) {
+                    unsigned int Wl = 0u;
+                    if (is < TS && iw < TS) Wl |= sm.cand[(is << 5) | iw];
+                    if (is < TS && iw > 0) Wl |= sm.cand[(is << 5) | (iw - 1)];
+                    if (is > 0 && iw < TS) Wl |= sm.cand[((is - 1) << 5) | iw];
+                    if (is > 0 && iw > 0) Wl |= sm.cand[((is - 1) << 5) | (iw - 1)];
+                    const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ln) : 0u;
+                    ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | (unsigned long long)__ldcg(masks + ln).y |
+                          ((unsigned long long)((h8 >> 1) & 1u) << 32);
+                }
+                sm.refm[ln] = ref;
+            }
+            __syncthreads();
+            // (3) compaction: one prefix sum over the per-thread popcounts (cubes in the low, samples in the
+            //     high half word), one slot + one pair of list ranges per tile, every thread writes its entries
+            unsigned int cnt = 0;
+            for (int wi = tid; wi < TS * TS; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
+            for (int wi = tid; wi < SIGN_LINES; wi += THREADS) cnt += ((unsigned)__popcll(sm.refm[wi])) << 16;
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            if (lane == 31) sm.warp_sums[warp] = incl;
+            __syncthreads();
+            unsigned int warp_off = 0, total = 0;
+#pragma unroll
+            for (int wi = 0; wi < NW; ++wi) {
+                const unsigned int sv = sm.warp_sums[wi];
+                if (wi < warp) warp_off += sv;
+                total += sv;
+            }
+            if (tid == 0) {
+                const unsigned int nc = total & 0xffffu, np = total >> 16;
+                unsigned int slot = 0;
+                if (nc | np) {
+                    slot = atomicAdd(&ctr->n_slots, 1u);
+                    if (slot < L.slot_cap) L.tile_meta[slot] = make_tile_meta(t, bid);
+                }
+                sm.slot = slot;
+                sm.cube_gbase = nc ? atomicAdd(&ctr->n_cubes, nc) : 0u;
+                sm.pt_gbase = np ? atomicAdd(&ctr->n_pts, np) : 0u;
+                atomicAdd(&ctr->pts_f32, (unsigned long long)(t.px * t.py * t.pz));
+            }
+            __syncthreads();
+            const unsigned int slot = sm.slot;
+            const unsigned int excl = warp_off + incl - cnt;
+            unsigned int cat = sm.cube_gbase + (excl & 0xffffu);
+            unsigned int pat = sm.pt_gbase + (excl >> 16);
+            if (slot < L.slot_cap) {
+                for (int wi = tid; wi < TS * TS; wi += THREADS) {
+                    unsigned int word = sm.cand[wi];
+                    int cc[3];
+                    cc[AS] = wi >> 5; cc[AW] = wi & 31;
+                    while (word) {
+                        cc[AU] = __ffs(word) - 1;
+                        word &= word - 1u;
+                        // cube id with fixed strides: cx << 10 | cy << 5 | cz
+                        if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)((cc[0] << 10) | (cc[1] << 5) | cc[2]));
+                        ++cat;
+                    }
+                }
+                for (int wi = tid; wi < SIGN_LINES; wi += THREADS) {
+                    unsigned long long word = sm.refm[wi];
+                    int ii[3];
+                    ii[AS] = wi / TP; ii[AW] = wi - ii[AS] * TP;
+                    while (word) {
+                        ii[AU] = __ffsll((long long)word) - 1;
+                        word &= word - 1ull;
+                        if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)((ii[0] * t.py + ii[1]) * t.pz + ii[2]));
+                        ++pat;
+                    }
+                }
+            }
+        }
+        __syncthreads();                                      // everyone is done with this item's shared state
+        if (tid == 0) sm.item = next_item;
+        __syncthreads();
+    }
+}
+
 // (B) float64 re-evaluation of the queued samples, flat over the whole list.
 template <int TS, class EV>
 __device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc& g, const TileLists L,
@@ -666,35 +858,106 @@ __device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc&
     const unsigned int n = min(ctr->n_pts, L.pt_cap);
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint2 e = L.pts[i];
-        const uint2 meta = L.tile_meta[e.x];
-        TileGeom t;
-        tile_geom<TS>(g, meta.x, (int)meta.y, t);
-        const unsigned int pyz = (unsigned int)(t.py * t.pz);
-        const unsigned int ix = e.y / pyz, rem = e.y - ix * pyz, iy = rem / (unsigned)t.pz, iz = rem - iy * t.pz;
-        double x[1] = {g.xs[t.bx0 + t.ox + ix]}, y[1] = {g.ys[t.by0 + t.oy + iy]}, z[1] = {g.zs[t.bz0 + t.oz + iz]}, d[1];
+        const TileMeta m = load_tile_meta(L.tile_meta + e.x);
+        const unsigned int py = (m.ext >> 8) & 0xffu, pz = (m.ext >> 16) & 0xffu;
+        const unsigned int pyz = py * pz;
+        const unsigned int ix = e.y / pyz, rem = e.y - ix * pyz, iy = rem / pz, iz = rem - iy * pz;
+        double x[1] = {g.xs[m.bx0 + m.ox + (int)ix]}, y[1] = {g.ys[m.by0 + m.oy + (int)iy]},
+               z[1] = {g.zs[m.bz0 + m.oz + (int)iz]}, d[1];
         ev.template run<double, 1, false>(x, y, z, d);
         L.vol[(size_t)e.x * VOL_STRIDE + e.y] = (float)d[0];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->pts_f64, (unsigned long long)n);
 }
 
-// (C) Lewiner marching cubes over the candidate list: one thread per cube selects the tiling
-// (tables in shared memory), a CTA prefix sum reserves the output range with one global atomic,
-// every thread then writes its cube's triangles (world-mapped, core.py:58-60).
+// (C) Lewiner marching cubes over the candidate list, two phases per CTA iteration of 256 cubes:
+//   1. one thread per CUBE: gather the 8 corner values (float64-confirmed by B), cube index, tiling
+//      selection (decision tables in shared memory; test_face / test_interior in non-contracted float64),
+//      triangle count; a CTA prefix sum reserves the output range with one global atomic;
+//   2. one thread per TRIANGLE (found by binary search in the prefix array): its three edge vertices
+//      (inverse-|value| weights, float64, rounded like the C restatement), world mapping (core.py:58-60),
+//      staged per warp in shared memory and written out as one contiguous, fully coalesced run -- to
+//      local HBM, or to the root GPU over NVLink in the multi-GPU case.
+// Splitting by triangle balances the lanes (a cube yields 0..12 triangles) and keeps the corner values
+// in shared memory, where the data-dependent corner indices of the tables cost one load instead of a
+// register-select chain or a local-memory array.
 #define EXTRACT_THREADS 256
 #ifndef EXTRACT_BLOCKS_PER_SM
-#define EXTRACT_BLOCKS_PER_SM 3      // register cap 85/thread: the fp64 divides are latency bound, occupancy wins
+#define EXTRACT_BLOCKS_PER_SM 4
 #endif
-
-#define EXTRACT_STAGE_TRIS 1024        // triangles of one CTA iteration staged in shared memory (36 KB)
 
 struct ExtractSmem {
     McTablesSmem mc;
-    float stage[EXTRACT_STAGE_TRIS * 9];
+    float cv[8][EXTRACT_THREADS];                   // corner values of this iteration's cubes
+    int org[6][EXTRACT_THREADS];                    // batch origin (bx0, by0, bz0), Lewiner cube position (lx, ly, lz)
+    unsigned int pre[EXTRACT_THREADS];              // exclusive prefix of the triangle counts
+    unsigned short toff[EXTRACT_THREADS];           // offset of the cube's tiling in tile_data
+    float stage[EXTRACT_THREADS / 32][32 * 9];
     unsigned int warp_sums[EXTRACT_THREADS / 32];
     unsigned long long tri_base;
-    unsigned int n_active;
 };
+
+// corner k of the thread's cube: cvp[k * EXTRACT_THREADS]
+__device__ __forceinline__ double cvd(const float* cvp, int k) { return (double)cvp[k * EXTRACT_THREADS]; }
+
+__device__ __forceinline__ bool mc_test_face_s(const float* cvp, int face) {
+    const int af = face < 0 ? -face : face;
+    const double A = cvd(cvp, c_face_corners[af][0]), B = cvd(cvp, c_face_corners[af][1]);
+    const double C = cvd(cvp, c_face_corners[af][2]), D = cvd(cvp, c_face_corners[af][3]);
+    const double acbd = xsub(xmul(A, C), xmul(B, D));
+    if (acbd > -(double)FLT_EPSILON && acbd < (double)FLT_EPSILON) return face >= 0;
+    return xmul(xmul((double)face, A), acbd) >= 0;
+}
+
+__device__ __forceinline__ int mc_select_tiling_s(const McTablesSmem* t, int index, const float* cvp) {
+    const int nf = t->nface[index];
+    const int sgn = (__popc(index) <= 4) ? 1 : -1;
+    int mask = 0;
+    for (int j = 0; j < nf; ++j)
+        if (mc_test_face_s(cvp, sgn * (int)t->faces[index * 6 + j])) mask |= 1 << j;
+    const int sub = t->sub_base[index] + mask;
+    const int mode = t->sub_interior[sub];
+    if (mode < 0) return t->sub_true[sub];
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = cvd(cvp, k);
+    return mc_test_interior(v, mode, 7 * sgn) ? t->sub_true[sub] : t->sub_false[sub];
+}
+
+// Vertex on edge e (12 = centre) of the cube whose corner values are cvp[k * EXTRACT_THREADS], Lewiner
+// cube-local coordinates added to (x,y,z).  With w = 1/(eps+|v|) per corner the coordinate along an edge
+// is x + w_far/(w0+w1); across the edge both corners share the coordinate c, where the generic form
+// (c*w0 + c*w1)/(w0+w1) gives 0 or exactly 1.  1/x is the correctly rounded reciprocal (== 1.0/x).
+__device__ __forceinline__ void mc_vertex_s(const float* cvp, int e, int x, int y, int z, float* out) {
+    const double eps = (double)FLT_EPSILON;
+    double fx, fy, fz;
+    if (e < 12) {
+        const int k0 = edge_corner(e, 0), k1 = edge_corner(e, 1);
+        const double w0 = __drcp_rn(xadd(eps, fabs(cvd(cvp, k0))));
+        const double w1 = __drcp_rn(xadd(eps, fabs(cvd(cvp, k1))));
+        const double ff = xadd(w0, w1);
+        const int dx = corner_x(k0) ^ corner_x(k1), dy = corner_y(k0) ^ corner_y(k1);
+        const int far_is_k1 = dx ? corner_x(k1) : (dy ? corner_y(k1) : corner_z(k1));
+        const double q = xdiv(far_is_k1 ? w1 : w0, ff);
+        fx = dx ? q : (double)corner_x(k0);
+        fy = dx ? (double)corner_y(k0) : (dy ? q : (double)corner_y(k0));
+        fz = (dx | dy) ? (double)corner_z(k0) : q;
+    } else {
+        double sx = 0, sy = 0, sz = 0, ff = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double w = __drcp_rn(xadd(eps, fabs(cvd(cvp, k))));
+            sx = xadd(sx, xmul((double)corner_x(k), w));
+            sy = xadd(sy, xmul((double)corner_y(k), w));
+            sz = xadd(sz, xmul((double)corner_z(k), w));
+            ff = xadd(ff, w);
+        }
+        fx = xdiv(sx, ff); fy = xdiv(sy, ff); fz = xdiv(sz, ff);
+    }
+    out[0] = (float)xadd((double)x, fx);
+    out[1] = (float)xadd((double)y, fy);
+    out[2] = (float)xadd((double)z, fz);
+}
 
 // `cursor`: where output ranges are reserved.  Normally &ctr->tri_cursor of this GPU; for the fused
 // multi-GPU gather it is a cursor in the ROOT GPU's memory (mapped through CUDA IPC) and `tri_out` is
@@ -706,38 +969,42 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
                                              unsigned int* __restrict__ batch_tris, float* __restrict__ tri_out,
                                              const unsigned long long tri_capacity,
                                              unsigned long long* __restrict__ ext_cursor) {
-    extern __shared__ __align__(16) unsigned char extract_smem_raw[];
-    ExtractSmem& sm = *reinterpret_cast<ExtractSmem*>(extract_smem_raw);
+    __shared__ ExtractSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     load_mc_tables(&sm.mc, tid, EXTRACT_THREADS);
     const unsigned int n = min(ctr->n_cubes, L.cube_cap);
     const unsigned int n_up = (n + EXTRACT_THREADS - 1) / EXTRACT_THREADS * EXTRACT_THREADS;
     unsigned int my_active = 0;
+    const float* cvp = &sm.cv[0][tid];
     __syncthreads();
     for (unsigned int i0 = blockIdx.x * EXTRACT_THREADS; i0 < n_up; i0 += gridDim.x * EXTRACT_THREADS) {
+        // ------------------------------------------------------------ phase 1: one thread per cube
         const unsigned int i = i0 + tid;
-        double v[8];
-        int tiling = -1;
         unsigned int nt = 0;
-        uint2 e = make_uint2(0u, 0u), meta = make_uint2(0u, 0u);
-        TileGeom t;
-        int cx = 0, cy = 0, cz = 0;
         if (i < n) {
-            e = L.cubes[i];
-            meta = L.tile_meta[e.x];
-            tile_geom<TS>(g, meta.x, (int)meta.y, t);
-            const int pz = t.pz, pyz = t.py * t.pz;
-            cx = (int)(e.y >> 10); cy = (int)((e.y >> 5) & 31u); cz = (int)(e.y & 31u);
-            const float* p = L.vol + (size_t)e.x * VOL_STRIDE + (size_t)((cx * t.py + cy) * pz + cz);
-            v[0] = (double)p[0]; v[1] = (double)p[1]; v[2] = (double)p[pz + 1]; v[3] = (double)p[pz];
-            v[4] = (double)p[pyz]; v[5] = (double)p[pyz + 1]; v[6] = (double)p[pyz + pz + 1]; v[7] = (double)p[pyz + pz];
-            int index = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) index |= (v[k] > 0.0) ? (1 << k) : 0;
+            const uint2 e = L.cubes[i];
+            const TileMeta m = load_tile_meta(L.tile_meta + e.x);
+            const int py = (int)((m.ext >> 8) & 0xffu), pz = (int)((m.ext >> 16) & 0xffu), pyz = py * pz;
+            const int cx = (int)(e.y >> 10), cy = (int)((e.y >> 5) & 31u), cz = (int)(e.y & 31u);
+            const float* p = L.vol + (size_t)e.x * VOL_STRIDE + (size_t)((cx * py + cy) * pz + cz);
+            const float f0 = p[0], f1 = p[1], f2 = p[pz + 1], f3 = p[pz];
+            const float f4 = p[pyz], f5 = p[pyz + 1], f6 = p[pyz + pz + 1], f7 = p[pyz + pz];
+            sm.cv[0][tid] = f0; sm.cv[1][tid] = f1; sm.cv[2][tid] = f2; sm.cv[3][tid] = f3;
+            sm.cv[4][tid] = f4; sm.cv[5][tid] = f5; sm.cv[6][tid] = f6; sm.cv[7][tid] = f7;
+            const int index = (f0 > 0.0f ? 1 : 0) | (f1 > 0.0f ? 2 : 0) | (f2 > 0.0f ? 4 : 0) | (f3 > 0.0f ? 8 : 0) |
+                              (f4 > 0.0f ? 16 : 0) | (f5 > 0.0f ? 32 : 0) | (f6 > 0.0f ? 64 : 0) | (f7 > 0.0f ? 128 : 0);
             if (index != 0 && index != 255) {
                 ++my_active;
-                tiling = mc_select_tiling(&sm.mc, index, v);
-                nt = tiling >= 0 ? sm.mc.tile_ntri[tiling] : 0;
+                const int tiling = mc_select_tiling_s(&sm.mc, index, cvp);
+                if (tiling >= 0) {
+                    nt = sm.mc.tile_ntri[tiling];
+                    sm.toff[tid] = sm.mc.tile_off[tiling];
+                }
+            }
+            if (nt != 0) {
+                batch_tris[m.bid] = 1u;                 // "this batch produced triangles" (core.py:135-141); all writers agree
+                sm.org[0][tid] = m.bx0; sm.org[1][tid] = m.by0; sm.org[2][tid] = m.bz0;
+                sm.org[3][tid] = m.oz + cz; sm.org[4][tid] = m.oy + cy; sm.org[5][tid] = m.ox + cx;   // Lewiner x,y,z (batch-local)
             }
         }
         // CTA-wide exclusive scan of nt
@@ -752,10 +1019,11 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
         unsigned int warp_off = 0, total = 0;
 #pragma unroll
         for (int wi = 0; wi < EXTRACT_THREADS / 32; ++wi) {
-            const unsigned int s = sm.warp_sums[wi];
-            if (wi < warp) warp_off += s;
-            total += s;
+            const unsigned int sv = sm.warp_sums[wi];
+            if (wi < warp) warp_off += sv;
+            total += sv;
         }
+        sm.pre[tid] = warp_off + incl - nt;
         if (tid == 0) {
             unsigned long long base = 0ull;
             if (total) {
@@ -769,50 +1037,50 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             sm.tri_base = base;
         }
         __syncthreads();
-        if (nt != 0) atomicAdd(&batch_tris[meta.x], nt);
-        const unsigned int local_first = warp_off + incl - nt;
+        // ------------------------------------------------------------ phase 2: one thread per triangle
         const unsigned long long gbase = sm.tri_base;
         const bool writable = tri_out != nullptr && gbase + total <= tri_capacity;      // else: count only / overflow
-        const bool staged = total <= EXTRACT_STAGE_TRIS;
-        if (nt != 0 && writable) {
-            // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
-            const double scx = __dsub_rn(g.xs[min(t.bx0 + 1, g.nx - 1)], g.xs[t.bx0]), ofx = g.xs[t.bx0];
-            const double scy = __dsub_rn(g.ys[min(t.by0 + 1, g.ny - 1)], g.ys[t.by0]), ofy = g.ys[t.by0];
-            const double scz = __dsub_rn(g.zs[min(t.bz0 + 1, g.nz - 1)], g.zs[t.bz0]), ofz = g.zs[t.bz0];
-            const int lx = t.oz + cz, ly = t.oy + cy, lz = t.ox + cx;             // Lewiner x,y,z (batch-local)
-            const unsigned char* ed = &sm.mc.tile_data[sm.mc.tile_off[tiling]];
-            float* dst = staged ? &sm.stage[local_first * 9u] : tri_out + (gbase + local_first) * 9ull;
-            // every edge vertex of the cube is computed once (a cube with nt triangles touches about
-            // nt + 2 edges, not 3 nt) and already world-mapped; triangles then only copy
-            float ev[13][3];
-            unsigned int have = 0;
-            for (unsigned int tri = 0; tri < nt; ++tri, dst += 9, ed += 3) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int ee = ed[k];
-                    if (!((have >> ee) & 1u)) {
-                        float q[3];
-                        if (ee < 12) mc_edge_vertex_fast(v, ee, lx, ly, lz, q);
-                        else mc_edge_vertex(v, ee, lx, ly, lz, q);
-                        // verts flipped to array-axis order (z,y,x)_L, then core.py:58-60
-                        ev[ee][0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
-                        ev[ee][1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
-                        ev[ee][2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
-                        have |= 1u << ee;
+        if (writable) {
+            for (unsigned int j0 = 0; j0 < total; j0 += EXTRACT_THREADS) {
+                const unsigned int j = j0 + tid;
+                if (j < total) {
+                    int lo = 0, hi = EXTRACT_THREADS - 1;                               // last c with pre[c] <= j
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (sm.pre[mid] <= j) lo = mid; else hi = mid - 1;
                     }
-                    float* o = dst + (2 - k) * 3;            // faces flipped (a,b,c) -> (c,b,a)
-                    o[0] = ev[ee][0]; o[1] = ev[ee][1]; o[2] = ev[ee][2];
+                    const int c = lo;
+                    const unsigned int tri = j - sm.pre[c];
+                    const unsigned char* ed = &sm.mc.tile_data[(unsigned int)sm.toff[c] + 3u * tri];
+                    const int bx0 = sm.org[0][c], by0 = sm.org[1][c], bz0 = sm.org[2][c];
+                    const int lx = sm.org[3][c], ly = sm.org[4][c], lz = sm.org[5][c];
+                    // world mapping of this batch (core.py:58-59): scale = X[1]-X[0], offset = X[0] of the slice
+                    const double ofx = g.xs[bx0], ofy = g.ys[by0], ofz = g.zs[bz0];
+                    const double scx = __dsub_rn(g.xs[min(bx0 + 1, g.nx - 1)], ofx);
+                    const double scy = __dsub_rn(g.ys[min(by0 + 1, g.ny - 1)], ofy);
+                    const double scz = __dsub_rn(g.zs[min(bz0 + 1, g.nz - 1)], ofz);
+                    float* o = &sm.stage[warp][lane * 9];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float q[3];
+                        mc_vertex_s(&sm.cv[0][c], (int)ed[k], lx, ly, lz, q);
+                        // verts flipped to array-axis order (z,y,x)_L, then core.py:58-60; faces flipped (a,b,c) -> (c,b,a)
+                        o[(2 - k) * 3 + 0] = (float)__dadd_rn(__dmul_rn((double)q[2], scx), ofx);
+                        o[(2 - k) * 3 + 1] = (float)__dadd_rn(__dmul_rn((double)q[1], scy), ofy);
+                        o[(2 - k) * 3 + 2] = (float)__dadd_rn(__dmul_rn((double)q[0], scz), ofz);
+                    }
                 }
+                __syncwarp();
+                const unsigned int wj0 = j0 + (unsigned int)warp * 32u;
+                if (wj0 < total) {
+                    const unsigned int nfl = min(32u, total - wj0) * 9u;
+                    float* gdst = tri_out + (gbase + wj0) * 9ull;
+                    for (unsigned int k = lane; k < nfl; k += 32) gdst[k] = sm.stage[warp][k];
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
-        if (writable && staged && total) {
-            // the CTA's triangles leave as one contiguous, fully coalesced run (local HBM or a peer over NVLink)
-            float* gdst = tri_out + gbase * 9ull;
-            const unsigned int nfl = total * 9u;
-            for (unsigned int k = tid; k < nfl; k += EXTRACT_THREADS) gdst[k] = sm.stage[k];
-        }
-        __syncthreads();
+        __syncthreads();                                      // the next iteration overwrites cv / org / pre
     }
     // statistics
 #pragma unroll

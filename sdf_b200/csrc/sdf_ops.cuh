@@ -37,13 +37,10 @@ struct ProgramImage {
 };
 
 namespace sdfm {
-// EXPERIMENT (off unless the translation unit defines SDF_EXP_NUMPY_MINMAX): numpy's
-// minimum / maximum return NaN when either operand is NaN, fmin / fmax return the other operand.
-#ifdef SDF_EXP_NUMPY_MINMAX
+// numpy's minimum / maximum (dn.py:14,29,44) return NaN when either operand is NaN; fmin / fmax would return
+// the other operand.  The accurate policies (float64, accurate float32) follow numpy; the FAST float32
+// policy keeps the single-instruction fminf / fmaxf -- everything it decides is re-evaluated in float64.
 #define SDF_MINMAX(T, F, a, b) (((a) != (a) || (b) != (b)) ? ((a) + (b)) : F((a), (b)))
-#else
-#define SDF_MINMAX(T, F, a, b) F((a), (b))
-#endif
 // ----------------------------------------------------------------------------------------------
 // Math policies.  MathP<double, *> and MathP<float, false> use IEEE-rounded division / square
 // root and the accurate libdevice transcendentals.  MathP<float, true> is the throughput path:

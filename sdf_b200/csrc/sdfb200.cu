@@ -2,15 +2,14 @@
 //
 // Hot path of fogleman/sdf's core.generate (sdf/core.py:84-150), B200-native:
 //
-//   skip_prepass_kernel   core._skip (core.py:28-43): float64, 1 + 8 samples per batch
-//   fused_tile_kernel     per batch tile: lattice samples generated in registers from the
-//                         float64 axes, whole SDF tree evaluated by the interpreter
-//                         (sdf_interp.cuh) into a shared-memory float32 tile
-//                         (core.py:51-52), float64 re-evaluation of sign-critical samples,
-//                         warp-shuffle min/max early-out (skimage's "level within data
-//                         range" check), Lewiner marching cubes on the staged tile with
-//                         the tables in shared memory and warp/CTA prefix-sum compaction
-//                         (core.py:16-18), world mapping (core.py:58-60)
+//   skip_prepass_kernel   core._skip (core.py:28-43): float64, 1 + 8 samples per batch (16 lanes per batch)
+//   tile_sign_kernel      (A, precision `exact`) lattice samples generated in registers from the float64
+//                         axes, whole SDF tree evaluated in fast float32, sign / uncertainty bit masks by
+//                         warp ballot, cube classification + compaction by the CTA that completes a tile
+//   tile_eval_kernel      (A, the other precisions) same with a shared-memory float32 value tile (core.py:51-52)
+//   refine_points_kernel  (B) float64 re-evaluation of every sample that can reach the output
+//   extract_kernel        (C) Lewiner marching cubes over the candidate cubes, tables in shared memory,
+//                         CTA prefix-sum compaction (core.py:16-18), world mapping (core.py:58-60)
 //   batch_stats_kernel    skipped / empty / nonempty (core.py:135-141)
 //   eval_stream_*         SDF3.__call__ on an explicit point block (d3.py:24-25): float3
 //                         points streamed HBM -> shared memory with cp.async.bulk (TMA
@@ -82,6 +81,14 @@ tile_eval_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, con
 }
 
 template <int TS>
+__global__ void __launch_bounds__(SIGN_THREADS, SIGN_BLOCKS_PER_SM)
+tile_sign_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const float tau,
+                 const unsigned int* active_list, const unsigned int work_begin, const unsigned int work_end,
+                 const TileLists L, Counters* ctr, unsigned char* scratch, unsigned int* tile_done) {
+    tile_sign_body<TS, SIGN_THREADS>(InterpEval{&img}, g, tau, active_list, work_begin, work_end, L, ctr, scratch, tile_done);
+}
+
+template <int TS>
 __global__ void __launch_bounds__(128)
 refine_points_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const TileLists L, Counters* ctr) {
     refine_points_body<TS>(InterpEval{&img}, g, L, ctr);
@@ -128,7 +135,10 @@ struct DeviceCtx {
     Counters* ctr_host = nullptr;       // pinned
     void* stage = nullptr; size_t stage_cap = 0;   // staging for host in/out buffers
     // tile pipeline work lists (TileLists)
-    float* vol = nullptr; size_t slot_cap = 0; uint2* tile_meta = nullptr; size_t meta_cap = 0;
+    float* vol = nullptr; size_t slot_cap = 0; TileMeta* tile_meta = nullptr; size_t meta_cap = 0;
+    unsigned char* scratch = nullptr; size_t scratch_cap = 0;       // tile_sign_kernel: per-tile mask blocks
+    unsigned int* tile_done = nullptr; size_t done_cap = 0;         //                   per-tile chunk counters (self-resetting)
+    bool done_dirty = false;                                        // a failed call may have left counters behind
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -526,6 +536,7 @@ static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& s
 // SDFB200_JIT_SHARE (-1 = flat, 0..2) / SDFB200_JIT_N force a grouping (experiments, A/B timing).
 static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_out) {
     const bool tile = kernel >= JK_TILE0 && kernel < JK_TILE0 + 4;
+    const bool sign = kernel == JK_TILE0 + SDFB200_PREC_EXACT;          // tile_sign_body: always thread-runs along one axis
     int cand[4][2];
     int n_cand = 0;
     const int env_share = env_int("SDFB200_JIT_SHARE", -2), env_n = env_int("SDFB200_JIT_N", 0);
@@ -535,10 +546,17 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
         else {
             double saved = 0;
             share = share_axis(p, nullptr, &saved);
-            if (saved < kColumnMinSavedCost) share = -1;
+            if (!sign && saved < kColumnMinSavedCost) share = -1;
         }
+        if (sign && share < 0) share = 2;
     }
     if (env_n >= 1 && env_n <= 16) { cand[0][0] = share; cand[0][1] = env_n; n_cand = 1; }
+    else if (sign) {
+        // 33 samples per line: 3 runs of 11, 6 of 6 (3 idle slots), 11 of 3
+        const int ns[3] = {11, 6, 3};
+        for (int k = 0; k < 3; ++k) { cand[k][0] = share; cand[k][1] = ns[k]; }
+        n_cand = 3;
+    }
     else if (share < 0) { cand[0][0] = -1; cand[0][1] = 4; n_cand = 1; }
     else {
         const int ns[3] = {11, 6, 4};
@@ -546,6 +564,8 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
         cand[3][0] = -1; cand[3][1] = 4;
         n_cand = 4;
     }
+    // a few spilled bytes cost less than a shorter run (SDFB200_JIT_SPILL_OK: bytes of spill stores tolerated)
+    const long spill_ok = env_int("SDFB200_JIT_SPILL_OK", 0);
     long best_spill = -1;
     std::string best_src;
     std::vector<char> cubin;
@@ -557,7 +577,7 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
             best_spill = spill; best_src = src; cubin_out->swap(cubin);
             p->plan_share[kernel] = cand[k][0]; p->plan_n[kernel] = cand[k][1];
         }
-        if (spill == 0) break;
+        if (spill <= spill_ok) break;
     }
     if (const char* dump = getenv("SDFB200_JIT_DUMP")) {       // debugging aid: keep source + cubin
         const std::string base = std::string(dump) + "/jit_k" + std::to_string(kernel);
@@ -599,20 +619,7 @@ static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true)
                         "specialisation is unavailable: %s", (prog)->code.size(), (prog)->jit_log.c_str());  \
     } while (0)
 
-// EXPERIMENT: SDFB200_EXP_CARVEOUT=1 asks for the maximum shared-memory
-// carve-out on every kernel of the step, so that the SMs are not reconfigured between the pre-pass (no
-// shared memory) and the 144 KB tile kernel.  Off unless the variable is set.
-static bool exp_carveout() {
-    const char* e = getenv("SDFB200_EXP_CARVEOUT");
-    return e && atoi(e) != 0;
-}
-
 static cudaError_t jit_launch(cudaKernel_t k, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args) {
-    if (exp_carveout()) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaKernelSetAttributeForDevice(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared, dev);
-    }
     return cudaLaunchKernel((const void*)k, grid, block, args, smem, stream);
 }
 
@@ -736,6 +743,7 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFree(c.axes); cudaFree(c.flags); cudaFree(c.active); cudaFree(c.batch_tris); cudaFree(c.ctr);
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
+        cudaFree(c.scratch); cudaFree(c.tile_done);
         for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
         for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
@@ -897,6 +905,10 @@ static cudaError_t launch_tile_eval(int grid, cudaStream_t stream, const Program
 
 static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kept per round
 
+// One generate call.  Everything is queued on `stream` without waiting for the device; the host
+// synchronises ONCE, at the end, when the output stays on the device (or is only counted), and only
+// where it needs a number to go on when the triangles travel to host memory (the count of active
+// batches to cut the work list into copy-overlapped rounds, the triangle count for the last copy).
 static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                          const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
                          int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
@@ -939,11 +951,14 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
     const float tau = (float)tau_;
     const long long lattice = (long long)nx * ny * nz;
     const bool big = lattice >= (1 << 21);
+    const bool sign_path = precision == SDFB200_PREC_EXACT;           // ballot masks, no value tile
     Counters& h = *c->ctr_host;
-    bool ran_pipeline = false;
+    const bool tail = stl_out != nullptr || (tri_out != nullptr && !out_dev);   // something still follows the counters
+    bool ran_pipeline = false, have_counters = false;
     unsigned long long copied = 0;      // triangles already on their way to tri_out (pipelined host output)
     if (total_b > 0) {
-        const int pb = (int)((total_b + 127) / 128);
+        const int pb = (int)((total_b * PREPASS_LANES + 127) / 128);
+        const int sb = (int)((total_b + 127) / 128);
         // ---- skip pre-pass
         if (cudaKernel_t jk = jit_get(prog, JK_SKIP, big)) {
             unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;
@@ -972,8 +987,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         }
         unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
         if (pipe > 1) {
-            // whole waves of the persistent tile kernel (one tile per SM) per round; a job of less than
-            // two waves has nothing to overlap
+            // whole waves of the tile kernel per round; a job of less than two waves has nothing to overlap
             const unsigned long long per = ((n_work + pipe - 1) / pipe + c->sms - 1) / c->sms * c->sms;
             if (n_work < 2ull * c->sms || n_work > max_round) pipe = 1;
             else round = (unsigned int)std::min<unsigned long long>(per, max_round);
@@ -982,6 +996,15 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             ran_pipeline = true;
             rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
             rc = grow(&c->tile_meta, &c->meta_cap, (size_t)round); if (rc) return rc;
+            if (sign_path) {
+                rc = grow(&c->scratch, &c->scratch_cap, (size_t)round * SIGN_STRIDE); if (rc) return rc;
+                const size_t had = c->done_cap;
+                rc = grow(&c->tile_done, &c->done_cap, (size_t)round); if (rc) return rc;
+                if (c->done_cap != had || c->done_dirty) {          // counters reset themselves in normal operation
+                    CUDA_TRY(cudaMemsetAsync(c->tile_done, 0, c->done_cap * sizeof(unsigned int), stream));
+                    c->done_dirty = false;
+                }
+            }
             const size_t est_tiles = sync_free ? std::max<size_t>(256, round / 4) : round;     // most batches are skipped / empty
             size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, est_tiles * 3072)));
             size_t want_pts = std::max<size_t>(c->pt_cap, precision == SDFB200_PREC_EXACT ? want_cubes * 3 : want_cubes);
@@ -999,6 +1022,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     const size_t nb = (size_t)g.nbx * g.nby * g.nbz;
                     CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->tri_cursor, 0, 4 * sizeof(unsigned long long), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->empty, 0, 2 * sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->max_cubes, 0, 2 * sizeof(unsigned int), stream));
                 }
                 for (unsigned long long wb = 0; wb < n_work; wb += round) {
@@ -1008,33 +1032,48 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
                     }
                     const unsigned int wbu = (unsigned int)wb;
-                    const int grid = (int)std::min<unsigned long long>(std::min<unsigned long long>(n_work, wb + round) - wb, (unsigned long long)c->sms);
+                    const unsigned long long tiles = std::min<unsigned long long>(n_work, wb + round) - wb;
                     // ---- (A) evaluate + classify
                     cudaError_t e;
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[4], stream));
-                    if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
-                        const bool f64 = precision == SDFB200_PREC_F64;
-                        const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
-                        JitEntry& je = prog->jit[JK_TILE0 + precision];
-                        if (!je.smem_set[device]) {
-                            CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
-                            je.smem_set[device] = true;
+                    if (sign_path) {
+                        const int grid = (int)std::min<unsigned long long>(tiles * SIGN_NCH, (unsigned long long)c->sms * SIGN_BLOCKS_PER_SM);
+                        if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
+                            const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
+                            unsigned char* scr = c->scratch; unsigned int* done = c->tile_done;
+                            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp,
+                                            (void*)&scr, (void*)&done};
+                            e = jit_launch(jk, dim3(grid), dim3(SIGN_THREADS), 0, stream, args);
+                        } else {
+                            REQUIRE_IMAGE(prog);
+                            tile_sign_kernel<kTS><<<grid, SIGN_THREADS, 0, stream>>>(prog->img, g, tau, c->active, wbu, we, L, c->ctr,
+                                                                                      c->scratch, c->tile_done);
+                            e = cudaGetLastError();
                         }
-                        const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
-                        void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
-                        e = jit_launch(jk, dim3(grid), dim3(f64 ? 512 : 1024), smem, stream, args);
-                    } else if (!prog->img_valid) {
-                        REQUIRE_IMAGE(prog);
-                        e = cudaSuccess;
-                    } else if (precision == SDFB200_PREC_F32)
-                        e = launch_tile_eval<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                    else if (precision == SDFB200_PREC_MIXED)
-                        e = launch_tile_eval<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                    else if (precision == SDFB200_PREC_EXACT)
-                        e = launch_tile_eval<SDFB200_PREC_EXACT>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                    else
-                        e = launch_tile_eval<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                    if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile_eval_kernel launch failed: %s", cudaGetErrorString(e));
+                    } else {
+                        const int grid = (int)std::min<unsigned long long>(tiles, (unsigned long long)c->sms);
+                        if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
+                            const bool f64 = precision == SDFB200_PREC_F64;
+                            const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
+                            JitEntry& je = prog->jit[JK_TILE0 + precision];
+                            if (!je.smem_set[device]) {
+                                CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
+                                je.smem_set[device] = true;
+                            }
+                            const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
+                            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
+                            e = jit_launch(jk, dim3(grid), dim3(f64 ? 512 : 1024), smem, stream, args);
+                        } else if (!prog->img_valid) {
+                            REQUIRE_IMAGE(prog);
+                            e = cudaSuccess;
+                        } else if (precision == SDFB200_PREC_F32)
+                            e = launch_tile_eval<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                        else if (precision == SDFB200_PREC_MIXED)
+                            e = launch_tile_eval<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                        else
+                            e = launch_tile_eval<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                    }
+                    if (e != cudaSuccess) { c->done_dirty = true; return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e)); }
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[5], stream));
                     // ---- (B) float64 refinement of the queued samples
                     if (precision == SDFB200_PREC_MIXED || precision == SDFB200_PREC_EXACT) {
@@ -1051,18 +1090,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     }
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[6], stream));
                     // ---- (C) extraction
-                    {
-                        static bool attr_set[64] = {false};
-                        if (!attr_set[device]) {
-                            CUDA_TRY(cudaFuncSetAttribute(extract_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExtractSmem)));
-                            attr_set[device] = true;
-                        }
-                    }
-                    if (exp_carveout()) {
-                        cudaFuncSetAttribute(extract_kernel<kTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                        cudaFuncSetAttribute(batch_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                    }
-                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, sizeof(ExtractSmem), stream>>>(
+                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, stream>>>(
                         g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor);
                     CUDA_TRY(cudaGetLastError());
                     if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[7], stream));
@@ -1072,6 +1100,12 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         ++n_rounds;
                     }
                 }
+                // ---- skipped / empty / nonempty, then the counters -- all queued behind the last round
+                CUDA_TRY(cudaEventRecord(c->ev[2], stream));
+                batch_stats_kernel<<<sb, 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                if (!tail) CUDA_TRY(cudaEventRecord(c->ev[3], stream));     // nothing follows on the device
                 // every round is queued; follow them and send each round's triangles as soon as it is done
                 for (int k = 0; k < n_rounds; ++k) {
                     CUDA_TRY(cudaEventSynchronize(c->pev[k]));
@@ -1084,8 +1118,8 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         copied = upto;
                     }
                 }
-                CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
+                have_counters = true;
                 if (const char* dd = getenv("SDFB200_DEBUG_DUMP")) {
                     auto dump = [&](const char* name, const void* dptr, size_t bytes) {
                         std::vector<char> hb(bytes);
@@ -1094,47 +1128,53 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hb.data(), 1, bytes, f); fclose(f); }
                     };
                     dump("vol.bin", c->vol, (size_t)h.n_slots * VOL_STRIDE * 4);
-                    dump("meta.bin", c->tile_meta, (size_t)h.n_slots * 8);
+                    dump("meta.bin", c->tile_meta, (size_t)h.n_slots * sizeof(TileMeta));
                     dump("cubes.bin", c->cubes, (size_t)std::min<unsigned>(h.n_cubes, L.cube_cap) * 8);
                     dump("pts.bin", c->pts, (size_t)std::min<unsigned>(h.n_pts, L.pt_cap) * 8);
                 }
                 if (getenv("SDFB200_DEBUG"))
-                    fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu nan=%u\n",
+                    fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu\n",
                             h.n_active, h.n_slots, h.n_cubes, h.n_pts, h.max_cubes, h.max_pts, L.cube_cap, L.pt_cap,
-                            h.tri_cursor, h.pts_f64, h.pad_[0]);
+                            h.tri_cursor, h.pts_f64);
                 if (h.max_cubes <= L.cube_cap && h.max_pts <= L.pt_cap) break;
                 want_cubes = std::max<size_t>(want_cubes, (size_t)h.max_cubes + (h.max_cubes >> 3));
                 want_pts = std::max<size_t>(want_pts, (size_t)h.max_pts + (h.max_pts >> 3));
                 if (attempt == 2) return fail(SDFB200_E_CUDA, "work lists kept overflowing (%u cubes, %u samples)", h.max_cubes, h.max_pts);
             }
         }
-        CUDA_TRY(cudaEventRecord(c->ev[2], stream));
-        batch_stats_kernel<<<pb, 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
-        CUDA_TRY(cudaGetLastError());
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[1], stream));
-        CUDA_TRY(cudaEventRecord(c->ev[2], stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!have_counters) {           // nothing ran behind the pre-pass (no batch at all, or every batch skipped)
+        CUDA_TRY(cudaEventRecord(c->ev[2], stream));
+        if (total_b > 0) {
+            batch_stats_kernel<<<(int)((total_b + 127) / 128), 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+        if (!tail) CUDA_TRY(cudaEventRecord(c->ev[3], stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
     *n_tri = (int64_t)h.tri_cursor;
     if (stats) {
         stats[0] = h.skipped; stats[1] = h.empty; stats[2] = h.nonempty;
         stats[3] = (int64_t)h.pts_f32; stats[4] = (int64_t)h.pts_f64; stats[5] = (int64_t)h.active_cubes;
     }
     const bool overflow = tri_out && !ext_cursor && h.tri_cursor > (unsigned long long)tri_capacity;
-    if (stl_out && !overflow && h.tri_cursor > 0) {
-        const long long nt = (long long)h.tri_cursor;
-        stl_records_kernel<<<(unsigned)((nt + STL_THREADS - 1) / STL_THREADS), STL_THREADS, 0, stream>>>(dtri, nt, drec);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(stl_out, drec, (size_t)nt * 50, cudaMemcpyDefault, stream));
-    } else if (tri_out && !out_dev && !overflow && h.tri_cursor > copied) {
-        CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(h.tri_cursor - copied) * 36,
-                                 cudaMemcpyDeviceToHost, stream));
+    if (tail) {            // the triangles (or their STL records) still have to reach the host
+        if (stl_out && !overflow && h.tri_cursor > 0) {
+            const long long nt = (long long)h.tri_cursor;
+            stl_records_kernel<<<(unsigned)((nt + STL_THREADS - 1) / STL_THREADS), STL_THREADS, 0, stream>>>(dtri, nt, drec);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(stl_out, drec, (size_t)nt * 50, cudaMemcpyDefault, stream));
+        } else if (!stl_out && !overflow && h.tri_cursor > copied) {
+            CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(h.tri_cursor - copied) * 36,
+                                     cudaMemcpyDeviceToHost, stream));
+        }
+        if (copied > 0) CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->ev[3], stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
     }
-    if (copied > 0) CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
-    CUDA_TRY(cudaEventRecord(c->ev[3], stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
     if (timings_ms) {
         float a = 0, b = 0, d = 0, ta = 0, tb = 0, tc = 0;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
@@ -1285,7 +1325,7 @@ extern "C" int sdfb200_skip_flags(sdfb200_prog* prog, const double* xs, int64_t 
     GridDesc g;
     rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, 0, -1, &g); if (rc) return rc;
     const long long total_b = (long long)g.nbx * g.nby * g.nbz;
-    const int pb = (int)((total_b + 127) / 128);
+    const int pb = (int)((total_b * PREPASS_LANES + 127) / 128);
     if (cudaKernel_t jk = jit_get(prog, JK_SKIP, total_b >= 4096)) {
         int sparse = 1;
         unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;

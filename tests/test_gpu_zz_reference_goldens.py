@@ -1,12 +1,10 @@
 """SDF3.__call__ on the GPU (float64) for 120 seeded random compositions against values produced by the
 REAL reference (tests/golden/random_trees.npz).  Needs a B200: -m gpu.  (Named to run last.)
 
-Known difference, found by this test on the B200 and reproduced on the CPU by giving the lowering
-simulator IEEE minNum/maxNum semantics: the device's fmin/fmax drop a NaN operand, numpy's
-minimum/maximum (dn.py:14,29,44) propagate it.  The only NaN source in these trees is the exact centre of
-an `ellipsoid` (0/0, d3.py:255-258); where a fold combines it with another shape the reference returns
-NaN and the device returns the other operand: trees 43 and 116 at the point (0,0,0).  Meshes are not
-affected (`NaN > 0` is false: the sample counts as inside, as its neighbours do).  DESIGN.md section 8.
+NaN semantics: numpy's minimum / maximum (dn.py:14,29,44) propagate a NaN operand (the only NaN source in these
+trees is the exact centre of an `ellipsoid`, 0/0, d3.py:255-258).  Round 1's device code used fmin/fmax, which
+drop it (trees 43 and 116 at the origin); the accurate math policies now follow numpy (sdf_ops.cuh SDF_MINMAX)
+and the NaN positions must agree exactly.
 """
 import numpy as np
 import pytest
@@ -15,7 +13,7 @@ import models
 
 pytestmark = pytest.mark.gpu
 
-KNOWN_NAN_DROPPED = {(43, 0), (116, 0)}          # (tree, point): reference NaN, device finite
+KNOWN_NAN_DROPPED = set()          # (tree, point) with a reference NaN and a finite device value: none allowed
 
 
 @pytest.mark.parametrize('front', ['interp', 'jit'])

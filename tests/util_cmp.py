@@ -45,6 +45,9 @@ def compare_soups(got, ref):
     else:
         rep['exact_triangles'] = -1
         rep['max_sorted_diff'] = float('inf')
+    if rep['exact_triangles'] == len(a):           # bit-identical multisets: nothing left to measure
+        rep['max_vertex_dist'] = 0.0
+        return rep
     # vertex multiset distance (robust to sort ties): nearest-neighbour both ways
     from scipy.spatial import cKDTree
     va, vb = a.reshape(-1, 3).astype(np.float64), b.reshape(-1, 3).astype(np.float64)
