@@ -16,10 +16,11 @@ covered (device-resident output), e2e = same through the public generate() with 
 roofline for the fused kernel (12 algorithmic bytes per evaluated sample), cpu_baseline = the
 CPU oracle port (numpy closures + C Lewiner MC) on the same lattice.
 
---impl reference times the reference's own CPU path: its numpy closure tree and ThreadPool
-(restated in oracle/sdf_ref.py, bit-identical to the real closures) with the marching-cubes call
-served by oracle/mc_lewiner.c, because scikit-image cannot be installed here ("reference eval +
-restated MC").
+--impl reference times the reference's own CPU path: the UNMODIFIED package installed in
+baseline/_ref (its numpy closure tree, _skip, _worker and ThreadPool, core.py:84-150) on all host
+threads, with the one call it cannot make here -- skimage.measure.marching_cubes, scikit-image is
+not installable -- served by oracle/mc_lewiner.c through a shim module ("reference eval + restated
+MC"; the eval+skip-only time, which is purely the reference's code, is reported next to it).
 """
 import argparse
 import json
@@ -181,50 +182,232 @@ def cpu_port(w, seconds_budget=20.0, workers=1):
                 mtris_per_s=st['triangles'] / dt / 1e6, seconds=dt)
 
 
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (pip-installed there with --no-deps).
+    Its one missing dependency, scikit-image, is not installable here, so ``skimage.measure.marching_cubes`` is
+    served by the C restatement (oracle/libmc_oracle.so) through a shim module -- every other line that runs is the
+    reference's own: the numpy closure tree, _skip, _worker, the ThreadPool (core.py:84-150)."""
+    import types
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'sdf')):
+        raise ImportError('baseline/_ref/sdf is missing (python -m pip install --no-index --no-build-isolation --no-deps '
+                          '--target baseline/_ref <copy of /root/reference>)')
+    from oracle import sdf_ref
+
+    def marching_cubes(volume, level=0.0, **kw):
+        soup = sdf_ref.marching_cubes_soup(volume, level)       # raises ValueError / RuntimeError like skimage
+        faces = np.arange(len(soup), dtype=np.int32).reshape(-1, 3)
+        return soup, faces, None, None
+
+    stub = types.ModuleType('skimage')
+    stub.measure = types.ModuleType('skimage.measure')
+    stub.measure.marching_cubes = marching_cubes
+    stub.__version__ = 'shim: oracle/mc_lewiner.c'
+    sys.modules['skimage'] = stub
+    sys.modules['skimage.measure'] = stub.measure
+    # the repo root holds an alias package named `sdf` (drop-in for scripts): the reference must win here
+    for k in [k for k in sys.modules if k == 'sdf' or k.startswith('sdf.')]:
+        del sys.modules[k]
+    sys.path.insert(0, ref_dir)
+    import sdf as ref
+    assert os.path.dirname(os.path.abspath(ref.__file__)).startswith(ref_dir), ref.__file__
+    return ref
+
+
 def run_reference(args):
+    """The reference's own multiprocessing CPU path on this box's host cores: its core.generate with
+    workers = all host threads, on the same workload as our arm."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     w = workload(args.gpus, args.grid, args.model)
     import models
-    import sdf_b200
-    from oracle import sdf_ref
-    f = models.CONFIGS[w['model']](sdf_b200)
     cores = os.cpu_count() or 1
-    nb = (w['n'] + BATCH - 1) // BATCH
-    total = nb ** 3
-    rng = np.random.default_rng(0)
-    m = min(total, args.ref_batches)
-    sample = np.sort(rng.choice(total, m, replace=False)) if m < total else None
-    times, tris = [], 0
-    for it in range(args.warmup + args.steps):
+    try:
+        ref = import_reference()
+        kind, how = 'reference', ('unmodified reference package (baseline/_ref): numpy closures, _skip, _worker, '
+                                  'ThreadPool(%d); skimage.measure.marching_cubes served by the C restatement '
+                                  '(scikit-image not installable): "reference eval + restated MC"' % cores)
+    except ImportError as e:
+        ref, kind, how = None, 'port', 'baseline/_ref unavailable (%s): oracle port, ThreadPool(%d)' % (e, cores)
+    times, tris, eval_only = [], 0, None
+    if ref is not None:
+        f = models.CONFIGS[w['model']](ref)
+        for it in range(args.warmup + args.steps):
+            t = time.time()
+            pts = ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores, verbose=False)
+            dt = time.time() - t
+            if it >= args.warmup:
+                times.append(dt)
+                tris = len(pts) // 3
+        # the same pass with marching cubes stubbed out: the part that is PURELY the reference's code
+        saved = sys.modules['skimage.measure'].marching_cubes
+
+        def no_mc(volume, level=0.0, **kw):
+            raise RuntimeError('marching cubes stubbed out')
+        ref.core.measure.marching_cubes = no_mc
         t = time.time()
-        pts, st = sdf_ref.generate(f, step=w['step'], bounds=w['bounds'], batch_subset=sample, workers=cores)
-        dt = time.time() - t
-        if it >= args.warmup:
-            times.append(dt)
-            tris = st['triangles']
-    covered = (m * BATCH ** 3) if sample is not None else w['n'] ** 3
+        ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores, verbose=False)
+        eval_only = time.time() - t
+        ref.core.measure.marching_cubes = saved
+    else:
+        import sdf_b200
+        from oracle import sdf_ref
+        f = models.CONFIGS[w['model']](sdf_b200)
+        for it in range(args.warmup + args.steps):
+            t = time.time()
+            pts, st = sdf_ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores)
+            dt = time.time() - t
+            if it >= args.warmup:
+                times.append(dt)
+                tris = st['triangles']
+    covered = w['n'] ** 3
     ms = 1e3 * sum(times) / len(times)
     val = covered / (ms / 1e3) / 1e6
     line = {'impl': 'reference', 'metric': 'Mpoints/s', 'value': val, 'unit': 'Mpoints/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(w), 'points': w['n'] ** 3, 'precision': 'f64 (the reference arithmetic)'},
-            'cpu_baseline': {'value': val, 'unit': 'Mpoints/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d of %d batches per step (seeded); reference numpy closures + ThreadPool(%d) '
-                                       'restated in oracle/, MC by the C restatement (skimage unavailable)' % (m, total, cores)},
-            'mtris_per_s': tris / (ms / 1e3) / 1e6,
+            'cpu_baseline': {'value': val, 'unit': 'Mpoints/s', 'cores': cores, 'kind': kind,
+                             'sample': 'the whole lattice per step (%d batches); %s' % (((w['n'] + BATCH - 1) // BATCH) ** 3, how),
+                             'eval_and_skip_only_mpoints_per_s': (covered / eval_only / 1e6) if eval_only else None},
+            'mtris_per_s': tris / (ms / 1e3) / 1e6, 'triangles': tris,
             'e2e': {'value': val, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
+class DeviceSeries:
+    """K timed passes of the hot path with device-resident output on this rank's Z-slab (barrier + synchronize on
+    both sides, CUDA events per step on the launching stream, L2 flushed between steps, max over ranks)."""
+
+    def __init__(self, f, w, args, world, rank, local, flush):
+        import torch
+        import torch.distributed as dist
+        from sdf_b200 import core, multi
+        self.torch, self.dist, self.world, self.rank, self.args, self.flush = torch, dist, world, rank, args, flush
+        self.f, self.w = f, w
+        _, _, (X, Y, Z) = core.make_lattice(f, w['step'], w['bounds'])
+        self.axes = (X, Y, Z)
+        self.n_points = len(X) * len(Y) * len(Z)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.plan = multi.plan_slabs(f, X, Y, Z, BATCH, world, device=local) if world > 1 else None
+        self.zb = self.plan[rank] if self.plan is not None else (0, -1)
+        self.h, _ = core.program_handle(f)
+        self.tau = core.mixed_tau(self.h.program, X, Y, Z)
+        self.local = local
+        need, _, _ = self.h.generate(X, Y, Z, BATCH, True, args.precision, self.tau, None, 0, zb=self.zb, device=local,
+                                     stream=self.stream)
+        self.cap = int(need * 1.02) + 1024
+        self.out = torch.empty((self.cap, 9), dtype=torch.float32, device='cuda')
+        self.root_gather = None
+        if world > 1 and args.gather == 'root':
+            needs = torch.tensor([need], dtype=torch.int64, device='cuda')
+            dist.all_reduce(needs)
+            self.root_gather = multi.RootGather(int(needs.item() * 1.02) + 4096, local)
+        self.gather_events = []
+
+    def step(self):
+        torch, args = self.torch, self.args
+        X, Y, Z = self.axes
+        if self.root_gather is not None:
+            return self.root_gather.run(self.h, X, Y, Z, BATCH, True, args.precision, self.tau, self.zb, stream=self.stream)
+        n_tri, stats, timings = self.h.generate(X, Y, Z, BATCH, True, args.precision, self.tau, self.out, self.cap,
+                                                zb=self.zb, device=self.local, stream=self.stream)
+        gathered = None
+        if self.world > 1:
+            from sdf_b200 import multi
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            gathered = multi.allgather_triangles(self.out[:n_tri])
+            g1.record()
+            self.gather_events.append((g0, g1))
+        return n_tri, stats, timings, gathered
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, steps, warmup, sampler=None):
+        torch, dist, world = self.torch, self.dist, self.world
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        if sampler is not None:
+            sampler.start()
+        t0 = time.time()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        fused_ms, prepass_ms, kern_ms, stats_acc, n_tri = [], [], [], None, 0
+        for k in range(steps):
+            self.flush.zero_()                                  # L2 flush between timed iterations (not timed)
+            ev[k][0].record()
+            n_tri, stats, timings, _ = self.step()
+            ev[k][1].record()
+            fused_ms.append(timings[1])
+            prepass_ms.append(timings[0])
+            kern_ms.append((timings[4], timings[5], timings[6]))
+            stats_acc = stats
+        self.barrier()
+        t1 = time.time()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        gather_ms = [a.elapsed_time(b) for a, b in self.gather_events[-steps:]] if self.gather_events else []
+        mine = sum(step_ms) / steps
+        t_max = torch.tensor([mine, sum(fused_ms) / steps, sum(k[0] for k in kern_ms) / steps], dtype=torch.float64, device='cuda')
+        t_min = t_max.clone()
+        agg = torch.tensor([float(n_tri), float(stats_acc[3]), float(stats_acc[4]), float(stats_acc[5]),
+                            float(stats_acc[0]), float(stats_acc[1]), float(stats_acc[2])], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        return dict(ms_per_step=float(t_max[0].item()), fused_ms=float(t_max[1].item()), tile_ms=float(t_max[2].item()),
+                    per_rank_min=dict(step_ms=float(t_min[0].item()), pipeline_ms=float(t_min[1].item()), tile_ms=float(t_min[2].item())),
+                    per_rank_max=dict(step_ms=float(t_max[0].item()), pipeline_ms=float(t_max[1].item()), tile_ms=float(t_max[2].item())),
+                    agg=[float(v) for v in agg.tolist()], prepass_ms=sum(prepass_ms) / steps,
+                    kern_ms=[sum(k[i] for k in kern_ms) / steps for i in range(3)],
+                    gather_ms=(sum(gather_ms) / len(gather_ms)) if gather_ms else None, t0=t0, t1=t1)
+
+
+COLD_SCRIPT = r"""
+import json, os, sys, time
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+import numpy as np
+import models, sdf_b200
+f0 = sdf_b200.sphere(1)
+f0(np.zeros((8, 3)))                                  # creates the CUDA context (not ours to speed up)
+f = models.CONFIGS[%(model)r](sdf_b200)
+out = {}
+for label in ('first', 'second'):
+    t = time.perf_counter()
+    pts = sdf_b200.generate(f, step=%(step)r, bounds=%(bounds)r, verbose=False, device=%(dev)d)
+    out[label + '_ms'] = (time.perf_counter() - t) * 1e3
+out['triangles'] = int(len(pts) // 3)
+print(json.dumps(out))
+"""
+
+
+def cold_start(w, local):
+    """First generate() of this tree in a FRESH process with an EMPTY kernel cache, default settings: the
+    specialised kernels compile in the background while the call runs on the interpreter kernels."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        env = dict(os.environ, SDFB200_JIT_CACHE=tmp)
+        env.pop('SDFB200_JIT', None)
+        code = COLD_SCRIPT % dict(root=ROOT, model=w['model'], step=w['step'], bounds=w['bounds'], dev=local)
+        try:
+            r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=240)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:           # never fail the bench line over the side measurement
+            return {'error': str(e)[:200]}
+
+
 def run_ours(args):
+    os.environ.setdefault('SDFB200_JIT', '2')       # timed arms: always the specialised kernels, compiled before the warm-up ends
     import torch
     import torch.distributed as dist
     import models
     import sdf_b200
-    from sdf_b200 import core, multi
+    from sdf_b200 import multi
 
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
@@ -232,86 +415,24 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device='cuda')   # 768 MB > 126 MB L2
     w = workload(world, args.grid, args.model)
     f = models.CONFIGS[w['model']](sdf_b200)
-    _, _, (X, Y, Z) = core.make_lattice(f, w['step'], w['bounds'])
-    n_points = len(X) * len(Y) * len(Z)
-    stream = torch.cuda.current_stream().cuda_stream
+    series = DeviceSeries(f, w, args, world, rank, local, flush)
+    X, Y, Z = series.axes
+    n_points, h, plan = series.n_points, series.h, series.plan
 
-    plan = multi.plan_slabs(f, X, Y, Z, BATCH, world, device=local) if world > 1 else None
-    zb = plan[rank] if plan is not None else (0, -1)
-    # device-resident output buffer, sized by a count-only pass
-    h, _ = core.program_handle(f)
-    tau = core.mixed_tau(h.program, X, Y, Z)
-    need, _, _ = h.generate(X, Y, Z, BATCH, True, args.precision, tau, None, 0, zb=zb, device=local, stream=stream)
-    cap = int(need * 1.02) + 1024
-    out = torch.empty((cap, 9), dtype=torch.float32, device='cuda')
-    flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device='cuda')   # 768 MB > 126 MB L2
-
-    root_gather = None
-    if world > 1 and args.gather == 'root':
-        needs = torch.tensor([need], dtype=torch.int64, device='cuda')
-        dist.all_reduce(needs)
-        root_gather = multi.RootGather(int(needs.item() * 1.02) + 4096, local)
-
-    def device_step():
-        if root_gather is not None:
-            n_loc, stats, timings, total = root_gather.run(h, X, Y, Z, BATCH, True, args.precision, tau, zb, stream=stream)
-            return n_loc, stats, timings, total
-        n_tri, stats, timings = h.generate(X, Y, Z, BATCH, True, args.precision, tau, out, cap, zb=zb,
-                                           device=local, stream=stream)
-        gathered = None
-        if world > 1:
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            gathered = multi.allgather_triangles(out[:n_tri])
-            g1.record()
-            gather_events.append((g0, g1))
-        return n_tri, stats, timings, gathered
-
-    gather_events = []
+    sampler = None
+    if rank == 0:
+        sampler = NvmlSampler(local)
+        if not sampler.ok:
+            sampler = ClockSampler(local)
+    res = series.run(args.steps, args.warmup, sampler)
+    ms_per_step = res['ms_per_step']
+    clocks = sampler.stop(res['t0'], res['t1']) if rank == 0 else None
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        device_step()
-    sampler = NvmlSampler(local)
-    if not sampler.ok:
-        sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t0 = time.time()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    fused_ms, prepass_ms, kern_ms, stats_acc, n_tri = [], [], [], None, 0
-    for k in range(args.steps):
-        flush.zero_()                                  # L2 flush between timed iterations (not timed)
-        ev[k][0].record()
-        n_tri, stats, timings, gathered = device_step()
-        ev[k][1].record()
-        fused_ms.append(timings[1])
-        prepass_ms.append(timings[0])
-        kern_ms.append((timings[4], timings[5], timings[6]))
-        stats_acc = stats
-    barrier()
-    t1 = time.time()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    gather_ms = [a.elapsed_time(b) for a, b in gather_events[-args.steps:]] if gather_events else []
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device='cuda')
-    agg = torch.tensor([float(n_tri), float(stats_acc[3]), float(stats_acc[4]), float(stats_acc[5]),
-                        float(stats_acc[0]), float(stats_acc[1]), float(stats_acc[2])], dtype=torch.float64, device='cuda')
-    fused_t = torch.tensor([sum(fused_ms) / len(fused_ms)], dtype=torch.float64, device='cuda')
-    tile_t = torch.tensor([sum(k[0] for k in kern_ms) / len(kern_ms)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        dist.all_reduce(fused_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tile_t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+        series.barrier()
 
     # end to end through the public API: host axes in, host triangle array out (rank-local slab)
     e2e_times, d2h = [], 0
@@ -334,10 +455,25 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # north_star's STRONG-scaling case next to the weak series the --gpus contract asks for: the knurling tree on a
+    # FIXED 1024^3 lattice split over the ranks (compare this object's ms_per_step across the N = 1, 2, 4, 8 lines)
+    strong = None
+    if not args.no_strong:
+        ws = workload(1, 1024, 'knurling')
+        fs = models.CONFIGS['knurling'](sdf_b200)
+        ss = DeviceSeries(fs, ws, args, world, rank, local, flush)
+        rs = ss.run(max(3, min(args.steps, 10)), 3)
+        strong = {'workload': workload_name(ws), 'scaling': 'strong', 'n_gpus': world, 'ms_per_step': rs['ms_per_step'],
+                  'value': ss.n_points / (rs['ms_per_step'] / 1e3) / 1e6, 'unit': 'Mpoints/s',
+                  'mtris_per_s': rs['agg'][0] / (rs['ms_per_step'] / 1e3) / 1e6, 'triangles': int(rs['agg'][0]),
+                  'per_rank_min_ms': rs['per_rank_min'], 'per_rank_max_ms': rs['per_rank_max'],
+                  'slabs': [list(p) for p in ss.plan] if ss.plan else None}
+        del ss
+
     if rank == 0:
-        tri_total, evaluated, refined, cubes = (float(agg[i].item()) for i in range(4))
+        tri_total, evaluated, refined, cubes = res['agg'][:4]
         peak, peak_src = peaks()
-        tile_s = float(tile_t.item()) / 1e3
+        tile_s = res['tile_ms'] / 1e3
         tile_kernel_name = ('tile_sign_body (jit_kernel, <= 592 x 256)' if args.precision == 'exact' else 'tile_eval_body (jit_kernel, 148 x 1024)')
         achieved = (evaluated / world) * 12.0 / tile_s / 1e9 if tile_s > 0 else 0.0     # per-GPU kernel
         # DRAM traffic of the dominant kernel: an ncu figure (profiles/r2_traffic.json, written from the committed
@@ -355,6 +491,7 @@ def run_ours(args):
                     traffic_note = 'ncu %s (%s): %.1f us per launch under ncu, %.1f us here' % (rec['capture'], rec['kernel'], t_ncu, t_now)
                 else:
                     traffic_note = 'capture %s is stale: %.1f us under ncu vs %.1f us measured here' % (rec['capture'], t_ncu, t_now)
+        cold = cold_start(w, local) if (world == 1 and not args.no_cold) else None
         line = {
             'metric': 'Mpoints/s', 'value': n_points / (ms_per_step / 1e3) / 1e6, 'unit': 'Mpoints/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
@@ -371,17 +508,20 @@ def run_ours(args):
                        'host_output_rounds': int(os.environ.get('SDFB200_PIPE', 8))},
             'mtris_per_s': tri_total / (ms_per_step / 1e3) / 1e6, 'triangles': int(tri_total),
             'mpoints_evaluated_per_s': evaluated / (ms_per_step / 1e3) / 1e6,
-            'batches': {'skipped': int(agg[4].item()), 'empty': int(agg[5].item()), 'nonempty': int(agg[6].item())},
+            'sdf_eval_mpoints_per_s': (evaluated / world) / tile_s / 1e6 if tile_s > 0 else None,
+            'batches': {'skipped': int(res['agg'][4]), 'empty': int(res['agg'][5]), 'nonempty': int(res['agg'][6])},
             'samples_evaluated': int(evaluated), 'samples_refined_f64': int(refined), 'active_cubes': int(cubes),
-            'kernel_ms': {'tile_pipeline_A+B+C': float(fused_t.item()), 'skip_prepass+setup': sum(prepass_ms) / len(prepass_ms),
-                          'tile_eval_kernel(A)': sum(k[0] for k in kern_ms) / len(kern_ms),
-                          'refine_points_kernel(B)': sum(k[1] for k in kern_ms) / len(kern_ms),
-                          'extract_kernel(C)': sum(k[2] for k in kern_ms) / len(kern_ms)},
+            'kernel_ms': {'tile_pipeline_A+B+C': res['fused_ms'], 'skip_prepass+setup': res['prepass_ms'],
+                          'tile_kernel(A)': res['kern_ms'][0], 'refine_points_kernel(B)': res['kern_ms'][1],
+                          'extract_kernel(C)': res['kern_ms'][2],
+                          'per_rank_min': res['per_rank_min'], 'per_rank_max': res['per_rank_max']},
             'gpu_launches': 5 * args.steps,
-            'allgather_ms_rank0': (sum(gather_ms) / len(gather_ms)) if gather_ms else None,
+            'allgather_ms_rank0': res['gather_ms'],
             'clocks': clocks,
             'e2e': {'value': n_points / e2e_s / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(8 * (len(X) + len(Y) + len(Z))),
-                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6},
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6,
+                    'd2h_gbs_if_copy_bound': d2h / e2e_s / 1e9,
+                    'cold_ms': (cold or {}).get('first_ms'), 'cold': cold},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'traffic_source': traffic_note,
                          'kernel': tile_kernel_name, 'peak_source': peak_src,
@@ -390,6 +530,7 @@ def run_ours(args):
                                  'sample (north_star float3 accounting) over its CUDA-event duration, measured live in this '
                                  'run; the kernel generates its samples in registers from the three lattice axes, so its real '
                                  'DRAM traffic is far below the algorithmic bytes and it is FP32/MUFU issue bound'},
+            'strong_1024': strong,
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_port(w, args.cpu_seconds)
@@ -409,7 +550,8 @@ def main():
     ap.add_argument('--precision', default='exact', choices=['f32', 'mixed', 'f64', 'exact'])
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--ref-batches', type=int, default=4096)
+    ap.add_argument('--no-strong', action='store_true', help='skip the knurling 1024^3 strong-scaling side series')
+    ap.add_argument('--no-cold', action='store_true', help='skip the cold-start side measurement')
     ap.add_argument('--gather', default='root', choices=['root', 'allgather'],
                     help='N>1: fused NVLink peer writes into rank 0 (default) or NCCL send/recv all-gather')
     args = ap.parse_args()

@@ -33,7 +33,7 @@ typedef unsigned long long uintptr_t;
 #define SDFB200_PREC_EXACT 3
 #endif
 
-#define MC_TABLE_QUAL __device__ __align__(16) const
+#define MC_TABLE_QUAL static const          // host-side data: packed into one device image by sdfb200.cu (get_ctx)
 #include "mc_tables.inc"
 
 // ---------------------------------------------------------------------------------------
@@ -43,6 +43,9 @@ struct GridDesc {
     const double* xs;
     const double* ys;
     const double* zs;
+    const float* xf;       // the same axes rounded to float32 (the fast classification pass reads these)
+    const float* yf;
+    const float* zf;
     int nx, ny, nz;        // lattice points per axis
     int bs;                // cubes per batch side (core.py BATCH_SIZE)
     int nbx, nby, nbz;     // batches per axis = ceil(n / bs)   (core.py:115-117)
@@ -60,7 +63,8 @@ struct Counters {
     unsigned int skipped, empty, nonempty;
     unsigned int n_slots, n_cubes, n_pts;       // per round: stored tiles, candidate cubes, queued samples
     unsigned int max_cubes, max_pts;            // high-water marks over rounds (capacity check)
-    unsigned int pad_[2];
+    unsigned int extract_done;                  // CTAs of the last extraction kernel that have finished (stats tail)
+    unsigned int pad_[1];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -132,6 +136,35 @@ __device__ __forceinline__ bool mc_test_interior(const double* v, int mode, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk: UBLKCP in SASS) helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // shared-memory copies of the decision tables ("edge table in shared memory")
 
 struct __align__(16) McTablesSmem {
@@ -146,25 +179,18 @@ struct __align__(16) McTablesSmem {
     unsigned char tile_data[MC_TILE_DATA_LEN];
 };
 
-// every table is a multiple of 4 bytes long and 16-byte aligned (MC_TABLE_QUAL): copied as 32-bit words
-__device__ __forceinline__ void copy_table(void* dst, const void* src, int bytes, int tid, int nthreads) {
-    unsigned int* d = reinterpret_cast<unsigned int*>(dst);
-    const unsigned int* s = reinterpret_cast<const unsigned int*>(src);
-    for (int i = tid; i < bytes / 4; i += nthreads) d[i] = s[i];
-}
+// The host packs the tables once per device into one McTablesSmem image in global memory (sdfb200.cu:
+// mc_tables_device); a CTA stages it with ONE cp.async.bulk (TMA bulk copy, mbarrier completion) that is in
+// flight while the CTA's first cubes are gathered.
+static_assert(sizeof(McTablesSmem) % 16 == 0, "bulk copy size");
 
-__device__ __forceinline__ void load_mc_tables(McTablesSmem* t, int tid, int nthreads) {
-    static_assert(MC_TILE_OFF_LEN % 4 == 0 && MC_SUB_TRUE_LEN % 4 == 0 && MC_TILE_DATA_LEN % 4 == 0 &&
-                  MC_SUB_INTERIOR_LEN % 4 == 0 && MC_TILE_NTRI_LEN % 4 == 0, "table lengths");
-    copy_table(t->sub_base, MC_SUB_BASE, sizeof(t->sub_base), tid, nthreads);
-    copy_table(t->tile_off, MC_TILE_OFF, sizeof(t->tile_off), tid, nthreads);
-    copy_table(t->sub_true, MC_SUB_TRUE, sizeof(t->sub_true), tid, nthreads);
-    copy_table(t->sub_false, MC_SUB_FALSE, sizeof(t->sub_false), tid, nthreads);
-    copy_table(t->sub_interior, MC_SUB_INTERIOR, sizeof(t->sub_interior), tid, nthreads);
-    copy_table(t->nface, MC_NFACE, sizeof(t->nface), tid, nthreads);
-    copy_table(t->faces, MC_FACES, sizeof(t->faces), tid, nthreads);
-    copy_table(t->tile_ntri, MC_TILE_NTRI, sizeof(t->tile_ntri), tid, nthreads);
-    copy_table(t->tile_data, MC_TILE_DATA, sizeof(t->tile_data), tid, nthreads);
+__device__ __forceinline__ void load_mc_tables_async(McTablesSmem* dst, const McTablesSmem* __restrict__ src, uint64_t* bar, int tid) {
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)sizeof(McTablesSmem));
+        tma_bulk_g2s(dst, src, (unsigned)sizeof(McTablesSmem), bar);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -607,7 +633,7 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 }
 
 // ---------------------------------------------------------------------------------------
-// (A') PREC_EXACT: evaluate + classify WITHOUT a value tile.
+// (A') PREC_EXACT: evaluate + classify WITHOUT a value tile, by autonomous warps.
 //
 // In `exact` mode every float32 value that could reach the output is re-evaluated in float64 by (B), so
 // the fast pass only has to answer two questions per sample: "is it > 0" and "is |d| < tau".  Both are
@@ -617,31 +643,134 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 // whose masks hold no mixed cube simply yields no candidates: skimage's "level within data range"
 // check, core.py:53-56), no tile store.
 //
-// Work item = (tile, chunk of SIGN_PW planes along the tile's W axis); CTAs are small (256 threads,
-// several per SM) and take items from one global cursor, so the sparse, uneven work balances at a
-// granularity of 1/7 tile.  A thread evaluates N consecutive samples along the share axis S (they
-// share their other two coordinates, i.e. registers: the axis-sharing of the generated evaluator),
-// its lane is the coordinate along the lane axis U.  Lanes 0..31 cover samples 0..31 of a U-line; the
-// 33rd sample of every line (the plane shared with the next tile) is evaluated by separate
-// thread-runs that write one byte per line.  Masks go to a per-tile scratch block in global memory
-// (10 KB, L2 resident); the CTA that completes a tile's last chunk (device-scope counter) classifies
-// the tile's 32^3 cubes with 64-bit word operations, compacts the candidate cubes and the samples
-// float64 must confirm, and allots the tile's volume slot.
+// There is no shared memory and no CTA barrier at all: every WARP is its own worker.  It takes batches
+// of SIGN_BATCH thread-runs of one tile from a global cursor (a tile = SIGN_NB batches, so the sparse,
+// uneven work balances at a granularity of 1/13 tile per warp).  In a thread-run a lane evaluates N
+// consecutive samples along the share axis S (they share their other two coordinates, i.e. registers:
+// the axis-sharing of the generated evaluator); the lane index is the coordinate along the lane axis U.
+// Lanes 0..31 cover samples 0..31 of a U-line; the 33rd sample of every line (the plane shared with the
+// next tile) is evaluated by separate thread-runs that write one byte per line.  Masks go to a per-tile
+// scratch block in global memory (10 KB, L2 resident).  The warp that completes a tile's last batch
+// (device-scope counter) classifies the tile by itself: it sweeps the 33 S-rows with its lanes along W,
+// classifies 32 cubes per lane and row with 64-bit word operations, and compacts the candidate cubes and
+// the samples float64 must confirm into the global lists (count pass, one pair of atomics, write pass).
 #define SIGN_TP 33
 #define SIGN_LINES (SIGN_TP * SIGN_TP)
-#define SIGN_PW 5                                               // W planes per work item
-#define SIGN_NCH ((SIGN_TP + SIGN_PW - 1) / SIGN_PW)            // work items per tile (7)
+#define SIGN_BATCH 8                                            // thread-runs per work item
 #define SIGN_STRIDE 9856                                        // bytes of scratch per tile: 1089 x {u32, u32} + 1089 u8, padded
 #define SIGN_THREADS 256
 #define SIGN_BLOCKS_PER_SM 4
 
-struct SignSmem {
-    float ax[3][SIGN_TP + 3];
-    unsigned int cand[32 * 32];                                 // per (cs, cw): bit cu <=> cube is a candidate
-    unsigned long long refm[SIGN_LINES];                        // per (is, iw) line: bit iu <=> sample queued for float64
-    unsigned int warp_sums[SIGN_THREADS / 32];
-    unsigned int item, last, slot, cube_gbase, pt_gbase;
+template <int N> struct SignShape {
+    static constexpr int RUNS_S = (SIGN_TP + N - 1) / N;        // thread-runs per S-line
+    static constexpr int R_MAIN = SIGN_TP * RUNS_S;             // run r = iw * RUNS_S + sr, lanes along U
+    static constexpr int R_EXTRA = (R_MAIN + 31) / 32;          // runs of the 33rd U-layer: lane = (iw, sr) pair
+    static constexpr int R_TILE = R_MAIN + R_EXTRA;
+    static constexpr int NB = (R_TILE + SIGN_BATCH - 1) / SIGN_BATCH;       // batches (work items) per tile
 };
+
+struct SignLine { unsigned long long p, u; };
+
+// masks of line `ln` as 33-bit words (bit 32 from the byte plane when the tile is 33 samples long along U)
+__device__ __forceinline__ SignLine sign_line(const uint2* __restrict__ masks, const unsigned char* __restrict__ hi,
+                                              int ln, bool has_hi) {
+    const uint2 mk = __ldcg(masks + ln);
+    const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ln) : 0u;
+    SignLine r;
+    r.p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
+    r.u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
+    return r;
+}
+
+// One warp classifies one tile from its mask block.  Lanes run along W: lane l owns column (cs, cw = l) of
+// cubes and line (is, iw = l); lane 31 also owns line (is, 32).  WRITE = false: count only.
+template <int TS, int AU, int AS, int AW, bool WRITE>
+__device__ __forceinline__ unsigned int sign_classify_pass(const uint2* __restrict__ masks, const unsigned char* __restrict__ hi,
+                                                           const int pu, const int ps, const int pw, const int py, const int pz,
+                                                           const int lane, const TileLists& L, const unsigned int slot,
+                                                           unsigned int cat, unsigned int pat) {
+    constexpr int TP = SIGN_TP;
+    const bool has_hi = (pu == TP);
+    const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
+    const bool col_on = lane < pw - 1;                  // this lane's cube column exists
+    const bool line_on = lane < pw;                     // this lane's line exists
+    const bool line32_on = lane == 31 && pw == TP;      // lane 31 also owns line iw = 32
+    unsigned int total = 0;
+    // row combination of the two lines a cube column touches in S-row `is`: all > 0 / any > 0 / any uncertain,
+    // each over sample pairs (bit j: samples j and j+1 along U)
+    unsigned long long ra = 0ull, ro = 0ull, ru = 0ull;       // row is
+    unsigned long long u_own = 0ull, u_32 = 0ull;             // uncertainty words of this lane's line(s) in row is
+    {
+        SignLine a = {0ull, 0ull}, b = {0ull, 0ull};
+        if (line_on) a = sign_line(masks, hi, lane, has_hi);
+        if (col_on || line32_on) b = sign_line(masks, hi, lane + 1, has_hi);
+        ra = (a.p & (a.p >> 1)) & (b.p & (b.p >> 1)); ro = (a.p | (a.p >> 1)) | (b.p | (b.p >> 1)); ru = (a.u | (a.u >> 1)) | (b.u | (b.u >> 1));
+        u_own = a.u; u_32 = b.u;
+    }
+    unsigned int w_prev = 0u;                                  // candidate word of column (is - 1, lane)
+    for (int is = 0; is < ps; ++is) {
+        // next row (is + 1)
+        unsigned long long na = 0ull, no = 0ull, nu = 0ull, nu_own = 0ull, nu_32 = 0ull;
+        if (is + 1 < ps) {
+            SignLine a = {0ull, 0ull}, b = {0ull, 0ull};
+            if (line_on) a = sign_line(masks, hi, (is + 1) * TP + lane, has_hi);
+            if (col_on || line32_on) b = sign_line(masks, hi, (is + 1) * TP + lane + 1, has_hi);
+            na = (a.p & (a.p >> 1)) & (b.p & (b.p >> 1)); no = (a.p | (a.p >> 1)) | (b.p | (b.p >> 1)); nu = (a.u | (a.u >> 1)) | (b.u | (b.u >> 1));
+            nu_own = a.u; nu_32 = b.u;
+        }
+        // cube column (cs = is, cw = lane): candidate when its corners are not all > 0 and not all <= 0, or one is uncertain
+        unsigned int W = 0u;
+        if (col_on && is + 1 < ps) W = (unsigned int)(((ro | no) & ~(ra & na)) | (ru | nu)) & cumask;
+        // line (is, lane) touches columns (is-1 | is, lane-1 | lane): queue every corner of a candidate cube
+        const unsigned int w_here = W | w_prev;
+        unsigned int w_left = __shfl_up_sync(0xffffffffu, w_here, 1);
+        if (lane == 0) w_left = 0u;
+        unsigned long long ref = 0ull, ref32 = 0ull;
+        if (line_on) { const unsigned int Wl = w_here | w_left; ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | u_own; }
+        if (line32_on) { ref32 = (unsigned long long)w_here | ((unsigned long long)w_here << 1) | u_32; }
+        const unsigned int cnt = (unsigned int)__popc(W) | (((unsigned int)__popcll(ref) + (unsigned int)__popcll(ref32)) << 16);
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const unsigned int row_total = __shfl_sync(0xffffffffu, incl, 31);
+        if (WRITE) {
+            const unsigned int excl = incl - cnt;
+            unsigned int c_at = cat + (total & 0xffffu) + (excl & 0xffffu);
+            unsigned int p_at = pat + (total >> 16) + (excl >> 16);
+            int cc[3], ii[3];
+            cc[AS] = is; cc[AW] = lane; ii[AS] = is; ii[AW] = lane;
+            unsigned int word = W;
+            while (word) {
+                cc[AU] = __ffs(word) - 1;
+                word &= word - 1u;
+                // cube id with fixed strides: cx << 10 | cy << 5 | cz
+                if (c_at < L.cube_cap) L.cubes[c_at] = make_uint2(slot, (unsigned int)((cc[0] << 10) | (cc[1] << 5) | cc[2]));
+                ++c_at;
+            }
+            unsigned long long lw = ref;
+            while (lw) {
+                ii[AU] = __ffsll((long long)lw) - 1;
+                lw &= lw - 1ull;
+                if (p_at < L.pt_cap) L.pts[p_at] = make_uint2(slot, (unsigned int)((ii[0] * py + ii[1]) * pz + ii[2]));
+                ++p_at;
+            }
+            ii[AW] = TP - 1;
+            lw = ref32;
+            while (lw) {
+                ii[AU] = __ffsll((long long)lw) - 1;
+                lw &= lw - 1ull;
+                if (p_at < L.pt_cap) L.pts[p_at] = make_uint2(slot, (unsigned int)((ii[0] * py + ii[1]) * pz + ii[2]));
+                ++p_at;
+            }
+        }
+        total += row_total;               // (low half: <= 32768 cubes, high half: <= 35937 samples per tile -- no carry)
+        ra = na; ro = no; ru = nu; u_own = nu_own; u_32 = nu_32; w_prev = W;
+    }
+    return total;
+}
 
 template <int TS, int THREADS, class EV>
 __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, const float tau,
@@ -649,26 +778,25 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
                                                const unsigned int work_begin, const unsigned int work_end_arg,
                                                const TileLists L, Counters* __restrict__ ctr,
                                                unsigned char* __restrict__ scratch, unsigned int* __restrict__ tile_done) {
-    static_assert(TS == 32 && THREADS == SIGN_THREADS, "one mask word per line; SignSmem is sized for SIGN_THREADS");
+    static_assert(TS == 32, "one mask word per line");
     constexpr int TP = SIGN_TP;
     constexpr int N = EV::kN;
-    constexpr int AS = EV::kShare < 0 ? 2 : EV::kShare;        // share axis (thread-run), lane axis, chunk axis
+    constexpr int AS = EV::kShare < 0 ? 2 : EV::kShare;        // share axis (thread-run), lane axis, batch axis
     constexpr int AU = AS == 2 ? 1 : 2;
     constexpr int AW = AS == 0 ? 1 : 0;
-    constexpr int NW = THREADS / 32;
-    __shared__ SignSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    typedef SignShape<N> SH;
+    const int lane = (int)(threadIdx.x & 31u);
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
     const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
-    const unsigned int n_items = (work_end > work_begin ? work_end - work_begin : 0u) * SIGN_NCH;
+    const unsigned int n_items = (work_end > work_begin ? work_end - work_begin : 0u) * (unsigned int)SH::NB;
 
-    if (tid == 0) sm.item = atomicAdd(&ctr->work_cursor, 1u);
-    __syncthreads();
     for (;;) {
-        const unsigned int q = sm.item;
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(&ctr->work_cursor, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= n_items) break;
-        const unsigned int tw = q / SIGN_NCH;
-        const int ch = (int)(q - tw * SIGN_NCH);
+        const unsigned int tw = q / (unsigned int)SH::NB;
+        const int bb = (int)(q - tw * (unsigned int)SH::NB);
         const unsigned int w = work_begin + tw;
         const unsigned int bid = active_list[w / subs3];
         const int sidx = (int)(w % subs3);
@@ -679,175 +807,76 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
         const bool thin = !valid || t.px < 2 || t.py < 2 || t.pz < 2;
         const int ext[3] = {thin ? 0 : t.px, thin ? 0 : t.py, thin ? 0 : t.pz};
         const int pu = ext[AU], ps = ext[AS], pw = ext[AW];
-        for (int i = tid; i < 3 * TP; i += THREADS) {
-            const int a = i / TP, j = i - a * TP;
-            const double* ap = a == 0 ? g.xs + (t.bx0 + t.ox) : (a == 1 ? g.ys + (t.by0 + t.oy) : g.zs + (t.bz0 + t.oz));
-            const int ea = a == 0 ? ext[0] : (a == 1 ? ext[1] : ext[2]);
-            if (j < ea) sm.ax[a][j] = (float)ap[j];
-        }
-        __syncthreads();
-        unsigned int next_item = 0;
-        if (tid == 0) next_item = atomicAdd(&ctr->work_cursor, 1u);       // consumed at the bottom of the loop
-
+        const float* const axf[3] = {g.xf + (t.bx0 + t.ox), g.yf + (t.by0 + t.oy), g.zf + (t.bz0 + t.oz)};
         uint2* const masks = reinterpret_cast<uint2*>(scratch + (size_t)tw * SIGN_STRIDE);      // per line {pos, unc}, bits 0..31
         unsigned char* const hi = reinterpret_cast<unsigned char*>(masks + SIGN_LINES);       // per line bit 32: pos | unc << 1
 
         // ---------------------------------------------------------------- evaluation
-        const int w0 = ch * SIGN_PW;
-        const int pwi = max(0, min(SIGN_PW, pw - w0));
-        const int runs_s = (ps + N - 1) / N;
-        const int r_main = pwi * runs_s;
-        const int r_extra = (pu == TP) ? (r_main + 31) / 32 : 0;
-        const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
-        for (int r = warp; r < r_main + r_extra; r += NW) {
-            const bool main_run = r < r_main;                         // warp uniform
-            int rr = main_run ? r : (r - r_main) * 32 + lane;
-            const bool on = rr < r_main;
-            if (!on) rr = 0;
-            const int wi = rr / runs_s, sr = rr - wi * runs_s;
-            const int iw = w0 + wi, is0 = sr * N;
-            const int iu = main_run ? min(lane, pu - 1) : TP - 1;
-            const float cu = sm.ax[AU][iu], cw = sm.ax[AW][iw];
-            float c[3][N], d[N];
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                c[AU][k] = cu; c[AW][k] = cw;
-                c[AS][k] = sm.ax[AS][min(is0 + k, ps - 1)];
-            }
-            ev.template run<float, N, true>(c[0], c[1], c[2], d);
-            if (main_run) {
+        if (!thin) {
+            const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
+            const float cu_main = __ldg(axf[AU] + min(lane, pu - 1));
+            const float cu_last = __ldg(axf[AU] + (pu - 1));
+            const int r_end = min((bb + 1) * SIGN_BATCH, SH::R_TILE);
+            for (int r = bb * SIGN_BATCH; r < r_end; ++r) {
+                const bool main_run = r < SH::R_MAIN;                       // warp uniform
+                const int rr = main_run ? r : (r - SH::R_MAIN) * 32 + lane;
+                const int iw = rr / SH::RUNS_S, is0 = (rr - iw * SH::RUNS_S) * N;
+                const bool on = rr < SH::R_MAIN && iw < pw && is0 < ps && (main_run || pu == TP);
+                if (!__any_sync(0xffffffffu, on)) continue;                // (ragged tile / nothing left in this run)
+                const int iwc = min(iw, pw - 1);
+                const float cw = __ldg(axf[AW] + iwc);
+                float c[3][N], d[N];
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
-                    const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
-                    if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
+                    c[AU][k] = main_run ? cu_main : cu_last; c[AW][k] = cw;
+                    c[AS][k] = __ldg(axf[AS] + min(is0 + k, ps - 1));
                 }
-            } else if (on) {
+                ev.template run<float, N, true>(c[0], c[1], c[2], d);
+                if (main_run) {
 #pragma unroll
-                for (int k = 0; k < N; ++k)
-                    if (is0 + k < ps)
-                        hi[(is0 + k) * TP + iw] = (unsigned char)((d[k] > 0.0f ? 1u : 0u) | (fabsf(d[k]) < tau ? 2u : 0u));
+                    for (int k = 0; k < N; ++k) {
+                        const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
+                        const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
+                        if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
+                    }
+                } else if (on) {
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+                        if (is0 + k < ps)
+                            hi[(is0 + k) * TP + iw] = (unsigned char)((d[k] > 0.0f ? 1u : 0u) | (fabsf(d[k]) < tau ? 2u : 0u));
+                }
             }
         }
         // ------------------------------------------------- who completes the tile classifies it
         __threadfence();
-        __syncthreads();
-        if (tid == 0) {
+        __syncwarp();
+        unsigned int last = 0;
+        if (lane == 0) {
             const unsigned int old = atomicAdd(&tile_done[tw], 1u);
-            const unsigned int last = (old == SIGN_NCH - 1) ? 1u : 0u;
+            last = (old == (unsigned int)SH::NB - 1u) ? 1u : 0u;
             if (last) tile_done[tw] = 0u;                               // ready for the next launch
-            sm.last = last;
         }
-        __syncthreads();
-        if (sm.last && !thin) {                                          // CTA uniform
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && !thin) {
             __threadfence();
-            // (1) one thread per (cs, cw) column of cubes: 32 cubes along U classified with word operations.
-            //     A cube is a candidate when its corners are not all > 0 and not all <= 0, or one is uncertain.
-            const bool has_hi = (pu == TP);
-            const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
-            for (int col = tid; col < TS * TS; col += THREADS) {
-                const int cs = col >> 5, cw = col & 31;
-                unsigned int W = 0u;
-                if (cs < ps - 1 && cw < pw - 1) {
-                    const int l00 = cs * TP + cw;
-                    const int ls[4] = {l00, l00 + 1, l00 + TP, l00 + TP + 1};
-                    unsigned long long allp = ~0ull, anyp = 0ull, anyu = 0ull;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ls[j]) : 0u;
-                        const uint2 mk = __ldcg(masks + ls[j]);
-                        const unsigned long long p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
-                        const unsigned long long u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
-                        allp &= p & (p >> 1); anyp |= p | (p >> 1); anyu |= u | (u >> 1);
-                    }
-                    W = (unsigned int)((anyp & ~allp) | anyu) & cumask;
-                }
-                sm.cand[col] = W;
-            }
-            __syncthreads();
-            // (2) one thread per line: queue every corner of a candidate cube (and every uncertain sample)
-            for (int ln = tid; ln < SIGN_LINES; ln += THREADS) {
-                const int is = ln / TP, iw = ln - is * TP;
-                unsigned long long ref = 0ull;
-                if (is < ps && iw < pw) {
-                    unsigned int Wl = 0u;
-                    if (is < TS && iw < TS) Wl |= sm.cand[(is << 5) | iw];
-                    if (is < TS && iw > 0) Wl |= sm.cand[(is << 5) | (iw - 1)];
-                    if (is > 0 && iw < TS) Wl |= sm.cand[((is - 1) << 5) | iw];
-                    if (is > 0 && iw > 0) Wl |= sm.cand[((is - 1) << 5) | (iw - 1)];
-                    const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ln) : 0u;
-                    ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | (unsigned long long)__ldcg(masks + ln).y |
-                          ((unsigned long long)((h8 >> 1) & 1u) << 32);
-                }
-                sm.refm[ln] = ref;
-            }
-            __syncthreads();
-            // (3) compaction: one prefix sum over the per-thread popcounts (cubes in the low, samples in the
-            //     high half word), one slot + one pair of list ranges per tile, every thread writes its entries
-            unsigned int cnt = 0;
-            for (int wi = tid; wi < TS * TS; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
-            for (int wi = tid; wi < SIGN_LINES; wi += THREADS) cnt += ((unsigned)__popcll(sm.refm[wi])) << 16;
-            unsigned int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += nb;
-            }
-            if (lane == 31) sm.warp_sums[warp] = incl;
-            __syncthreads();
-            unsigned int warp_off = 0, total = 0;
-#pragma unroll
-            for (int wi = 0; wi < NW; ++wi) {
-                const unsigned int sv = sm.warp_sums[wi];
-                if (wi < warp) warp_off += sv;
-                total += sv;
-            }
-            if (tid == 0) {
-                const unsigned int nc = total & 0xffffu, np = total >> 16;
-                unsigned int slot = 0;
+            const unsigned int tot = sign_classify_pass<TS, AU, AS, AW, false>(masks, hi, pu, ps, pw, t.py, t.pz, lane, L, 0u, 0u, 0u);
+            const unsigned int nc = tot & 0xffffu, np = tot >> 16;
+            unsigned int slot = 0, cat = 0, pat = 0;
+            if (lane == 0) {
                 if (nc | np) {
                     slot = atomicAdd(&ctr->n_slots, 1u);
                     if (slot < L.slot_cap) L.tile_meta[slot] = make_tile_meta(t, bid);
                 }
-                sm.slot = slot;
-                sm.cube_gbase = nc ? atomicAdd(&ctr->n_cubes, nc) : 0u;
-                sm.pt_gbase = np ? atomicAdd(&ctr->n_pts, np) : 0u;
+                cat = nc ? atomicAdd(&ctr->n_cubes, nc) : 0u;
+                pat = np ? atomicAdd(&ctr->n_pts, np) : 0u;
                 atomicAdd(&ctr->pts_f32, (unsigned long long)(t.px * t.py * t.pz));
             }
-            __syncthreads();
-            const unsigned int slot = sm.slot;
-            const unsigned int excl = warp_off + incl - cnt;
-            unsigned int cat = sm.cube_gbase + (excl & 0xffffu);
-            unsigned int pat = sm.pt_gbase + (excl >> 16);
-            if (slot < L.slot_cap) {
-                for (int wi = tid; wi < TS * TS; wi += THREADS) {
-                    unsigned int word = sm.cand[wi];
-                    int cc[3];
-                    cc[AS] = wi >> 5; cc[AW] = wi & 31;
-                    while (word) {
-                        cc[AU] = __ffs(word) - 1;
-                        word &= word - 1u;
-                        // cube id with fixed strides: cx << 10 | cy << 5 | cz
-                        if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)((cc[0] << 10) | (cc[1] << 5) | cc[2]));
-                        ++cat;
-                    }
-                }
-                for (int wi = tid; wi < SIGN_LINES; wi += THREADS) {
-                    unsigned long long word = sm.refm[wi];
-                    int ii[3];
-                    ii[AS] = wi / TP; ii[AW] = wi - ii[AS] * TP;
-                    while (word) {
-                        ii[AU] = __ffsll((long long)word) - 1;
-                        word &= word - 1ull;
-                        if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)((ii[0] * t.py + ii[1]) * t.pz + ii[2]));
-                        ++pat;
-                    }
-                }
-            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            cat = __shfl_sync(0xffffffffu, cat, 0);
+            pat = __shfl_sync(0xffffffffu, pat, 0);
+            if ((nc | np) && slot < L.slot_cap)
+                sign_classify_pass<TS, AU, AS, AW, true>(masks, hi, pu, ps, pw, t.py, t.pz, lane, L, slot, cat, pat);
         }
-        __syncthreads();                                      // everyone is done with this item's shared state
-        if (tid == 0) sm.item = next_item;
-        __syncthreads();
     }
 }
 
@@ -895,6 +924,8 @@ struct ExtractSmem {
     float stage[EXTRACT_THREADS / 32][32 * 9];
     unsigned int warp_sums[EXTRACT_THREADS / 32];
     unsigned long long tri_base;
+    uint64_t tables_bar;
+    unsigned int last_cta;
 };
 
 // corner k of the thread's cube: cvp[k * EXTRACT_THREADS]
@@ -964,19 +995,24 @@ __device__ __forceinline__ void mc_vertex_s(const float* cvp, int e, int x, int 
 // the root's buffer: ranges are reserved with one system-scope atomic per CTA iteration over NVLink and
 // the triangles leave this GPU as fully coalesced peer stores straight from the staging area -- the
 // transfer overlaps the extraction math, no collective follows.
+// `stats_flags` != nullptr (the last round of a call): the CTA that finishes last also counts the empty /
+// nonempty batches (core.py:135-141) -- "nonempty" = a non-skipped batch that produced at least one triangle.
 template <int TS>
 __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists L, Counters* __restrict__ ctr,
                                              unsigned int* __restrict__ batch_tris, float* __restrict__ tri_out,
                                              const unsigned long long tri_capacity,
-                                             unsigned long long* __restrict__ ext_cursor) {
-    __shared__ ExtractSmem sm;
+                                             unsigned long long* __restrict__ ext_cursor,
+                                             const McTablesSmem* __restrict__ tables,
+                                             const unsigned char* __restrict__ stats_flags) {
+    __shared__ __align__(128) ExtractSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    load_mc_tables(&sm.mc, tid, EXTRACT_THREADS);
+    load_mc_tables_async(&sm.mc, tables, &sm.tables_bar, tid);
     const unsigned int n = min(ctr->n_cubes, L.cube_cap);
     const unsigned int n_up = (n + EXTRACT_THREADS - 1) / EXTRACT_THREADS * EXTRACT_THREADS;
     unsigned int my_active = 0;
     const float* cvp = &sm.cv[0][tid];
-    __syncthreads();
+    bool tables_ready = false;
+    __syncthreads();                                          // the barrier object is initialised
     for (unsigned int i0 = blockIdx.x * EXTRACT_THREADS; i0 < n_up; i0 += gridDim.x * EXTRACT_THREADS) {
         // ------------------------------------------------------------ phase 1: one thread per cube
         const unsigned int i = i0 + tid;
@@ -993,6 +1029,7 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             sm.cv[4][tid] = f4; sm.cv[5][tid] = f5; sm.cv[6][tid] = f6; sm.cv[7][tid] = f7;
             const int index = (f0 > 0.0f ? 1 : 0) | (f1 > 0.0f ? 2 : 0) | (f2 > 0.0f ? 4 : 0) | (f3 > 0.0f ? 8 : 0) |
                               (f4 > 0.0f ? 16 : 0) | (f5 > 0.0f ? 32 : 0) | (f6 > 0.0f ? 64 : 0) | (f7 > 0.0f ? 128 : 0);
+            if (!tables_ready) { mbar_wait(&sm.tables_bar, 0u); tables_ready = true; }      // (the gathers above overlapped the copy)
             if (index != 0 && index != 255) {
                 ++my_active;
                 const int tiling = mc_select_tiling_s(&sm.mc, index, cvp);
@@ -1038,6 +1075,7 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
         }
         __syncthreads();
         // ------------------------------------------------------------ phase 2: one thread per triangle
+        if (!tables_ready) { mbar_wait(&sm.tables_bar, 0u); tables_ready = true; }
         const unsigned long long gbase = sm.tri_base;
         const bool writable = tri_out != nullptr && gbase + total <= tri_capacity;      // else: count only / overflow
         if (writable) {
@@ -1089,6 +1127,31 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
     if (blockIdx.x == 0 && tid == 0) {
         atomicMax(&ctr->max_cubes, ctr->n_cubes);
         atomicMax(&ctr->max_pts, ctr->n_pts);
+    }
+    if (!tables_ready) mbar_wait(&sm.tables_bar, 0u);          // never leave with a bulk copy in flight
+    if (stats_flags != nullptr) {
+        __threadfence();                                       // this CTA's batch_tris flags are visible device wide
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int done = atomicAdd(&ctr->extract_done, 1u);
+            sm.last_cta = (done == gridDim.x - 1u) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (sm.last_cta) {
+            __threadfence();
+            const int nzl = g.zb1 - g.zb0;
+            const int total_b = g.nbx * g.nby * nzl;
+            unsigned int ne = 0, nn = 0;
+            for (int t = tid; t < total_b; t += EXTRACT_THREADS) {
+                const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
+                const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + g.zb0 + bzl);
+                if (stats_flags[bid]) continue;
+                if (__ldcg(batch_tris + bid)) ++nn; else ++ne;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ne += __shfl_xor_sync(0xffffffffu, ne, o); nn += __shfl_xor_sync(0xffffffffu, nn, o); }
+            if (lane == 0) { if (ne) atomicAdd(&ctr->empty, ne); if (nn) atomicAdd(&ctr->nonempty, nn); }
+        }
     }
 }
 
@@ -1152,32 +1215,6 @@ __device__ __forceinline__ void stl_records_body(const float* __restrict__ tris,
 #define STREAM_PTS_PER_THREAD 4
 #define STREAM_TILE (STREAM_THREADS * STREAM_PTS_PER_THREAD)      // 1024 points = 12288 B
 #define STREAM_STAGES 3
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // Persistent CTAs; each owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a 3-stage ring of
 // 12 KB point tiles is kept in flight by one elected thread issuing cp.async.bulk.

@@ -31,6 +31,8 @@
 #include <memory>
 #include <new>
 #include <mutex>
+#include <future>
+#include <chrono>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -97,8 +99,15 @@ refine_points_kernel(const __grid_constant__ ProgramImage img, const GridDesc g,
 template <int TS>
 __global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_BLOCKS_PER_SM)
 extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
-               const unsigned long long tri_capacity, unsigned long long* ext_cursor) {
-    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor);
+               const unsigned long long tri_capacity, unsigned long long* ext_cursor, const McTablesSmem* tables,
+               const unsigned char* stats_flags) {
+    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags);
+}
+
+// float32 copies of the lattice axes for the fast classification pass (same rounding as a host-side cast)
+__global__ void axes_to_float_kernel(const double* a, float* f, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = (float)a[i];
 }
 
 __global__ void batch_stats_kernel(const GridDesc g, const unsigned char* flags, const unsigned int* batch_tris,
@@ -139,6 +148,11 @@ struct DeviceCtx {
     unsigned char* scratch = nullptr; size_t scratch_cap = 0;       // tile_sign_kernel: per-tile mask blocks
     unsigned int* tile_done = nullptr; size_t done_cap = 0;         //                   per-tile chunk counters (self-resetting)
     bool done_dirty = false;                                        // a failed call may have left counters behind
+    McTablesSmem* mc_tables = nullptr;                              // packed decision tables (one bulk copy per extraction CTA)
+    // the whole device-resident step as one CUDA graph, re-used while every launch parameter stays the same
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t step_exec = nullptr;
+    std::vector<unsigned char> step_key;
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -157,8 +171,19 @@ static int pipe_rounds() {
 
 enum JitKernel { JK_SKIP = 0, JK_TILE0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_REFINE = 8, JK_COUNT = 9 };
 
+// Outcome of compiling one kernel of one program: pure CPU work (NVRTC or the disk cache), produced on a
+// background thread, loaded into the CUDA context by the thread that owns the program lock.
+struct JitResult {
+    bool ok = false;
+    std::vector<char> cubin;
+    int share = -1, n = 0;          // the tile kernels' sample grouping
+    std::string log;                // NVRTC failure, if any
+};
+
 struct JitEntry {
-    bool tried = false;
+    bool started = false;           // a compile has been launched (fut is valid until harvested)
+    bool tried = false;             // harvested: kern is final (nullptr = unavailable)
+    std::future<JitResult> fut;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
     bool smem_set[64] = {false};
@@ -484,9 +509,9 @@ static void jit_cache_store(const std::string& path, const std::vector<char>& cu
     if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
 }
 
-// NVRTC: source -> cubin for sm_100a (or the cached cubin of the same source).  Needs no GPU.
+// NVRTC: source -> cubin for sm_100a (or the cached cubin of the same source).  Needs no GPU; thread safe.
 // *spill = bytes of register spill stores ptxas reported for the kernel.
-static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& src, std::vector<char>* cubin_out, long* spill) {
+static bool jit_compile_source(int kernel, const std::string& src, std::vector<char>* cubin_out, long* spill, std::string* err) {
     const std::string cpath = jit_cache_path(src);
     *spill = 0;
     if (jit_cache_load(cpath, cubin_out)) {
@@ -494,9 +519,9 @@ static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& s
         return true;
     }
     NvrtcApi& rt = nvrtc_api();
-    if (!rt.ok) { p->jit_log = "NVRTC (libnvrtc.so.12) not available"; return false; }
+    if (!rt.ok) { *err = "NVRTC (libnvrtc.so.12) not available"; return false; }
     void* prog = nullptr;
-    if (rt.CreateProgram(&prog, src.c_str(), "sdfb200_jit.cu", 0, nullptr, nullptr) != 0) { p->jit_log = "nvrtcCreateProgram failed"; return false; }
+    if (rt.CreateProgram(&prog, src.c_str(), "sdfb200_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return false; }
     const std::string inc = "-I" + csrc_dir();
     const char* opts[] = {kJitOptions[0], kJitOptions[1], kJitOptions[2], kJitOptions[3], kJitOptions[4], inc.c_str()};
     const int rc = rt.CompileProgram(prog, 6, opts);
@@ -505,8 +530,8 @@ static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& s
     std::string log(n, '\0');
     if (n) rt.GetProgramLog(prog, &log[0]);
     if (rc != 0) {
-        p->jit_log = "NVRTC compile failed (kernel " + std::to_string(kernel) + "): " + log;
-        if (getenv("SDFB200_JIT_VERBOSE")) fprintf(stderr, "%s\n", p->jit_log.c_str());
+        *err = "NVRTC compile failed (kernel " + std::to_string(kernel) + "): " + log;
+        if (getenv("SDFB200_JIT_VERBOSE")) fprintf(stderr, "%s\n", err->c_str());
         rt.DestroyProgram(&prog);
         return false;
     }
@@ -530,11 +555,14 @@ static bool jit_compile_source(sdfb200_prog* p, int kernel, const std::string& s
     return true;
 }
 
-// Source generation + compilation of one kernel.  The tile kernels (1..4) choose their sample grouping
-// here: groups of 11 samples along the axis share_axis() names (three groups per 33-sample line),
-// backing off to 6, 4 and finally the flat 4-sample mapping when ptxas had to spill registers.
+// Source generation + compilation of one kernel -- a pure function of the program (code, constants) and the
+// environment, safe to run on a background thread.  The tile kernels (1..4) choose their sample grouping here:
+// thread-runs of 11 samples along the axis share_axis() names (three per 33-sample line), backing off to 6
+// and 3 (4 and the flat 4-sample mapping for the value-tile kernels) when ptxas had to spill registers; the
+// candidates compile CONCURRENTLY (a cold first call waits for the slowest one, not for their sum).
 // SDFB200_JIT_SHARE (-1 = flat, 0..2) / SDFB200_JIT_N force a grouping (experiments, A/B timing).
-static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_out) {
+static JitResult jit_compile(const sdfb200_prog* p, int kernel) {
+    JitResult res;
     const bool tile = kernel >= JK_TILE0 && kernel < JK_TILE0 + 4;
     const bool sign = kernel == JK_TILE0 + SDFB200_PREC_EXACT;          // tile_sign_body: always thread-runs along one axis
     int cand[4][2];
@@ -566,38 +594,65 @@ static bool jit_compile(sdfb200_prog* p, int kernel, std::vector<char>* cubin_ou
     }
     // a few spilled bytes cost less than a shorter run (SDFB200_JIT_SPILL_OK: bytes of spill stores tolerated)
     const long spill_ok = env_int("SDFB200_JIT_SPILL_OK", 0);
-    long best_spill = -1;
-    std::string best_src;
-    std::vector<char> cubin;
-    for (int k = 0; k < n_cand; ++k) {
-        const std::string src = jit_source(p, kernel, cand[k][0], cand[k][1]);
-        long spill = 0;
-        if (!jit_compile_source(p, kernel, src, &cubin, &spill)) return false;
-        if (best_spill < 0 || spill < best_spill) {
-            best_spill = spill; best_src = src; cubin_out->swap(cubin);
-            p->plan_share[kernel] = cand[k][0]; p->plan_n[kernel] = cand[k][1];
+    struct One { std::string src; std::vector<char> cubin; long spill = 0; bool ok = false; std::string err; };
+    std::vector<One> ones((size_t)n_cand);
+    for (int k = 0; k < n_cand; ++k) ones[(size_t)k].src = jit_source(p, kernel, cand[k][0], cand[k][1]);
+    auto build = [&](int k) { One& o = ones[(size_t)k]; o.ok = jit_compile_source(kernel, o.src, &o.cubin, &o.spill, &o.err); };
+    // the preferred candidate first (normally it does not spill, or sits in the disk cache); only when it spills
+    // are the shorter runs built, side by side
+    build(0);
+    int best = 0;
+    if (ones[0].ok && ones[0].spill > spill_ok && n_cand > 1) {
+        std::vector<std::future<void>> jobs;
+        for (int k = 1; k < n_cand; ++k) jobs.push_back(std::async(std::launch::async, build, k));
+        for (auto& j : jobs) j.get();
+        for (int k = 1; k < n_cand; ++k) {
+            if (!ones[(size_t)k].ok) continue;
+            if (ones[(size_t)best].spill > spill_ok && ones[(size_t)k].spill < ones[(size_t)best].spill) best = k;
         }
-        if (spill <= spill_ok) break;
     }
+    One& o = ones[(size_t)best];
+    if (!o.ok) { res.log = o.err; return res; }
+    res.ok = true;
+    res.cubin.swap(o.cubin);
+    res.share = cand[best][0]; res.n = cand[best][1];
     if (const char* dump = getenv("SDFB200_JIT_DUMP")) {       // debugging aid: keep source + cubin
         const std::string base = std::string(dump) + "/jit_k" + std::to_string(kernel);
-        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fputs(best_src.c_str(), f); fclose(f); }
-        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(cubin_out->data(), 1, cubin_out->size(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cu").c_str(), "w")) { fputs(o.src.c_str(), f); fclose(f); }
+        if (FILE* f = fopen((base + ".cubin").c_str(), "wb")) { fwrite(res.cubin.data(), 1, res.cubin.size(), f); fclose(f); }
     }
-    return true;
+    return res;
 }
 
-// Compile (once) and return the specialised kernel, or nullptr when unavailable.
+// Launch the compile of `kernel` on a background thread (once).  Called for every kernel a generate call will
+// need before the first of them is used, so that a cold call compiles them side by side.
+static void jit_start(sdfb200_prog* p, int kernel) {
+    JitEntry& e = p->jit[kernel];
+    if (e.started || e.tried) return;
+    e.started = true;
+    const sdfb200_prog* cp = p;
+    e.fut = std::async(std::launch::async, [cp, kernel] { return jit_compile(cp, kernel); });
+}
+
+// The specialised kernel, or nullptr when the interpreter kernels should run.
+//   mode 0: never specialise.  mode 2: always, waiting for the compiler.  mode 1 (default): for jobs big enough
+//   to repay it the compile runs in the BACKGROUND -- until the cubin is ready the call in hand (a one-shot
+//   `f.save()` script's only call) runs on the interpreter kernels instead of waiting seconds for NVRTC; later
+//   calls pick the specialised kernel up.  Programs too large for the interpreter image always wait.
 static cudaKernel_t jit_get(sdfb200_prog* p, int kernel, bool big_enough = true) {
     const int mode = jit_mode();
     if (p->img_valid && (mode == 0 || (mode == 1 && !big_enough))) return nullptr;      // (no image: only this path exists)
     JitEntry& e = p->jit[kernel];
     if (e.tried) return e.kern;
+    jit_start(p, kernel);
+    const bool may_defer = mode == 1 && p->img_valid;
+    if (may_defer && e.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return nullptr;
+    JitResult r = e.fut.get();
     e.tried = true;
-    std::vector<char> cubin;
-    if (!jit_compile(p, kernel, &cubin)) return nullptr;
+    p->plan_share[kernel] = r.share; p->plan_n[kernel] = r.n;
+    if (!r.ok) { p->jit_log = r.log; return nullptr; }
     cudaLibrary_t lib = nullptr;
-    if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+    if (cudaLibraryLoadData(&lib, r.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
         p->jit_log = std::string("cudaLibraryLoadData failed: ") + cudaGetErrorString(cudaGetLastError());
         return nullptr;
     }
@@ -641,6 +696,22 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
     for (int i = 0; i < kMaxPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.pev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking));
+    {   // the marching-cubes decision tables, packed exactly as the extraction kernel keeps them in shared memory
+        std::unique_ptr<McTablesSmem> t(new McTablesSmem());
+        memset(t.get(), 0, sizeof(McTablesSmem));
+        memcpy(t->sub_base, MC_SUB_BASE, sizeof(t->sub_base));
+        memcpy(t->tile_off, MC_TILE_OFF, sizeof(t->tile_off));
+        memcpy(t->sub_true, MC_SUB_TRUE, sizeof(t->sub_true));
+        memcpy(t->sub_false, MC_SUB_FALSE, sizeof(t->sub_false));
+        memcpy(t->sub_interior, MC_SUB_INTERIOR, sizeof(t->sub_interior));
+        memcpy(t->nface, MC_NFACE, sizeof(t->nface));
+        memcpy(t->faces, MC_FACES, sizeof(t->faces));
+        memcpy(t->tile_ntri, MC_TILE_NTRI, sizeof(t->tile_ntri));
+        memcpy(t->tile_data, MC_TILE_DATA, sizeof(t->tile_data));
+        CUDA_TRY(cudaMalloc(&c.mc_tables, sizeof(McTablesSmem)));
+        CUDA_TRY(cudaMemcpy(c.mc_tables, t.get(), sizeof(McTablesSmem), cudaMemcpyHostToDevice));
+    }
     prog->ctxs.reserve(16);
     prog->ctxs.push_back(c);
     *out = &prog->ctxs.back();
@@ -738,12 +809,15 @@ extern "C" int sdfb200_program_create(const uint32_t* code, int n_code, const do
 
 extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
     if (!prog) return;
+    for (auto& e : prog->jit) if (e.started && !e.tried && e.fut.valid()) e.fut.wait();      // background compiles read the program
     for (auto& c : prog->ctxs) {
         cudaSetDevice(c.device);
         cudaFree(c.axes); cudaFree(c.flags); cudaFree(c.active); cudaFree(c.batch_tris); cudaFree(c.ctr);
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
-        cudaFree(c.scratch); cudaFree(c.tile_done);
+        cudaFree(c.scratch); cudaFree(c.tile_done); cudaFree(c.mc_tables);
+        if (c.step_exec) cudaGraphExecDestroy(c.step_exec);
+        if (c.cap_stream) cudaStreamDestroy(c.cap_stream);
         for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
         for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
@@ -834,9 +908,11 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
     if (need > c->axes_cap) {
         if (c->axes) cudaFree(c->axes);
         c->axes = nullptr; c->axes_cap = 0;
-        CUDA_TRY(cudaMalloc(&c->axes, need * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&c->axes, need * (sizeof(double) + sizeof(float))));      // float64 axes, then their float32 copies
         c->axes_cap = need;
+        c->axes_host.clear();
     }
+    float* const axes_f = reinterpret_cast<float*>(c->axes + c->axes_cap);
     // upload the axes unless they are the ones already resident (host copy kept for the comparison)
     const bool host_axes = !is_device_ptr(xs) && !is_device_ptr(ys) && !is_device_ptr(zs);
     bool same = host_axes && c->axes_host.size() == need;
@@ -856,8 +932,11 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
             CUDA_TRY(cudaMemcpyAsync(c->axes + nx, ys, ny * sizeof(double), kind, stream));
             CUDA_TRY(cudaMemcpyAsync(c->axes + nx + ny, zs, nz * sizeof(double), kind, stream));
         }
+        axes_to_float_kernel<<<(unsigned)((need + 255) / 256), 256, 0, stream>>>(c->axes, axes_f, (int)need);
+        CUDA_TRY(cudaGetLastError());
     }
     g->xs = c->axes; g->ys = c->axes + nx; g->zs = c->axes + nx + ny;
+    g->xf = axes_f; g->yf = axes_f + nx; g->zf = axes_f + nx + ny;
     g->nx = (int)nx; g->ny = (int)ny; g->nz = (int)nz;
     g->bs = batch_size;
     g->nbx = (int)((nx + batch_size - 1) / batch_size);
@@ -897,18 +976,37 @@ static cudaError_t launch_tile_eval(int grid, cudaStream_t stream, const Program
                                     const unsigned int* active, unsigned int wb, unsigned int we, const TileLists& L,
                                     Counters* ctr) {
     const size_t smem = sizeof(TileSmem<kTS, PREC == SDFB200_PREC_F64>);
-    cudaError_t e = cudaFuncSetAttribute(tile_eval_kernel<kTS, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     tile_eval_kernel<kTS, PREC><<<grid, INTERP_TILE_THREADS, smem, stream>>>(img, g, tau, active, wb, we, L, ctr);
     return cudaGetLastError();
 }
 
+// dynamic shared-memory opt-in of the value-tile kernels (once per device; never inside a stream capture)
+static cudaError_t prepare_tile_eval(int precision) {
+    cudaError_t e = cudaSuccess;
+    if (precision == SDFB200_PREC_F32)
+        e = cudaFuncSetAttribute(tile_eval_kernel<kTS, SDFB200_PREC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<kTS, false>));
+    else if (precision == SDFB200_PREC_MIXED)
+        e = cudaFuncSetAttribute(tile_eval_kernel<kTS, SDFB200_PREC_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<kTS, false>));
+    else if (precision == SDFB200_PREC_F64)
+        e = cudaFuncSetAttribute(tile_eval_kernel<kTS, SDFB200_PREC_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<kTS, true>));
+    return e;
+}
+
 static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kept per round
+
+static bool graph_enabled() {
+    const char* e = getenv("SDFB200_GRAPH");
+    return e ? atoi(e) != 0 : true;
+}
 
 // One generate call.  Everything is queued on `stream` without waiting for the device; the host
 // synchronises ONCE, at the end, when the output stays on the device (or is only counted), and only
 // where it needs a number to go on when the triangles travel to host memory (the count of active
 // batches to cut the work list into copy-overlapped rounds, the triangle count for the last copy).
+// In the first case the whole step -- counters reset, pre-pass, A, B, C (+ batch statistics), counter
+// read-back -- is ONE CUDA graph, captured the first time and re-launched for as long as every launch
+// parameter stays the same (SDFB200_GRAPH=0 disables it): four API calls per step instead of twenty,
+// and no launch gaps between the kernels.
 static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                          const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
                          int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
@@ -952,24 +1050,18 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
     const long long lattice = (long long)nx * ny * nz;
     const bool big = lattice >= (1 << 21);
     const bool sign_path = precision == SDFB200_PREC_EXACT;           // ballot masks, no value tile
+    const bool refine = precision == SDFB200_PREC_MIXED || precision == SDFB200_PREC_EXACT;
     Counters& h = *c->ctr_host;
     const bool tail = stl_out != nullptr || (tri_out != nullptr && !out_dev);   // something still follows the counters
     bool ran_pipeline = false, have_counters = false;
     unsigned long long copied = 0;      // triangles already on their way to tri_out (pipelined host output)
     if (total_b > 0) {
         const int pb = (int)((total_b * PREPASS_LANES + 127) / 128);
-        const int sb = (int)((total_b + 127) / 128);
-        // ---- skip pre-pass
-        if (cudaKernel_t jk = jit_get(prog, JK_SKIP, big)) {
-            unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;
-            void* args[] = {(void*)&g, (void*)&sparse, (void*)&fl, (void*)&act, (void*)&bt, (void*)&ctrp};
-            CUDA_TRY(jit_launch(jk, dim3(pb), dim3(128), 0, stream, args));
-        } else {
-            REQUIRE_IMAGE(prog);
-            skip_prepass_kernel<<<pb, 128, 0, stream>>>(prog->img, g, sparse, c->flags, c->active, c->batch_tris, c->ctr);
-            CUDA_TRY(cudaGetLastError());
+        if (jit_mode() >= 2 || (jit_mode() == 1 && big) || !prog->img_valid) {      // the kernels of this call compile side by side
+            jit_start(prog, JK_SKIP);
+            jit_start(prog, JK_TILE0 + precision);
+            if (refine) jit_start(prog, JK_REFINE);
         }
-        CUDA_TRY(cudaEventRecord(c->ev[1], stream));
         // Work-list sizing.  When one tile volume per batch of the range fits the budget, the kernels
         // read the number of active batches from the pre-pass's counter themselves and the host never
         // synchronises in the middle; otherwise the host reads it and runs rounds of `max_round` tiles.
@@ -979,8 +1071,98 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         // while round k+1 is computed (the copy is the longer leg: 36 B per triangle at PCIe speed).
         int pipe = (tri_out && !out_dev && !stl_out && !ext_cursor && big) ? pipe_rounds() : 1;
         const bool sync_free = upper <= max_round && pipe == 1;
+
+        // every kernel of the step resolved up front (nothing may compile or load inside a stream capture)
+        cudaKernel_t k_skip = jit_get(prog, JK_SKIP, big);
+        cudaKernel_t k_tile = jit_get(prog, JK_TILE0 + precision, big);
+        cudaKernel_t k_refine = refine ? jit_get(prog, JK_REFINE, big) : nullptr;
+        if ((!k_skip || !k_tile || (refine && !k_refine)) && !prog->img_valid) REQUIRE_IMAGE(prog);
+        if (k_tile && !sign_path) {
+            const bool f64 = precision == SDFB200_PREC_F64;
+            const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
+            JitEntry& je = prog->jit[JK_TILE0 + precision];
+            if (!je.smem_set[device]) {
+                CUDA_TRY(cudaKernelSetAttributeForDevice(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
+                je.smem_set[device] = true;
+            }
+        }
+
+        if (!k_tile && !sign_path) CUDA_TRY(prepare_tile_eval(precision));
+
+        auto rec = [&](cudaEvent_t ev, cudaStream_t s, bool captured) -> cudaError_t {
+            return captured ? cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal) : cudaEventRecord(ev, s);
+        };
+        auto launch_prepass = [&](cudaStream_t s) -> int {
+            if (k_skip) {
+                unsigned char* fl = c->flags; unsigned int* act = c->active; unsigned int* bt = c->batch_tris; Counters* ctrp = c->ctr;
+                int sp = sparse;
+                void* args[] = {(void*)&g, (void*)&sp, (void*)&fl, (void*)&act, (void*)&bt, (void*)&ctrp};
+                CUDA_TRY(jit_launch(k_skip, dim3(pb), dim3(128), 0, s, args));
+            } else {
+                skip_prepass_kernel<<<pb, 128, 0, s>>>(prog->img, g, sparse, c->flags, c->active, c->batch_tris, c->ctr);
+                CUDA_TRY(cudaGetLastError());
+            }
+            return 0;
+        };
+        // one round = (A) evaluate + classify, (B) float64 refinement, (C) extraction [+ batch statistics when last]
+        auto launch_round = [&](cudaStream_t s, bool captured, const TileLists& L, unsigned int wbu, unsigned int we,
+                                unsigned long long tiles, bool first, bool last) -> int {
+            cudaError_t e = cudaSuccess;
+            if (first) CUDA_TRY(rec(c->ev[4], s, captured));
+            if (sign_path) {
+                // autonomous warps pull 1/13-tile batches from a cursor: fill the machine, surplus warps leave at once
+                const int grid = (int)std::min<unsigned long long>(tiles * 16ull, (unsigned long long)c->sms * SIGN_BLOCKS_PER_SM);
+                if (k_tile) {
+                    const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
+                    unsigned char* scr = c->scratch; unsigned int* done = c->tile_done;
+                    void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp,
+                                    (void*)&scr, (void*)&done};
+                    e = jit_launch(k_tile, dim3(grid), dim3(SIGN_THREADS), 0, s, args);
+                } else {
+                    tile_sign_kernel<kTS><<<grid, SIGN_THREADS, 0, s>>>(prog->img, g, tau, c->active, wbu, we, L, c->ctr,
+                                                                         c->scratch, c->tile_done);
+                    e = cudaGetLastError();
+                }
+            } else {
+                const int grid = (int)std::min<unsigned long long>(tiles, (unsigned long long)c->sms);
+                if (k_tile) {
+                    const bool f64 = precision == SDFB200_PREC_F64;
+                    const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
+                    const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
+                    void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
+                    e = jit_launch(k_tile, dim3(grid), dim3(f64 ? 512 : 1024), smem, s, args);
+                } else if (precision == SDFB200_PREC_F32)
+                    e = launch_tile_eval<SDFB200_PREC_F32>(grid, s, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                else if (precision == SDFB200_PREC_MIXED)
+                    e = launch_tile_eval<SDFB200_PREC_MIXED>(grid, s, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+                else
+                    e = launch_tile_eval<SDFB200_PREC_F64>(grid, s, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
+            }
+            if (e != cudaSuccess) { c->done_dirty = true; return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e)); }
+            if (first) CUDA_TRY(rec(c->ev[5], s, captured));
+            if (refine) {
+                const int rgrid = c->sms * 8;
+                if (k_refine) {
+                    Counters* ctrp = c->ctr;
+                    void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
+                    CUDA_TRY(jit_launch(k_refine, dim3(rgrid), dim3(128), 0, s, args));
+                } else {
+                    refine_points_kernel<kTS><<<rgrid, 128, 0, s>>>(prog->img, g, L, c->ctr);
+                    CUDA_TRY(cudaGetLastError());
+                }
+            }
+            if (first) CUDA_TRY(rec(c->ev[6], s, captured));
+            extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, s>>>(
+                g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor, c->mc_tables, last ? c->flags : nullptr);
+            CUDA_TRY(cudaGetLastError());
+            if (first) CUDA_TRY(rec(c->ev[7], s, captured));
+            return 0;
+        };
+
         unsigned long long n_work = upper;
         if (!sync_free) {
+            rc = launch_prepass(stream); if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(c->ev[1], stream));
             CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
@@ -1013,6 +1195,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 rc = grow(&c->cubes, &c->cube_cap, want_cubes); if (rc) return rc;
                 rc = grow(&c->pts, &c->pt_cap, want_pts); if (rc) return rc;
                 TileLists L;
+                memset(&L, 0, sizeof(L));
                 L.vol = c->vol; L.tile_meta = c->tile_meta; L.cubes = c->cubes; L.pts = c->pts;
                 L.slot_cap = round; L.cube_cap = (unsigned int)std::min<size_t>(c->cube_cap, 0xffffffffu);
                 L.pt_cap = (unsigned int)std::min<size_t>(c->pt_cap, 0xffffffffu);
@@ -1022,100 +1205,88 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     const size_t nb = (size_t)g.nbx * g.nby * g.nbz;
                     CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->tri_cursor, 0, 4 * sizeof(unsigned long long), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->empty, 0, 2 * sizeof(unsigned int), stream));
-                    CUDA_TRY(cudaMemsetAsync(&c->ctr->max_cubes, 0, 2 * sizeof(unsigned int), stream));
+                    CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 6 * sizeof(unsigned int), stream));      // n_slots .. extract_done
                 }
-                for (unsigned long long wb = 0; wb < n_work; wb += round) {
-                    const unsigned int we = sync_free ? 0xffffffffu : (unsigned int)std::min<unsigned long long>(n_work, wb + round);
-                    if (wb > 0 || attempt > 0) {        // (the first round starts from the zeroed counters)
-                        CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
-                        CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
-                    }
-                    const unsigned int wbu = (unsigned int)wb;
-                    const unsigned long long tiles = std::min<unsigned long long>(n_work, wb + round) - wb;
-                    // ---- (A) evaluate + classify
-                    cudaError_t e;
-                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[4], stream));
-                    if (sign_path) {
-                        const int grid = (int)std::min<unsigned long long>(tiles * SIGN_NCH, (unsigned long long)c->sms * SIGN_BLOCKS_PER_SM);
-                        if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
-                            const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
-                            unsigned char* scr = c->scratch; unsigned int* done = c->tile_done;
-                            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp,
-                                            (void*)&scr, (void*)&done};
-                            e = jit_launch(jk, dim3(grid), dim3(SIGN_THREADS), 0, stream, args);
-                        } else {
-                            REQUIRE_IMAGE(prog);
-                            tile_sign_kernel<kTS><<<grid, SIGN_THREADS, 0, stream>>>(prog->img, g, tau, c->active, wbu, we, L, c->ctr,
-                                                                                      c->scratch, c->tile_done);
-                            e = cudaGetLastError();
-                        }
-                    } else {
-                        const int grid = (int)std::min<unsigned long long>(tiles, (unsigned long long)c->sms);
-                        if (cudaKernel_t jk = jit_get(prog, JK_TILE0 + precision, big)) {
-                            const bool f64 = precision == SDFB200_PREC_F64;
-                            const size_t smem = f64 ? sizeof(TileSmem<kTS, true>) : sizeof(TileSmem<kTS, false>);
-                            JitEntry& je = prog->jit[JK_TILE0 + precision];
-                            if (!je.smem_set[device]) {
-                                CUDA_TRY(cudaKernelSetAttributeForDevice(jk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device));
-                                je.smem_set[device] = true;
+                if (sync_free && attempt == 0) {
+                    // ---- the whole step in one go: pre-pass, A, B, C + statistics, counters to the host
+                    auto enqueue = [&](cudaStream_t s, bool captured) -> int {
+                        int r = launch_prepass(s); if (r) return r;
+                        CUDA_TRY(rec(c->ev[1], s, captured));
+                        r = launch_round(s, captured, L, 0u, 0xffffffffu, n_work, true, true); if (r) return r;
+                        CUDA_TRY(rec(c->ev[2], s, captured));
+                        CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+                        if (!tail) CUDA_TRY(rec(c->ev[3], s, captured));
+                        return 0;
+                    };
+                    bool launched = false;
+                    if (graph_enabled()) {
+                        // key: every value the launches above depend on
+                        struct { GridDesc g; TileLists L; float tau; int sparse, precision, tail; float* dtri; unsigned long long cap, n_work;
+                                 unsigned long long* ext; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr, *done; } key;
+                        memset(&key, 0, sizeof(key));
+                        key.g = g; key.L = L; key.tau = tau; key.sparse = sparse; key.precision = precision; key.tail = tail ? 1 : 0;
+                        key.dtri = dtri; key.cap = cap; key.n_work = n_work; key.ext = ext_cursor;
+                        key.k0 = (void*)k_skip; key.k1 = (void*)k_tile; key.k2 = (void*)k_refine;
+                        key.flags = c->flags; key.active = c->active; key.bt = c->batch_tris; key.ctr = c->ctr; key.ctrh = c->ctr_host;
+                        key.scr = c->scratch; key.done = c->tile_done;
+                        const bool hit = c->step_exec && c->step_key.size() == sizeof(key) && memcmp(c->step_key.data(), &key, sizeof(key)) == 0;
+                        if (!hit) {
+                            if (c->step_exec) { cudaGraphExecDestroy(c->step_exec); c->step_exec = nullptr; }
+                            c->step_key.clear();
+                            cudaGraph_t graph = nullptr;
+                            if (cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                                const int r = enqueue(c->cap_stream, true);
+                                const cudaError_t ee = cudaStreamEndCapture(c->cap_stream, &graph);
+                                if (r == 0 && ee == cudaSuccess && graph &&
+                                    cudaGraphInstantiate(&c->step_exec, graph, 0) == cudaSuccess) {
+                                    c->step_key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+                                } else {
+                                    c->step_exec = nullptr;
+                                }
+                                if (graph) cudaGraphDestroy(graph);
                             }
-                            const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
-                            void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp};
-                            e = jit_launch(jk, dim3(grid), dim3(f64 ? 512 : 1024), smem, stream, args);
-                        } else if (!prog->img_valid) {
-                            REQUIRE_IMAGE(prog);
-                            e = cudaSuccess;
-                        } else if (precision == SDFB200_PREC_F32)
-                            e = launch_tile_eval<SDFB200_PREC_F32>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                        else if (precision == SDFB200_PREC_MIXED)
-                            e = launch_tile_eval<SDFB200_PREC_MIXED>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                        else
-                            e = launch_tile_eval<SDFB200_PREC_F64>(grid, stream, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
-                    }
-                    if (e != cudaSuccess) { c->done_dirty = true; return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e)); }
-                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[5], stream));
-                    // ---- (B) float64 refinement of the queued samples
-                    if (precision == SDFB200_PREC_MIXED || precision == SDFB200_PREC_EXACT) {
-                        const int rgrid = c->sms * 8;
-                        if (cudaKernel_t jk = jit_get(prog, JK_REFINE, big)) {
-                            Counters* ctrp = c->ctr;
-                            void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
-                            CUDA_TRY(jit_launch(jk, dim3(rgrid), dim3(128), 0, stream, args));
-                        } else {
-                            REQUIRE_IMAGE(prog);
-                            refine_points_kernel<kTS><<<rgrid, 128, 0, stream>>>(prog->img, g, L, c->ctr);
-                            CUDA_TRY(cudaGetLastError());
+                            cudaGetLastError();          // a failed capture falls back to plain launches below
+                        }
+                        if (c->step_exec) {
+                            CUDA_TRY(cudaGraphLaunch(c->step_exec, stream));
+                            launched = true;
                         }
                     }
-                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[6], stream));
-                    // ---- (C) extraction
-                    extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, stream>>>(
-                        g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor);
-                    CUDA_TRY(cudaGetLastError());
-                    if (wb == 0) CUDA_TRY(cudaEventRecord(c->ev[7], stream));
-                    if (pipe > 1 && n_rounds < kMaxPipe) {
-                        CUDA_TRY(cudaMemcpyAsync(c->ctr_host + 1 + n_rounds, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                        CUDA_TRY(cudaEventRecord(c->pev[n_rounds], stream));
-                        ++n_rounds;
+                    if (!launched) { rc = enqueue(stream, false); if (rc) return rc; }
+                } else {
+                    if (sync_free) {            // (a retry: the pre-pass results are still there)
+                        CUDA_TRY(cudaEventRecord(c->ev[1], stream));
                     }
-                }
-                // ---- skipped / empty / nonempty, then the counters -- all queued behind the last round
-                CUDA_TRY(cudaEventRecord(c->ev[2], stream));
-                batch_stats_kernel<<<sb, 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
-                CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                if (!tail) CUDA_TRY(cudaEventRecord(c->ev[3], stream));     // nothing follows on the device
-                // every round is queued; follow them and send each round's triangles as soon as it is done
-                for (int k = 0; k < n_rounds; ++k) {
-                    CUDA_TRY(cudaEventSynchronize(c->pev[k]));
-                    const Counters& hk = c->ctr_host[1 + k];
-                    if (hk.max_cubes > L.cube_cap || hk.max_pts > L.pt_cap) break;       // lists overflowed: retried below
-                    const unsigned long long upto = std::min<unsigned long long>(hk.tri_cursor, cap);
-                    if (upto > copied) {
-                        CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(upto - copied) * 36,
-                                                 cudaMemcpyDeviceToHost, c->copy_stream));
-                        copied = upto;
+                    for (unsigned long long wb = 0; wb < n_work; wb += round) {
+                        const unsigned int we = sync_free ? 0xffffffffu : (unsigned int)std::min<unsigned long long>(n_work, wb + round);
+                        if (wb > 0) {        // (the first round starts from the zeroed counters)
+                            CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
+                            CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
+                        }
+                        const unsigned long long tiles = std::min<unsigned long long>(n_work, wb + round) - wb;
+                        rc = launch_round(stream, false, L, (unsigned int)wb, we, tiles, wb == 0, wb + round >= n_work); if (rc) return rc;
+                        if (pipe > 1 && n_rounds < kMaxPipe) {
+                            CUDA_TRY(cudaMemcpyAsync(c->ctr_host + 1 + n_rounds, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                            CUDA_TRY(cudaEventRecord(c->pev[n_rounds], stream));
+                            ++n_rounds;
+                        }
+                    }
+                    CUDA_TRY(cudaEventRecord(c->ev[2], stream));
+                    CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                    if (!tail) CUDA_TRY(cudaEventRecord(c->ev[3], stream));     // nothing follows on the device
+                    // every round is queued; follow them and send each round's triangles as soon as it is done
+                    for (int k = 0; k < n_rounds; ++k) {
+                        CUDA_TRY(cudaEventSynchronize(c->pev[k]));
+                        const Counters& hk = c->ctr_host[1 + k];
+                        if (hk.max_cubes > L.cube_cap || hk.max_pts > L.pt_cap) break;       // lists overflowed: retried below
+                        const unsigned long long upto = std::min<unsigned long long>(hk.tri_cursor, cap);
+                        if (upto > copied) {
+                            CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(upto - copied) * 36,
+                                                     cudaMemcpyDeviceToHost, c->copy_stream));
+                            copied = upto;
+                        }
                     }
                 }
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1133,9 +1304,9 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     dump("pts.bin", c->pts, (size_t)std::min<unsigned>(h.n_pts, L.pt_cap) * 8);
                 }
                 if (getenv("SDFB200_DEBUG"))
-                    fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu\n",
+                    fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu graph=%d\n",
                             h.n_active, h.n_slots, h.n_cubes, h.n_pts, h.max_cubes, h.max_pts, L.cube_cap, L.pt_cap,
-                            h.tri_cursor, h.pts_f64);
+                            h.tri_cursor, h.pts_f64, c->step_exec ? 1 : 0);
                 if (h.max_cubes <= L.cube_cap && h.max_pts <= L.pt_cap) break;
                 want_cubes = std::max<size_t>(want_cubes, (size_t)h.max_cubes + (h.max_cubes >> 3));
                 want_pts = std::max<size_t>(want_pts, (size_t)h.max_pts + (h.max_pts >> 3));
@@ -1145,7 +1316,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
     } else {
         CUDA_TRY(cudaEventRecord(c->ev[1], stream));
     }
-    if (!have_counters) {           // nothing ran behind the pre-pass (no batch at all, or every batch skipped)
+    if (!have_counters) {           // nothing ran behind the pre-pass (no batch at all, or no active batch)
         CUDA_TRY(cudaEventRecord(c->ev[2], stream));
         if (total_b > 0) {
             batch_stats_kernel<<<(int)((total_b + 127) / 128), 128, 0, stream>>>(g, c->flags, c->batch_tris, c->ctr);
@@ -1297,9 +1468,9 @@ extern "C" int sdfb200_generate_shared(sdfb200_prog* prog, const double* xs, int
 extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {
     if (!prog || kernel < 0 || kernel >= JK_COUNT) return fail(SDFB200_E_INVALID, "jit_probe: bad argument");
     std::lock_guard<std::mutex> guard(prog->lock);
-    std::vector<char> cubin;
-    if (!jit_compile(prog, kernel, &cubin)) return fail(SDFB200_E_INVALID, "%s", prog->jit_log.c_str());
-    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    const JitResult r = jit_compile(prog, kernel);
+    if (!r.ok) return fail(SDFB200_E_INVALID, "%s", r.log.c_str());
+    if (cubin_bytes) *cubin_bytes = (int64_t)r.cubin.size();
     return 0;
 }
 
@@ -1307,11 +1478,12 @@ extern "C" int sdfb200_jit_plan(sdfb200_prog* prog, int precision, int* share_ax
                                 double* invariant_fraction) {
     if (!prog || precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "jit_plan: bad argument");
     std::lock_guard<std::mutex> guard(prog->lock);
-    std::vector<char> cubin;
     const int kernel = JK_TILE0 + precision;
-    if (!jit_compile(prog, kernel, &cubin)) return fail(SDFB200_E_INVALID, "%s", prog->jit_log.c_str());
-    if (share_axis_out) *share_axis_out = prog->plan_share[kernel];
-    if (samples_per_thread) *samples_per_thread = prog->plan_n[kernel];
+    const JitResult r = jit_compile(prog, kernel);
+    if (!r.ok) return fail(SDFB200_E_INVALID, "%s", r.log.c_str());
+    prog->plan_share[kernel] = r.share; prog->plan_n[kernel] = r.n;
+    if (share_axis_out) *share_axis_out = r.share;
+    if (samples_per_thread) *samples_per_thread = r.n;
     if (invariant_fraction) share_axis(prog, invariant_fraction);
     return 0;
 }
