@@ -290,29 +290,59 @@ class DeviceSeries:
         self.axes = (X, Y, Z)
         self.n_points = len(X) * len(Y) * len(Z)
         self.stream = torch.cuda.current_stream().cuda_stream
-        self.plan = multi.plan_slabs(f, X, Y, Z, BATCH, world, device=local) if world > 1 else None
-        self.zb = self.plan[rank] if self.plan is not None else (0, -1)
+        self.plan = multi.plan_windows(f, X, Y, Z, BATCH, world, device=local) if world > 1 else None
         self.h, _ = core.program_handle(f)
         self.tau = core.mixed_tau(self.h.program, X, Y, Z)
         self.local = local
-        need, _, _ = self.h.generate(X, Y, Z, BATCH, True, args.precision, self.tau, None, 0, zb=self.zb, device=local,
-                                     stream=self.stream)
+        self.root_gather = None
+        self._size_buffers()
+        self.gather_events = []
+        if world > 1 and not args.no_rebalance:
+            self.rebalance()
+
+    def _size_buffers(self):
+        """Count-only pass of this rank's window -> output capacity (and the shared root buffer, once)."""
+        torch, dist, args = self.torch, self.dist, self.args
+        X, Y, Z = self.axes
+        self.window = self.plan[self.rank] if self.plan is not None else None
+        nb = [(len(a) + BATCH - 1) // BATCH for a in (X, Y, Z)]
+        win = self.window if self.window is not None else (0, nb[0] * nb[1] * nb[2])
+        need, _, _ = self.h.generate_window(X, Y, Z, BATCH, True, args.precision, self.tau, win, device=self.local, stream=self.stream)
+        self.win = win
         self.cap = int(need * 1.02) + 1024
         self.out = torch.empty((self.cap, 9), dtype=torch.float32, device='cuda')
-        self.root_gather = None
-        if world > 1 and args.gather == 'root':
+        if self.world > 1 and args.gather == 'root' and self.root_gather is None:
+            from sdf_b200 import multi
             needs = torch.tensor([need], dtype=torch.int64, device='cuda')
             dist.all_reduce(needs)
-            self.root_gather = multi.RootGather(int(needs.item() * 1.02) + 4096, local)
-        self.gather_events = []
+            self.root_gather = multi.RootGather(int(needs.item() * 1.05) + 65536, self.local)
+
+    def rebalance(self):
+        """One measured re-plan: three untimed steps, per-rank device time of the pipeline, windows re-cut so that
+        batches in costlier regions weigh more (multi.plan_windows rates)."""
+        torch, dist = self.torch, self.dist
+        from sdf_b200 import multi
+        X, Y, Z = self.axes
+        ms = []
+        for _ in range(3):
+            _, _, timings, _ = self.step()
+            ms.append(float(timings[2]))
+        mine = torch.tensor([sorted(ms)[1]], dtype=torch.float64, device='cuda')
+        allt = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allt, mine)
+        seconds = [float(t.item()) * 1e-3 for t in allt]
+        self.first_plan, self.first_plan_ms = self.plan, [t * 1e3 for t in seconds]
+        self.plan = multi.plan_windows(self.f, X, Y, Z, BATCH, self.world, device=self.local, rates=(self.plan, seconds))
+        self._size_buffers()
 
     def step(self):
         torch, args = self.torch, self.args
         X, Y, Z = self.axes
         if self.root_gather is not None:
-            return self.root_gather.run(self.h, X, Y, Z, BATCH, True, args.precision, self.tau, self.zb, stream=self.stream)
-        n_tri, stats, timings = self.h.generate(X, Y, Z, BATCH, True, args.precision, self.tau, self.out, self.cap,
-                                                zb=self.zb, device=self.local, stream=self.stream)
+            return self.root_gather.run(self.h, X, Y, Z, BATCH, True, args.precision, self.tau, None, stream=self.stream,
+                                        window=self.win)
+        n_tri, stats, timings = self.h.generate_window(X, Y, Z, BATCH, True, args.precision, self.tau, self.win,
+                                                       tri_out=self.out, capacity=self.cap, device=self.local, stream=self.stream)
         gathered = None
         if self.world > 1:
             from sdf_b200 import multi
@@ -345,7 +375,7 @@ class DeviceSeries:
             ev[k][1].record()
             fused_ms.append(timings[1])
             prepass_ms.append(timings[0])
-            kern_ms.append((timings[4], timings[5], timings[6]))
+            kern_ms.append((timings[4], timings[5], timings[6], timings[7]))
             stats_acc = stats
         self.barrier()
         t1 = time.time()
@@ -364,7 +394,7 @@ class DeviceSeries:
                     per_rank_min=dict(step_ms=float(t_min[0].item()), pipeline_ms=float(t_min[1].item()), tile_ms=float(t_min[2].item())),
                     per_rank_max=dict(step_ms=float(t_max[0].item()), pipeline_ms=float(t_max[1].item()), tile_ms=float(t_max[2].item())),
                     agg=[float(v) for v in agg.tolist()], prepass_ms=sum(prepass_ms) / steps,
-                    kern_ms=[sum(k[i] for k in kern_ms) / steps for i in range(3)],
+                    kern_ms=[sum(k[i] for k in kern_ms) / steps for i in range(4)],
                     gather_ms=(sum(gather_ms) / len(gather_ms)) if gather_ms else None, t0=t0, t1=t1)
 
 
@@ -467,14 +497,15 @@ def run_ours(args):
                   'value': ss.n_points / (rs['ms_per_step'] / 1e3) / 1e6, 'unit': 'Mpoints/s',
                   'mtris_per_s': rs['agg'][0] / (rs['ms_per_step'] / 1e3) / 1e6, 'triangles': int(rs['agg'][0]),
                   'per_rank_min_ms': rs['per_rank_min'], 'per_rank_max_ms': rs['per_rank_max'],
-                  'slabs': [list(p) for p in ss.plan] if ss.plan else None}
+                  'windows': [list(p) for p in ss.plan] if ss.plan else None,
+                  'first_plan_per_rank_ms': getattr(ss, 'first_plan_ms', None)}
         del ss
 
     if rank == 0:
         tri_total, evaluated, refined, cubes = res['agg'][:4]
         peak, peak_src = peaks()
         tile_s = res['tile_ms'] / 1e3
-        tile_kernel_name = ('tile_sign_body (jit_kernel, <= 592 x 256)' if args.precision == 'exact' else 'tile_eval_body (jit_kernel, 148 x 1024)')
+        tile_kernel_name = ('tile_sign_body (jit_kernel, 592 x 256: fused SDF evaluation + sign masks)' if args.precision == 'exact' else 'tile_eval_body (jit_kernel, 148 x 1024)')
         achieved = (evaluated / world) * 12.0 / tile_s / 1e9 if tile_s > 0 else 0.0     # per-GPU kernel
         # DRAM traffic of the dominant kernel: an ncu figure (profiles/r2_traffic.json, written from the committed
         # capture of THIS kernel on THIS workload); reported only when that capture's kernel time agrees with the
@@ -501,7 +532,8 @@ def run_ours(args):
             'config': {'workload': workload_name(w),
                        'points': n_points, 'precision': args.precision,
                        'l2': 'flushed between timed iterations (768 MB memset, outside the per-step events)',
-                       'parallelism': 'z-slab x%d' % world,
+                       'parallelism': 'z-slab x%d (windows of the Z-major batch order, balanced by active batches%s)' % (
+                           world, ', one measured re-plan' if (world > 1 and not args.no_rebalance) else ''),
                        'gather': (args.gather if world > 1 else None),
                        'sample_grouping': dict(zip(('share_axis', 'samples_per_thread', 'invariant_fraction'),
                                                    h.jit_plan({'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}[args.precision]))),
@@ -512,7 +544,8 @@ def run_ours(args):
             'batches': {'skipped': int(res['agg'][4]), 'empty': int(res['agg'][5]), 'nonempty': int(res['agg'][6])},
             'samples_evaluated': int(evaluated), 'samples_refined_f64': int(refined), 'active_cubes': int(cubes),
             'kernel_ms': {'tile_pipeline_A+B+C': res['fused_ms'], 'skip_prepass+setup': res['prepass_ms'],
-                          'tile_kernel(A)': res['kern_ms'][0], 'refine_points_kernel(B)': res['kern_ms'][1],
+                          'tile_kernel(A)': res['kern_ms'][0], 'tile_classify_kernel(A2)': res['kern_ms'][3],
+                          'refine_points_kernel(B)': res['kern_ms'][1],
                           'extract_kernel(C)': res['kern_ms'][2],
                           'per_rank_min': res['per_rank_min'], 'per_rank_max': res['per_rank_max']},
             'gpu_launches': 5 * args.steps,
@@ -552,6 +585,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the knurling 1024^3 strong-scaling side series')
     ap.add_argument('--no-cold', action='store_true', help='skip the cold-start side measurement')
+    ap.add_argument('--no-rebalance', action='store_true', help='N>1: keep the plan balanced by active batches (no measured re-plan)')
     ap.add_argument('--gather', default='root', choices=['root', 'allgather'],
                     help='N>1: fused NVLink peer writes into rank 0 (default) or NCCL send/recv all-gather')
     args = ap.parse_args()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SDFB200_ABI_VERSION 1
+#define SDFB200_ABI_VERSION 2
 
 #define SDFB200_OK 0
 #define SDFB200_E_INVALID (-1)   /* bad argument / malformed program            */
@@ -92,15 +92,16 @@ int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n, double* d
  *   n_tri        triangles produced (or required, with SDFB200_E_CAPACITY)
  *   stats[6]     skipped, empty, nonempty batches (core.py:135-141), samples evaluated in f32,
  *                samples re-evaluated in f64, active cubes
- *   timings_ms[7] optional, CUDA events on `stream`: [0] setup + skip pre-pass, [1] tile pipeline (A+B+C),
- *                [2] whole device section, [3] statistics + result copy, [4] tile_eval kernel (A),
- *                [5] float64 refinement kernel (B), [6] extraction kernel (C)
+ *   timings_ms[8] optional, CUDA events on `stream`: [0] setup + skip pre-pass, [1] tile pipeline (A+B+C),
+ *                [2] whole device section, [3] statistics + result copy, [4] tile evaluation kernel (A; for
+ *                precision `exact` the sign-mask evaluation alone), [5] float64 refinement kernel (B),
+ *                [6] extraction kernel (C), [7] tile classification kernel (precision `exact`, else 0)
  */
 int sdfb200_generate(sdfb200_prog* prog,
                      const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
                      int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
                      float* tri_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
-                     double timings_ms[7], int device, void* stream);
+                     double timings_ms[8], int device, void* stream);
 
 /*
  * Replaces: core.save() for '.stl' paths (sdf/core.py:152-156) = generate() followed by
@@ -113,7 +114,7 @@ int sdfb200_generate_stl(sdfb200_prog* prog,
                          const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
                          int batch_size, int sparse, int precision, double tau,
                          void* records_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
-                         double timings_ms[7], int device, void* stream);
+                         double timings_ms[8], int device, void* stream);
 
 /*
  * Fused multi-GPU gather (replaces nothing in the reference, which is single process): the ROOT rank
@@ -136,7 +137,22 @@ int sdfb200_generate_shared(sdfb200_prog* prog,
                             const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
                             int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,
                             sdfb200_shared* dst, int which, int64_t* n_tri_local, int64_t stats[6],
-                            double timings_ms[7], int device, void* stream);
+                            double timings_ms[8], int device, void* stream);
+
+/*
+ * Multi-GPU with slabs cut INSIDE a batch layer (replaces nothing in the reference, whose only parallelism is
+ * the ThreadPool over independent batches, sdf/core.py:131-133): like sdfb200_generate (dst == NULL) or
+ * sdfb200_generate_shared (dst != NULL, `which` = cursor), but the batches of the call are the window
+ * [ub_begin, ub_end) of the Z-MAJOR batch order  u = bz * (nbx * nby) + bx * nby + by  instead of whole Z batch
+ * layers -- a Z-slab with ragged first and last layers, so that N ranks get equal numbers of ACTIVE batches
+ * even when the surface lives in fewer layers than there are ranks.  Batches stay the reference's batches (same
+ * lattice slices, same _skip decisions): the union of the windows' triangles is the single-call result.
+ */
+int sdfb200_generate_window(sdfb200_prog* prog,
+                            const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
+                            int batch_size, int sparse, int precision, double tau, int64_t ub_begin, int64_t ub_end,
+                            float* tri_out, int64_t tri_capacity, sdfb200_shared* dst, int which,
+                            int64_t* n_tri, int64_t stats[6], double timings_ms[8], int device, void* stream);
 
 /*
  * Run-time specialisation check (needs no GPU): generate the straight-line evaluator of `prog` for

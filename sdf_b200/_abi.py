@@ -20,7 +20,7 @@ EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
            'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
            'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
-           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared']
+           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared', 'sdfb200_generate_window']
 
 
 class SdfB200Error(RuntimeError):
@@ -74,6 +74,8 @@ def lib():
     L.sdfb200_shared_count.argtypes = [vp, i32, ctypes.POINTER(i64), vp]
     L.sdfb200_generate_shared.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
                                           vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
+    L.sdfb200_generate_window.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i64, i64,
+                                          vp, i64, vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
     L.sdfb200_jit_plan.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(dbl)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
@@ -225,7 +227,7 @@ class ProgramHandle:
         """Like generate(), but fills 50-byte binary-STL records; returns (n_tri, stats[6], timings_ms[4])."""
         n_tri = ctypes.c_int64(0)
         stats = np.zeros(6, np.int64)
-        timings = np.zeros(7, np.float64)
+        timings = np.zeros(8, np.float64)
         rc = lib().sdfb200_generate_stl(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y), Z.ctypes.data, len(Z),
                                         int(batch_size), int(bool(sparse)), PREC[precision], float(tau),
                                         _ptr(records_out), int(capacity), ctypes.byref(n_tri), stats.ctypes.data,
@@ -240,11 +242,29 @@ class ProgramHandle:
         """This rank's slab, written straight into the root's shared buffer; returns (n_local, stats, timings)."""
         n_tri = ctypes.c_int64(0)
         stats = np.zeros(6, np.int64)
-        timings = np.zeros(7, np.float64)
+        timings = np.zeros(8, np.float64)
         _check(lib().sdfb200_generate_shared(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y), Z.ctypes.data, len(Z),
                                              int(batch_size), int(bool(sparse)), PREC[precision], float(tau),
                                              int(zb[0]), int(zb[1]), shared._h, int(which), ctypes.byref(n_tri),
                                              stats.ctypes.data, timings.ctypes.data, device, stream))
+        return n_tri.value, stats, timings
+
+    def generate_window(self, X, Y, Z, batch_size, sparse, precision, tau, window, tri_out=None, capacity=0,
+                        shared=None, which=0, device=0, stream=None):
+        """The batches [window[0], window[1]) of the Z-major batch order (include/sdfb200.h); output into
+        ``tri_out`` (device / host / None = count only) or, with ``shared``, into the root GPU's buffer.
+        Returns (n_tri, stats[6], timings_ms[7]); raises CapacityError with .needed."""
+        n_tri = ctypes.c_int64(0)
+        stats = np.zeros(6, np.int64)
+        timings = np.zeros(8, np.float64)
+        rc = lib().sdfb200_generate_window(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y), Z.ctypes.data, len(Z),
+                                           int(batch_size), int(bool(sparse)), PREC[precision], float(tau),
+                                           int(window[0]), int(window[1]), _ptr(tri_out), int(capacity),
+                                           shared._h if shared is not None else None, int(which),
+                                           ctypes.byref(n_tri), stats.ctypes.data, timings.ctypes.data, device, stream)
+        if rc == E_CAPACITY:
+            raise CapacityError(rc, lib().sdfb200_last_error().decode(), n_tri.value)
+        _check(rc)
         return n_tri.value, stats, timings
 
     def generate(self, X, Y, Z, batch_size, sparse, precision, tau, tri_out, capacity,
@@ -252,7 +272,7 @@ class ProgramHandle:
         """Returns (n_tri, stats[6], timings_ms[4]); raises CapacityError with .needed."""
         n_tri = ctypes.c_int64(0)
         stats = np.zeros(6, np.int64)
-        timings = np.zeros(7, np.float64)
+        timings = np.zeros(8, np.float64)
         rc = lib().sdfb200_generate(self._h, X.ctypes.data, len(X), Y.ctypes.data, len(Y),
                                     Z.ctypes.data, len(Z), int(batch_size), int(bool(sparse)),
                                     PREC[precision], float(tau), int(zb[0]), int(zb[1]), _ptr(tri_out), int(capacity),

@@ -133,14 +133,24 @@ def batch_counts(X, Y, Z, batch_size):
 
 
 def mixed_tau(program, X, Y, Z):
-    """Guard band of PREC_MIXED: TAU_ULPS float32 ulps of the largest coordinate / constant."""
-    mag = 1.0
+    """Guard band of the float32 pass (precisions `mixed` and `exact`): samples with |d| < tau are re-evaluated
+    in float64.  TAU_ULPS float32 ulps of the largest coordinate / constant (+ a few per program word) -- tuned
+    and tested on trees whose constants do not amplify rounding errors -- times the a-priori amplification of
+    THIS tree (errbound.gain: reciprocals of small constant differences, steep easings, large twist rates ...;
+    1 for the BASELINE configurations, inf -- float64 everywhere -- for a tree with a jump)."""
+    from . import errbound
+    cmax = 1.0
     for a in (X, Y, Z):
         if len(a):
-            mag = max(mag, abs(float(a[0])), abs(float(a[-1])))
-    mag = max(mag, min(program.scale_hint, 1e6))
+            cmax = max(cmax, abs(float(a[0])), abs(float(a[-1])))
+    mag = max(cmax, min(program.scale_hint, 1e6))
     ulps = TAU_ULPS + TAU_ULPS_PER_WORD * len(program.code)
-    return ulps * float(np.finfo(np.float32).eps) * mag
+    cache = program.__dict__.setdefault('_gain', {})          # per program and coordinate magnitude
+    key = float(np.float32(cmax))
+    g = cache.get(key)
+    if g is None:
+        g = cache[key] = errbound.gain(program, cmax)
+    return ulps * float(np.finfo(np.float32).eps) * mag * g
 
 
 def default_capacity(X, Y, Z):
@@ -181,7 +191,7 @@ def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='exa
                 evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]),
                 prepass_ms=float(timings[0]), fused_ms=float(timings[1]), device_ms=float(timings[2]),
                 d2h_ms=float(timings[3]), tile_eval_ms=float(timings[4]), refine_ms=float(timings[5]),
-                extract_ms=float(timings[6]), tau=tau, precision=precision)
+                extract_ms=float(timings[6]), classify_ms=float(timings[7]), tau=tau, precision=precision)
     return out[:n_tri], info
 
 

@@ -12,8 +12,8 @@ jit_kernel(const GridDesc g, int sparse, unsigned char* flags, unsigned int* act
 #elif SDF_JIT_KERNEL == 4          // precision `exact`: sign masks by ballot, no value tile
 extern "C" __global__ void __launch_bounds__(SIGN_THREADS, SIGN_BLOCKS_PER_SM)
 jit_kernel(const GridDesc g, const float tau, const unsigned int* active_list, const unsigned int work_begin,
-           const unsigned int work_end, const TileLists L, Counters* ctr, unsigned char* scratch, unsigned int* tile_done) {
-    tile_sign_body<32, SIGN_THREADS>(SpecEval(), g, tau, active_list, work_begin, work_end, L, ctr, scratch, tile_done);
+           const unsigned int work_end, Counters* ctr, unsigned char* scratch) {
+    tile_sign_body<32, SIGN_THREADS>(SpecEval(), g, tau, active_list, work_begin, work_end, ctr, scratch);
 }
 #elif SDF_JIT_KERNEL >= 1 && SDF_JIT_KERNEL <= 3
 #define SDF_JIT_TILE_THREADS ((SDF_JIT_KERNEL - 1) == SDFB200_PREC_F64 ? 512 : 1024)

@@ -49,7 +49,8 @@ struct GridDesc {
     int nx, ny, nz;        // lattice points per axis
     int bs;                // cubes per batch side (core.py BATCH_SIZE)
     int nbx, nby, nbz;     // batches per axis = ceil(n / bs)   (core.py:115-117)
-    int zb0, zb1;          // Z batch layers handled by this call
+    int ub0, ub1;          // batch window of this call, in Z-MAJOR order u = bz * (nbx * nby) + bx * nby + by
+                           // (a Z-slab of whole batch layers [zb0, zb1) is the window [zb0, zb1) * nbx * nby)
     int sub;               // sub-tiles per batch side = ceil(bs / TS)
 };
 
@@ -66,6 +67,16 @@ struct Counters {
     unsigned int extract_done;                  // CTAs of the last extraction kernel that have finished (stats tail)
     unsigned int pad_[1];
 };
+
+// t-th batch of the call's window -> batch coordinates; the batch id keeps core.py:119's order (X-major)
+__device__ __forceinline__ unsigned int window_batch(const GridDesc& g, int t, int* bx, int* by, int* bz) {
+    const int u = g.ub0 + t, nxy = g.nbx * g.nby;
+    *bz = u / nxy;
+    const int r = u - *bz * nxy;
+    *bx = r / g.nby;
+    *by = r - *bx * g.nby;
+    return (unsigned int)((*bx * g.nby + *by) * g.nbz + *bz);
+}
 
 // ---------------------------------------------------------------------------------------
 // float64 helpers that the compiler may not contract into FMAs: the marching-cubes
@@ -215,15 +226,13 @@ __device__ __forceinline__ void skip_prepass_body(const EV& img, const GridDesc&
                                                   unsigned int* __restrict__ active_list,
                                                   unsigned int* __restrict__ batch_tris,
                                                   Counters* __restrict__ ctr) {
-    const int nzl = g.zb1 - g.zb0;
-    const int total = g.nbx * g.nby * nzl;
+    const int total = g.ub1 - g.ub0;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int tb = gt / PREPASS_LANES, k = gt % PREPASS_LANES;
     const bool in = tb < total;
     const int t = in ? tb : 0;
-    const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
-    const int bz = g.zb0 + bzl;
-    const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + bz);
+    int bx, by, bz;
+    const unsigned int bid = window_batch(g, t, &bx, &by, &bz);
     bool skipped = false;
     if (sparse) {                                               // (uniform: every lane reaches the shuffles)
         const int ix0 = bx * g.bs, iy0 = by * g.bs, iz0 = bz * g.bs;
@@ -633,7 +642,7 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 }
 
 // ---------------------------------------------------------------------------------------
-// (A') PREC_EXACT: evaluate + classify WITHOUT a value tile, by autonomous warps.
+// (A') PREC_EXACT: evaluate + classify WITHOUT a value tile.
 //
 // In `exact` mode every float32 value that could reach the output is re-evaluated in float64 by (B), so
 // the fast pass only has to answer two questions per sample: "is it > 0" and "is |d| < tau".  Both are
@@ -643,23 +652,26 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 // whose masks hold no mixed cube simply yields no candidates: skimage's "level within data range"
 // check, core.py:53-56), no tile store.
 //
-// There is no shared memory and no CTA barrier at all: every WARP is its own worker.  It takes batches
-// of SIGN_BATCH thread-runs of one tile from a global cursor (a tile = SIGN_NB batches, so the sparse,
-// uneven work balances at a granularity of 1/13 tile per warp).  In a thread-run a lane evaluates N
+// (A'1) tile_sign_body -- evaluation by autonomous warps: no CTA barrier anywhere, every WARP is its own
+// worker.  It takes batches of SIGN_BATCH thread-runs of one tile from a global cursor (a tile = 13
+// batches, so the sparse, uneven work balances at 1/13 tile per warp).  In a thread-run a lane evaluates N
 // consecutive samples along the share axis S (they share their other two coordinates, i.e. registers:
 // the axis-sharing of the generated evaluator); the lane index is the coordinate along the lane axis U.
 // Lanes 0..31 cover samples 0..31 of a U-line; the 33rd sample of every line (the plane shared with the
 // next tile) is evaluated by separate thread-runs that write one byte per line.  Masks go to a per-tile
-// scratch block in global memory (10 KB, L2 resident).  The warp that completes a tile's last batch
-// (device-scope counter) classifies the tile by itself: it sweeps the 33 S-rows with its lanes along W,
-// classifies 32 cubes per lane and row with 64-bit word operations, and compacts the candidate cubes and
-// the samples float64 must confirm into the global lists (count pass, one pair of atomics, write pass).
+// scratch block in global memory (10 KB, L2 resident).
+// (A'2) tile_classify_body -- one CTA per tile reads the masks back, classifies the 32^3 cubes with 64-bit
+// word operations (one thread per column of 32 cubes), queues the candidate cubes and every sample
+// float64 must confirm (bitmap compaction: one CTA prefix sum, one slot + one pair of list ranges per tile).
+// All tiles classify side by side in a few microseconds; inside the evaluation kernel the same work
+// was a serial, latency-bound tail (measured: profiles/r2_tile_gearlike_autonomous_v1.txt).
 #define SIGN_TP 33
 #define SIGN_LINES (SIGN_TP * SIGN_TP)
 #define SIGN_BATCH 8                                            // thread-runs per work item
 #define SIGN_STRIDE 9856                                        // bytes of scratch per tile: 1089 x {u32, u32} + 1089 u8, padded
 #define SIGN_THREADS 256
 #define SIGN_BLOCKS_PER_SM 4
+#define CLASSIFY_THREADS 256
 
 template <int N> struct SignShape {
     static constexpr int RUNS_S = (SIGN_TP + N - 1) / N;        // thread-runs per S-line
@@ -669,123 +681,27 @@ template <int N> struct SignShape {
     static constexpr int NB = (R_TILE + SIGN_BATCH - 1) / SIGN_BATCH;       // batches (work items) per tile
 };
 
-struct SignLine { unsigned long long p, u; };
-
-// masks of line `ln` as 33-bit words (bit 32 from the byte plane when the tile is 33 samples long along U)
-__device__ __forceinline__ SignLine sign_line(const uint2* __restrict__ masks, const unsigned char* __restrict__ hi,
-                                              int ln, bool has_hi) {
-    const uint2 mk = __ldcg(masks + ln);
-    const unsigned int h8 = has_hi ? (unsigned int)__ldcg(hi + ln) : 0u;
-    SignLine r;
-    r.p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
-    r.u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
-    return r;
-}
-
-// One warp classifies one tile from its mask block.  Lanes run along W: lane l owns column (cs, cw = l) of
-// cubes and line (is, iw = l); lane 31 also owns line (is, 32).  WRITE = false: count only.
-template <int TS, int AU, int AS, int AW, bool WRITE>
-__device__ __forceinline__ unsigned int sign_classify_pass(const uint2* __restrict__ masks, const unsigned char* __restrict__ hi,
-                                                           const int pu, const int ps, const int pw, const int py, const int pz,
-                                                           const int lane, const TileLists& L, const unsigned int slot,
-                                                           unsigned int cat, unsigned int pat) {
-    constexpr int TP = SIGN_TP;
-    const bool has_hi = (pu == TP);
-    const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
-    const bool col_on = lane < pw - 1;                  // this lane's cube column exists
-    const bool line_on = lane < pw;                     // this lane's line exists
-    const bool line32_on = lane == 31 && pw == TP;      // lane 31 also owns line iw = 32
-    unsigned int total = 0;
-    // row combination of the two lines a cube column touches in S-row `is`: all > 0 / any > 0 / any uncertain,
-    // each over sample pairs (bit j: samples j and j+1 along U)
-    unsigned long long ra = 0ull, ro = 0ull, ru = 0ull;       // row is
-    unsigned long long u_own = 0ull, u_32 = 0ull;             // uncertainty words of this lane's line(s) in row is
-    {
-        SignLine a = {0ull, 0ull}, b = {0ull, 0ull};
-        if (line_on) a = sign_line(masks, hi, lane, has_hi);
-        if (col_on || line32_on) b = sign_line(masks, hi, lane + 1, has_hi);
-        ra = (a.p & (a.p >> 1)) & (b.p & (b.p >> 1)); ro = (a.p | (a.p >> 1)) | (b.p | (b.p >> 1)); ru = (a.u | (a.u >> 1)) | (b.u | (b.u >> 1));
-        u_own = a.u; u_32 = b.u;
-    }
-    unsigned int w_prev = 0u;                                  // candidate word of column (is - 1, lane)
-    for (int is = 0; is < ps; ++is) {
-        // next row (is + 1)
-        unsigned long long na = 0ull, no = 0ull, nu = 0ull, nu_own = 0ull, nu_32 = 0ull;
-        if (is + 1 < ps) {
-            SignLine a = {0ull, 0ull}, b = {0ull, 0ull};
-            if (line_on) a = sign_line(masks, hi, (is + 1) * TP + lane, has_hi);
-            if (col_on || line32_on) b = sign_line(masks, hi, (is + 1) * TP + lane + 1, has_hi);
-            na = (a.p & (a.p >> 1)) & (b.p & (b.p >> 1)); no = (a.p | (a.p >> 1)) | (b.p | (b.p >> 1)); nu = (a.u | (a.u >> 1)) | (b.u | (b.u >> 1));
-            nu_own = a.u; nu_32 = b.u;
-        }
-        // cube column (cs = is, cw = lane): candidate when its corners are not all > 0 and not all <= 0, or one is uncertain
-        unsigned int W = 0u;
-        if (col_on && is + 1 < ps) W = (unsigned int)(((ro | no) & ~(ra & na)) | (ru | nu)) & cumask;
-        // line (is, lane) touches columns (is-1 | is, lane-1 | lane): queue every corner of a candidate cube
-        const unsigned int w_here = W | w_prev;
-        unsigned int w_left = __shfl_up_sync(0xffffffffu, w_here, 1);
-        if (lane == 0) w_left = 0u;
-        unsigned long long ref = 0ull, ref32 = 0ull;
-        if (line_on) { const unsigned int Wl = w_here | w_left; ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | u_own; }
-        if (line32_on) { ref32 = (unsigned long long)w_here | ((unsigned long long)w_here << 1) | u_32; }
-        const unsigned int cnt = (unsigned int)__popc(W) | (((unsigned int)__popcll(ref) + (unsigned int)__popcll(ref32)) << 16);
-        unsigned int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        const unsigned int row_total = __shfl_sync(0xffffffffu, incl, 31);
-        if (WRITE) {
-            const unsigned int excl = incl - cnt;
-            unsigned int c_at = cat + (total & 0xffffu) + (excl & 0xffffu);
-            unsigned int p_at = pat + (total >> 16) + (excl >> 16);
-            int cc[3], ii[3];
-            cc[AS] = is; cc[AW] = lane; ii[AS] = is; ii[AW] = lane;
-            unsigned int word = W;
-            while (word) {
-                cc[AU] = __ffs(word) - 1;
-                word &= word - 1u;
-                // cube id with fixed strides: cx << 10 | cy << 5 | cz
-                if (c_at < L.cube_cap) L.cubes[c_at] = make_uint2(slot, (unsigned int)((cc[0] << 10) | (cc[1] << 5) | cc[2]));
-                ++c_at;
-            }
-            unsigned long long lw = ref;
-            while (lw) {
-                ii[AU] = __ffsll((long long)lw) - 1;
-                lw &= lw - 1ull;
-                if (p_at < L.pt_cap) L.pts[p_at] = make_uint2(slot, (unsigned int)((ii[0] * py + ii[1]) * pz + ii[2]));
-                ++p_at;
-            }
-            ii[AW] = TP - 1;
-            lw = ref32;
-            while (lw) {
-                ii[AU] = __ffsll((long long)lw) - 1;
-                lw &= lw - 1ull;
-                if (p_at < L.pt_cap) L.pts[p_at] = make_uint2(slot, (unsigned int)((ii[0] * py + ii[1]) * pz + ii[2]));
-                ++p_at;
-            }
-        }
-        total += row_total;               // (low half: <= 32768 cubes, high half: <= 35937 samples per tile -- no carry)
-        ra = na; ro = no; ru = nu; u_own = nu_own; u_32 = nu_32; w_prev = W;
-    }
-    return total;
-}
+// lattice axis roles of the sign kernels, from the evaluator's share axis (-1: no preference -> z)
+template <int SHARE> struct SignAxes {
+    static constexpr int AS = SHARE < 0 ? 2 : SHARE;           // thread-runs
+    static constexpr int AU = AS == 2 ? 1 : 2;                  // lanes
+    static constexpr int AW = AS == 0 ? 1 : 0;                  // batches of runs
+};
 
 template <int TS, int THREADS, class EV>
 __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, const float tau,
                                                const unsigned int* __restrict__ active_list,
                                                const unsigned int work_begin, const unsigned int work_end_arg,
-                                               const TileLists L, Counters* __restrict__ ctr,
-                                               unsigned char* __restrict__ scratch, unsigned int* __restrict__ tile_done) {
+                                               Counters* __restrict__ ctr, unsigned char* __restrict__ scratch) {
     static_assert(TS == 32, "one mask word per line");
     constexpr int TP = SIGN_TP;
     constexpr int N = EV::kN;
-    constexpr int AS = EV::kShare < 0 ? 2 : EV::kShare;        // share axis (thread-run), lane axis, batch axis
-    constexpr int AU = AS == 2 ? 1 : 2;
-    constexpr int AW = AS == 0 ? 1 : 0;
+    typedef SignAxes<EV::kShare> AX;
+    constexpr int AS = AX::AS, AU = AX::AU, AW = AX::AW;
     typedef SignShape<N> SH;
+    __shared__ float s_axis[THREADS / 32][TP + 15];             // warp-private: the tile's S-axis values (clamped past the end)
     const int lane = (int)(threadIdx.x & 31u);
+    float* const sax = s_axis[threadIdx.x >> 5];
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
     const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
     const unsigned int n_items = (work_end > work_begin ? work_end - work_begin : 0u) * (unsigned int)SH::NB;
@@ -804,79 +720,190 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
         const bool valid = tile_geom<TS>(g, bid, sidx, t);
         // a tile that is one sample thick along some axis holds no cube (the reference still evaluates it,
         // skimage raises, the batch counts as empty: core.py:53-56): nothing to evaluate
-        const bool thin = !valid || t.px < 2 || t.py < 2 || t.pz < 2;
-        const int ext[3] = {thin ? 0 : t.px, thin ? 0 : t.py, thin ? 0 : t.pz};
+        if (!valid || t.px < 2 || t.py < 2 || t.pz < 2) continue;
+        const int ext[3] = {t.px, t.py, t.pz};
         const int pu = ext[AU], ps = ext[AS], pw = ext[AW];
         const float* const axf[3] = {g.xf + (t.bx0 + t.ox), g.yf + (t.by0 + t.oy), g.zf + (t.bz0 + t.oz)};
         uint2* const masks = reinterpret_cast<uint2*>(scratch + (size_t)tw * SIGN_STRIDE);      // per line {pos, unc}, bits 0..31
         unsigned char* const hi = reinterpret_cast<unsigned char*>(masks + SIGN_LINES);       // per line bit 32: pos | unc << 1
 
-        // ---------------------------------------------------------------- evaluation
-        if (!thin) {
-            const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
-            const float cu_main = __ldg(axf[AU] + min(lane, pu - 1));
-            const float cu_last = __ldg(axf[AU] + (pu - 1));
-            const int r_end = min((bb + 1) * SIGN_BATCH, SH::R_TILE);
-            for (int r = bb * SIGN_BATCH; r < r_end; ++r) {
-                const bool main_run = r < SH::R_MAIN;                       // warp uniform
-                const int rr = main_run ? r : (r - SH::R_MAIN) * 32 + lane;
-                const int iw = rr / SH::RUNS_S, is0 = (rr - iw * SH::RUNS_S) * N;
-                const bool on = rr < SH::R_MAIN && iw < pw && is0 < ps && (main_run || pu == TP);
-                if (!__any_sync(0xffffffffu, on)) continue;                // (ragged tile / nothing left in this run)
-                const int iwc = min(iw, pw - 1);
-                const float cw = __ldg(axf[AW] + iwc);
-                float c[3][N], d[N];
+        __syncwarp();                                             // (the previous batch is done with sax)
+        sax[lane] = __ldg(axf[AS] + min(lane, ps - 1));
+        if (lane < TP + 15 - 32) sax[32 + lane] = __ldg(axf[AS] + min(32 + lane, ps - 1));
+        const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
+        const float cu_main = __ldg(axf[AU] + min(lane, pu - 1));
+        const float cu_last = __ldg(axf[AU] + (pu - 1));
+        __syncwarp();
+        const int r_end = min((bb + 1) * SIGN_BATCH, SH::R_TILE);
+        for (int r = bb * SIGN_BATCH; r < r_end; ++r) {
+            const bool main_run = r < SH::R_MAIN;                       // warp uniform
+            const int rr = main_run ? r : (r - SH::R_MAIN) * 32 + lane;
+            const int iw = rr / SH::RUNS_S, is0 = (rr - iw * SH::RUNS_S) * N;
+            const bool on = rr < SH::R_MAIN && iw < pw && is0 < ps && (main_run || pu == TP);
+            if (!__any_sync(0xffffffffu, on)) continue;                // (ragged tile / nothing left in this run)
+            const float cw = __ldg(axf[AW] + min(iw, pw - 1));
+            const float* const sp = sax + min(is0, TP - 1);            // (is0 + k <= 32 + N - 1 < TP + 15: filled, clamped)
+            float c[3][N], d[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                c[AU][k] = main_run ? cu_main : cu_last; c[AW][k] = cw;
+                c[AS][k] = sp[k];
+            }
+            ev.template run<float, N, true>(c[0], c[1], c[2], d);
+            if (main_run) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    c[AU][k] = main_run ? cu_main : cu_last; c[AW][k] = cw;
-                    c[AS][k] = __ldg(axf[AS] + min(is0 + k, ps - 1));
+                    const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
+                    const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
+                    if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
                 }
-                ev.template run<float, N, true>(c[0], c[1], c[2], d);
-                if (main_run) {
+            } else if (on) {
 #pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
-                        const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
-                        if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
-                    }
-                } else if (on) {
+                for (int k = 0; k < N; ++k)
+                    if (is0 + k < ps)
+                        hi[(is0 + k) * TP + iw] = (unsigned char)((d[k] > 0.0f ? 1u : 0u) | (fabsf(d[k]) < tau ? 2u : 0u));
+            }
+        }
+    }
+}
+
+struct ClassifySmem {
+    unsigned int cand[32 * 32];                                 // per (cs, cw): bit cu <=> cube is a candidate
+    unsigned long long refm[SIGN_LINES];                        // per (is, iw) line: bit iu <=> sample queued for float64
+    unsigned int warp_sums[CLASSIFY_THREADS / 32];
+    unsigned int slot, cube_gbase, pt_gbase;
+};
+
+// (A'2) one CTA per tile of the round (grid-stride); SHARE = the share axis the sign kernel ran with
+template <int TS, int SHARE>
+__device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsigned int* __restrict__ active_list,
+                                                   const unsigned int work_begin, const unsigned int work_end_arg,
+                                                   const TileLists L, Counters* __restrict__ ctr,
+                                                   const unsigned char* __restrict__ scratch) {
+    constexpr int TP = SIGN_TP;
+    constexpr int THREADS = CLASSIFY_THREADS, NW = THREADS / 32;
+    typedef SignAxes<SHARE> AX;
+    constexpr int AS = AX::AS, AU = AX::AU, AW = AX::AW;
+    __shared__ ClassifySmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
+    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
+    const unsigned int n_tiles = work_end > work_begin ? work_end - work_begin : 0u;
+    for (unsigned int tw = blockIdx.x; tw < n_tiles; tw += gridDim.x) {
+        const unsigned int w = work_begin + tw;
+        const unsigned int bid = active_list[w / subs3];
+        const int sidx = (int)(w % subs3);
+        TileGeom t;
+        const bool valid = tile_geom<TS>(g, bid, sidx, t);
+        if (!valid || t.px < 2 || t.py < 2 || t.pz < 2) continue;        // (CTA uniform) thin tile: no cube, not evaluated
+        const int ext[3] = {t.px, t.py, t.pz};
+        const int pu = ext[AU], ps = ext[AS], pw = ext[AW];
+        const uint2* const masks = reinterpret_cast<const uint2*>(scratch + (size_t)tw * SIGN_STRIDE);
+        const unsigned char* const hi = reinterpret_cast<const unsigned char*>(masks + SIGN_LINES);
+        const bool has_hi = (pu == TP);
+        const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
+        // (1) one thread per (cs, cw) column of cubes: 32 cubes along U classified with word operations.
+        //     A cube is a candidate when its corners are not all > 0 and not all <= 0, or one is uncertain.
+        for (int col = tid; col < TS * TS; col += THREADS) {
+            const int cs = col >> 5, cw = col & 31;
+            unsigned int W = 0u;
+            if (cs < ps - 1 && cw < pw - 1) {
+                const int l00 = cs * TP + cw;
+                const int ls[4] = {l00, l00 + 1, l00 + TP, l00 + TP + 1};
+                unsigned long long allp = ~0ull, anyp = 0ull, anyu = 0ull;
 #pragma unroll
-                    for (int k = 0; k < N; ++k)
-                        if (is0 + k < ps)
-                            hi[(is0 + k) * TP + iw] = (unsigned char)((d[k] > 0.0f ? 1u : 0u) | (fabsf(d[k]) < tau ? 2u : 0u));
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned int h8 = has_hi ? (unsigned int)hi[ls[j]] : 0u;
+                    const uint2 mk = masks[ls[j]];
+                    const unsigned long long p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
+                    const unsigned long long u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
+                    allp &= p & (p >> 1); anyp |= p | (p >> 1); anyu |= u | (u >> 1);
+                }
+                W = (unsigned int)((anyp & ~allp) | anyu) & cumask;
+            }
+            sm.cand[col] = W;
+        }
+        __syncthreads();
+        // (2) one thread per line: queue every corner of a candidate cube (and every uncertain sample)
+        for (int ln = tid; ln < SIGN_LINES; ln += THREADS) {
+            const int is = ln / TP, iw = ln - is * TP;
+            unsigned long long ref = 0ull;
+            if (is < ps && iw < pw) {
+                unsigned int Wl = 0u;
+                if (is < TS && iw < TS) Wl |= sm.cand[(is << 5) | iw];
+                if (is < TS && iw > 0) Wl |= sm.cand[(is << 5) | (iw - 1)];
+                if (is > 0 && iw < TS) Wl |= sm.cand[((is - 1) << 5) | iw];
+                if (is > 0 && iw > 0) Wl |= sm.cand[((is - 1) << 5) | (iw - 1)];
+                const unsigned int h8 = has_hi ? (unsigned int)hi[ln] : 0u;
+                ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | (unsigned long long)masks[ln].y |
+                      ((unsigned long long)((h8 >> 1) & 1u) << 32);
+            }
+            sm.refm[ln] = ref;
+        }
+        __syncthreads();
+        // (3) compaction: one prefix sum over the per-thread popcounts (cubes in the low, samples in the
+        //     high half word), one slot + one pair of list ranges per tile, every thread writes its entries
+        unsigned int cnt = 0;
+        for (int wi = tid; wi < TS * TS; wi += THREADS) cnt += (unsigned)__popc(sm.cand[wi]);
+        for (int wi = tid; wi < SIGN_LINES; wi += THREADS) cnt += ((unsigned)__popcll(sm.refm[wi])) << 16;
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        __syncthreads();
+        unsigned int warp_off = 0, total = 0;
+#pragma unroll
+        for (int wi = 0; wi < NW; ++wi) {
+            const unsigned int sv = sm.warp_sums[wi];
+            if (wi < warp) warp_off += sv;
+            total += sv;
+        }
+        if (tid == 0) {
+            const unsigned int nc = total & 0xffffu, np = total >> 16;
+            unsigned int slot = 0;
+            if (nc | np) {
+                slot = atomicAdd(&ctr->n_slots, 1u);
+                if (slot < L.slot_cap) L.tile_meta[slot] = make_tile_meta(t, bid);
+            }
+            sm.slot = slot;
+            sm.cube_gbase = nc ? atomicAdd(&ctr->n_cubes, nc) : 0u;
+            sm.pt_gbase = np ? atomicAdd(&ctr->n_pts, np) : 0u;
+            atomicAdd(&ctr->pts_f32, (unsigned long long)(t.px * t.py * t.pz));
+        }
+        __syncthreads();
+        const unsigned int slot = sm.slot;
+        const unsigned int excl = warp_off + incl - cnt;
+        unsigned int cat = sm.cube_gbase + (excl & 0xffffu);
+        unsigned int pat = sm.pt_gbase + (excl >> 16);
+        if (total != 0u && slot < L.slot_cap) {
+            for (int wi = tid; wi < TS * TS; wi += THREADS) {
+                unsigned int word = sm.cand[wi];
+                int cc[3];
+                cc[AS] = wi >> 5; cc[AW] = wi & 31;
+                while (word) {
+                    cc[AU] = __ffs(word) - 1;
+                    word &= word - 1u;
+                    // cube id with fixed strides: cx << 10 | cy << 5 | cz
+                    if (cat < L.cube_cap) L.cubes[cat] = make_uint2(slot, (unsigned int)((cc[0] << 10) | (cc[1] << 5) | cc[2]));
+                    ++cat;
+                }
+            }
+            for (int wi = tid; wi < SIGN_LINES; wi += THREADS) {
+                unsigned long long word = sm.refm[wi];
+                int ii[3];
+                ii[AS] = wi / TP; ii[AW] = wi - ii[AS] * TP;
+                while (word) {
+                    ii[AU] = __ffsll((long long)word) - 1;
+                    word &= word - 1ull;
+                    if (pat < L.pt_cap) L.pts[pat] = make_uint2(slot, (unsigned int)((ii[0] * t.py + ii[1]) * t.pz + ii[2]));
+                    ++pat;
                 }
             }
         }
-        // ------------------------------------------------- who completes the tile classifies it
-        __threadfence();
-        __syncwarp();
-        unsigned int last = 0;
-        if (lane == 0) {
-            const unsigned int old = atomicAdd(&tile_done[tw], 1u);
-            last = (old == (unsigned int)SH::NB - 1u) ? 1u : 0u;
-            if (last) tile_done[tw] = 0u;                               // ready for the next launch
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && !thin) {
-            __threadfence();
-            const unsigned int tot = sign_classify_pass<TS, AU, AS, AW, false>(masks, hi, pu, ps, pw, t.py, t.pz, lane, L, 0u, 0u, 0u);
-            const unsigned int nc = tot & 0xffffu, np = tot >> 16;
-            unsigned int slot = 0, cat = 0, pat = 0;
-            if (lane == 0) {
-                if (nc | np) {
-                    slot = atomicAdd(&ctr->n_slots, 1u);
-                    if (slot < L.slot_cap) L.tile_meta[slot] = make_tile_meta(t, bid);
-                }
-                cat = nc ? atomicAdd(&ctr->n_cubes, nc) : 0u;
-                pat = np ? atomicAdd(&ctr->n_pts, np) : 0u;
-                atomicAdd(&ctr->pts_f32, (unsigned long long)(t.px * t.py * t.pz));
-            }
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            cat = __shfl_sync(0xffffffffu, cat, 0);
-            pat = __shfl_sync(0xffffffffu, pat, 0);
-            if ((nc | np) && slot < L.slot_cap)
-                sign_classify_pass<TS, AU, AS, AW, true>(masks, hi, pu, ps, pw, t.py, t.pz, lane, L, slot, cat, pat);
-        }
+        __syncthreads();                                      // the next tile overwrites cand / refm
     }
 }
 
@@ -1139,12 +1166,11 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
         __syncthreads();
         if (sm.last_cta) {
             __threadfence();
-            const int nzl = g.zb1 - g.zb0;
-            const int total_b = g.nbx * g.nby * nzl;
+            const int total_b = g.ub1 - g.ub0;
             unsigned int ne = 0, nn = 0;
             for (int t = tid; t < total_b; t += EXTRACT_THREADS) {
-                const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
-                const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + g.zb0 + bzl);
+                int bx, by, bz;
+                const unsigned int bid = window_batch(g, t, &bx, &by, &bz);
                 if (stats_flags[bid]) continue;
                 if (__ldcg(batch_tris + bid)) ++nn; else ++ne;
             }
@@ -1159,12 +1185,11 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
 // non-skipped batch that produced at least one triangle
 __device__ __forceinline__ void batch_stats_body(const GridDesc& g, const unsigned char* __restrict__ flags,
                                                  const unsigned int* __restrict__ batch_tris, Counters* __restrict__ ctr) {
-    const int nzl = g.zb1 - g.zb0;
-    const int total = g.nbx * g.nby * nzl;
+    const int total = g.ub1 - g.ub0;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int bzl = t % nzl, by = (t / nzl) % g.nby, bx = t / (nzl * g.nby);
-    const unsigned int bid = (unsigned int)((bx * g.nby + by) * g.nbz + g.zb0 + bzl);
+    int bx, by, bz;
+    const unsigned int bid = window_batch(g, t, &bx, &by, &bz);
     if (flags[bid]) return;
     if (batch_tris[bid]) atomicAdd(&ctr->nonempty, 1u); else atomicAdd(&ctr->empty, 1u);
 }

@@ -86,8 +86,16 @@ template <int TS>
 __global__ void __launch_bounds__(SIGN_THREADS, SIGN_BLOCKS_PER_SM)
 tile_sign_kernel(const __grid_constant__ ProgramImage img, const GridDesc g, const float tau,
                  const unsigned int* active_list, const unsigned int work_begin, const unsigned int work_end,
-                 const TileLists L, Counters* ctr, unsigned char* scratch, unsigned int* tile_done) {
-    tile_sign_body<TS, SIGN_THREADS>(InterpEval{&img}, g, tau, active_list, work_begin, work_end, L, ctr, scratch, tile_done);
+                 Counters* ctr, unsigned char* scratch) {
+    tile_sign_body<TS, SIGN_THREADS>(InterpEval{&img}, g, tau, active_list, work_begin, work_end, ctr, scratch);
+}
+
+// SHARE = the share axis the sign kernel of the call ran with (fixes which lattice axis the mask bits run along)
+template <int TS, int SHARE>
+__global__ void __launch_bounds__(CLASSIFY_THREADS)
+tile_classify_kernel(const GridDesc g, const unsigned int* active_list, const unsigned int work_begin,
+                     const unsigned int work_end, const TileLists L, Counters* ctr, const unsigned char* scratch) {
+    tile_classify_body<TS, SHARE>(g, active_list, work_begin, work_end, L, ctr, scratch);
 }
 
 template <int TS>
@@ -146,8 +154,6 @@ struct DeviceCtx {
     // tile pipeline work lists (TileLists)
     float* vol = nullptr; size_t slot_cap = 0; TileMeta* tile_meta = nullptr; size_t meta_cap = 0;
     unsigned char* scratch = nullptr; size_t scratch_cap = 0;       // tile_sign_kernel: per-tile mask blocks
-    unsigned int* tile_done = nullptr; size_t done_cap = 0;         //                   per-tile chunk counters (self-resetting)
-    bool done_dirty = false;                                        // a failed call may have left counters behind
     McTablesSmem* mc_tables = nullptr;                              // packed decision tables (one bulk copy per extraction CTA)
     // the whole device-resident step as one CUDA graph, re-used while every launch parameter stays the same
     cudaStream_t cap_stream = nullptr;
@@ -155,7 +161,7 @@ struct DeviceCtx {
     std::vector<unsigned char> step_key;
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // pipelined host output: the triangles of round k travel over PCIe while round k+1 computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pev[kMaxPipe] = {};
@@ -693,7 +699,7 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c.ctr, sizeof(Counters)));
     CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters) * (1 + kMaxPipe)));     // [0] final, [1 + k] after round k
-    for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
+    for (int i = 0; i < 9; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
     for (int i = 0; i < kMaxPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.pev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking));
@@ -815,10 +821,10 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFree(c.axes); cudaFree(c.flags); cudaFree(c.active); cudaFree(c.batch_tris); cudaFree(c.ctr);
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
-        cudaFree(c.scratch); cudaFree(c.tile_done); cudaFree(c.mc_tables);
+        cudaFree(c.scratch); cudaFree(c.mc_tables);
         if (c.step_exec) cudaGraphExecDestroy(c.step_exec);
         if (c.cap_stream) cudaStreamDestroy(c.cap_stream);
-        for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+        for (int i = 0; i < 9; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
         for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     }
@@ -898,8 +904,11 @@ extern "C" int sdfb200_eval_f64(sdfb200_prog* prog, const double* xyz, int64_t n
 
 static constexpr int kTS = 32;
 
+// The batch range of a call: a Z-slab of whole batch layers [zb_begin, zb_end) (zb_end < 0: to the end) when
+// ub_begin < 0, else the window [ub_begin, ub_end) of the Z-major batch order (multi-GPU: slabs cut inside a layer).
 static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64_t nx, const double* ys, int64_t ny,
-                      const double* zs, int64_t nz, int batch_size, int zb_begin, int zb_end, GridDesc* g) {
+                      const double* zs, int64_t nz, int batch_size, int zb_begin, int zb_end, int64_t ub_begin, int64_t ub_end,
+                      GridDesc* g) {
     if (!xs || !ys || !zs || nx < 1 || ny < 1 || nz < 1 || batch_size < 1)
         return fail(SDFB200_E_INVALID, "generate: bad lattice (%lld x %lld x %lld, batch %d)", (long long)nx, (long long)ny,
                     (long long)nz, batch_size);
@@ -945,10 +954,14 @@ static int setup_grid(DeviceCtx* c, cudaStream_t stream, const double* xs, int64
     if (zb_end < 0) zb_end = g->nbz;
     if (zb_begin < 0 || zb_begin > zb_end || zb_end > g->nbz)
         return fail(SDFB200_E_INVALID, "z batch range [%d,%d) outside [0,%d)", zb_begin, zb_end, g->nbz);
-    g->zb0 = zb_begin; g->zb1 = zb_end;
     g->sub = (batch_size + kTS - 1) / kTS;
     const size_t nb = (size_t)g->nbx * g->nby * g->nbz;
-    if (nb > (size_t)1 << 31) return fail(SDFB200_E_INVALID, "too many batches");
+    if (nb >= (size_t)1 << 31) return fail(SDFB200_E_INVALID, "too many batches");
+    const int64_t nxy = (int64_t)g->nbx * g->nby;
+    if (ub_begin < 0) { ub_begin = (int64_t)zb_begin * nxy; ub_end = (int64_t)zb_end * nxy; }
+    if (ub_begin > ub_end || ub_end > (int64_t)nb)
+        return fail(SDFB200_E_INVALID, "batch window [%lld,%lld) outside [0,%lld)", (long long)ub_begin, (long long)ub_end, (long long)nb);
+    g->ub0 = (int)ub_begin; g->ub1 = (int)ub_end;
     if (nb > c->nb_cap) {
         cudaFree(c->flags); cudaFree(c->active); cudaFree(c->batch_tris);
         c->flags = nullptr; c->active = nullptr; c->batch_tris = nullptr; c->nb_cap = 0;
@@ -1010,8 +1023,8 @@ static bool graph_enabled() {
 static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                          const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
                          int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
-                         int64_t stats[6], double timings_ms[7], int device, void* stream_, unsigned char* stl_out,
-                         unsigned long long* ext_cursor = nullptr) {
+                         int64_t stats[6], double timings_ms[8], int device, void* stream_, unsigned char* stl_out,
+                         unsigned long long* ext_cursor = nullptr, int64_t ub_begin = -1, int64_t ub_end = -1) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
     if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
@@ -1020,7 +1033,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
     cudaStream_t stream = (cudaStream_t)stream_;
     GridDesc g;
     CUDA_TRY(cudaEventRecord(c->ev[0], stream));
-    rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, zb_begin, zb_end, &g); if (rc) return rc;
+    rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, zb_begin, zb_end, ub_begin, ub_end, &g); if (rc) return rc;
     // output placement: device pointer -> written in place; pinned host -> either written in place by
     // the kernel over PCIe (zero copy, overlaps the transfer with the computation) or staged + one async
     // copy; pageable host -> staged + copy
@@ -1043,8 +1056,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         rc = ensure_stage(c, (size_t)tri_capacity * 36 + 256); if (rc) return rc;
         dtri = (float*)c->stage;
     }
-    const int nzl = g.zb1 - g.zb0;
-    const long long total_b = (long long)g.nbx * g.nby * nzl;
+    const long long total_b = (long long)g.ub1 - g.ub0;
     const unsigned long long cap = tri_out ? (unsigned long long)tri_capacity : 0ull;
     const float tau = (float)tau_;
     const long long lattice = (long long)nx * ny * nz;
@@ -1110,17 +1122,26 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             cudaError_t e = cudaSuccess;
             if (first) CUDA_TRY(rec(c->ev[4], s, captured));
             if (sign_path) {
-                // autonomous warps pull 1/13-tile batches from a cursor: fill the machine, surplus warps leave at once
+                // (A'1) autonomous warps pull 1/13-tile batches from a cursor: fill the machine, surplus warps leave at once
                 const int grid = (int)std::min<unsigned long long>(tiles * 16ull, (unsigned long long)c->sms * SIGN_BLOCKS_PER_SM);
+                int share = 2;                                        // the interpreter kernel: runs along z
                 if (k_tile) {
                     const unsigned int* act = c->active; Counters* ctrp = c->ctr; float tauv = tau;
-                    unsigned char* scr = c->scratch; unsigned int* done = c->tile_done;
-                    void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&L, (void*)&ctrp,
-                                    (void*)&scr, (void*)&done};
+                    unsigned char* scr = c->scratch;
+                    void* args[] = {(void*)&g, (void*)&tauv, (void*)&act, (void*)&wbu, (void*)&we, (void*)&ctrp, (void*)&scr};
                     e = jit_launch(k_tile, dim3(grid), dim3(SIGN_THREADS), 0, s, args);
+                    share = prog->plan_share[JK_TILE0 + precision] < 0 ? 2 : prog->plan_share[JK_TILE0 + precision];
                 } else {
-                    tile_sign_kernel<kTS><<<grid, SIGN_THREADS, 0, s>>>(prog->img, g, tau, c->active, wbu, we, L, c->ctr,
-                                                                         c->scratch, c->tile_done);
+                    tile_sign_kernel<kTS><<<grid, SIGN_THREADS, 0, s>>>(prog->img, g, tau, c->active, wbu, we, c->ctr, c->scratch);
+                    e = cudaGetLastError();
+                }
+                if (e == cudaSuccess) {
+                    // (A'2) every tile of the round classified side by side, one CTA each
+                    if (first) CUDA_TRY(rec(c->ev[8], s, captured));
+                    const int cgrid = (int)std::min<unsigned long long>(tiles, (unsigned long long)c->sms * 8);
+                    if (share == 0) tile_classify_kernel<kTS, 0><<<cgrid, CLASSIFY_THREADS, 0, s>>>(g, c->active, wbu, we, L, c->ctr, c->scratch);
+                    else if (share == 1) tile_classify_kernel<kTS, 1><<<cgrid, CLASSIFY_THREADS, 0, s>>>(g, c->active, wbu, we, L, c->ctr, c->scratch);
+                    else tile_classify_kernel<kTS, 2><<<cgrid, CLASSIFY_THREADS, 0, s>>>(g, c->active, wbu, we, L, c->ctr, c->scratch);
                     e = cudaGetLastError();
                 }
             } else {
@@ -1138,7 +1159,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 else
                     e = launch_tile_eval<SDFB200_PREC_F64>(grid, s, prog->img, g, tau, c->active, wbu, we, L, c->ctr);
             }
-            if (e != cudaSuccess) { c->done_dirty = true; return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e)); }
+            if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e));
             if (first) CUDA_TRY(rec(c->ev[5], s, captured));
             if (refine) {
                 const int rgrid = c->sms * 8;
@@ -1180,12 +1201,6 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             rc = grow(&c->tile_meta, &c->meta_cap, (size_t)round); if (rc) return rc;
             if (sign_path) {
                 rc = grow(&c->scratch, &c->scratch_cap, (size_t)round * SIGN_STRIDE); if (rc) return rc;
-                const size_t had = c->done_cap;
-                rc = grow(&c->tile_done, &c->done_cap, (size_t)round); if (rc) return rc;
-                if (c->done_cap != had || c->done_dirty) {          // counters reset themselves in normal operation
-                    CUDA_TRY(cudaMemsetAsync(c->tile_done, 0, c->done_cap * sizeof(unsigned int), stream));
-                    c->done_dirty = false;
-                }
             }
             const size_t est_tiles = sync_free ? std::max<size_t>(256, round / 4) : round;     // most batches are skipped / empty
             size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, est_tiles * 3072)));
@@ -1224,13 +1239,13 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     if (graph_enabled()) {
                         // key: every value the launches above depend on
                         struct { GridDesc g; TileLists L; float tau; int sparse, precision, tail; float* dtri; unsigned long long cap, n_work;
-                                 unsigned long long* ext; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr, *done; } key;
+                                 unsigned long long* ext; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr; } key;
                         memset(&key, 0, sizeof(key));
                         key.g = g; key.L = L; key.tau = tau; key.sparse = sparse; key.precision = precision; key.tail = tail ? 1 : 0;
                         key.dtri = dtri; key.cap = cap; key.n_work = n_work; key.ext = ext_cursor;
                         key.k0 = (void*)k_skip; key.k1 = (void*)k_tile; key.k2 = (void*)k_refine;
                         key.flags = c->flags; key.active = c->active; key.bt = c->batch_tris; key.ctr = c->ctr; key.ctrh = c->ctr_host;
-                        key.scr = c->scratch; key.done = c->tile_done;
+                        key.scr = c->scratch;
                         const bool hit = c->step_exec && c->step_key.size() == sizeof(key) && memcmp(c->step_key.data(), &key, sizeof(key)) == 0;
                         if (!hit) {
                             if (c->step_exec) { cudaGraphExecDestroy(c->step_exec); c->step_exec = nullptr; }
@@ -1347,17 +1362,18 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
     if (timings_ms) {
-        float a = 0, b = 0, d = 0, ta = 0, tb = 0, tc = 0;
+        float a = 0, b = 0, d = 0, ta = 0, tb = 0, tc = 0, tk = 0;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
         if (ran_pipeline) {
-            cudaEventElapsedTime(&ta, c->ev[4], c->ev[5]);
+            if (sign_path) { cudaEventElapsedTime(&ta, c->ev[4], c->ev[8]); cudaEventElapsedTime(&tk, c->ev[8], c->ev[5]); }
+            else cudaEventElapsedTime(&ta, c->ev[4], c->ev[5]);
             cudaEventElapsedTime(&tb, c->ev[5], c->ev[6]);
             cudaEventElapsedTime(&tc, c->ev[6], c->ev[7]);
         }
         timings_ms[0] = a; timings_ms[1] = b; timings_ms[2] = a + b; timings_ms[3] = d;
-        timings_ms[4] = ta; timings_ms[5] = tb; timings_ms[6] = tc;
+        timings_ms[4] = ta; timings_ms[5] = tb; timings_ms[6] = tc; timings_ms[7] = tk;
     }
     if (overflow)
         return fail(SDFB200_E_CAPACITY, "triangle buffer too small: %lld needed, %lld given", (long long)h.tri_cursor,
@@ -1368,7 +1384,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
 extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                                 const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
                                 int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
-                                int64_t stats[6], double timings_ms[7], int device, void* stream) {
+                                int64_t stats[6], double timings_ms[8], int device, void* stream) {
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, zb_begin, zb_end, tri_out,
                          tri_capacity, n_tri, stats, timings_ms, device, stream, nullptr);
 }
@@ -1376,7 +1392,7 @@ extern "C" int sdfb200_generate(sdfb200_prog* prog, const double* xs, int64_t nx
 extern "C" int sdfb200_generate_stl(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                                     const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
                                     void* records_out, int64_t tri_capacity, int64_t* n_tri, int64_t stats[6],
-                                    double timings_ms[7], int device, void* stream) {
+                                    double timings_ms[8], int device, void* stream) {
     if (!records_out) return fail(SDFB200_E_INVALID, "generate_stl: records_out is NULL");
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, nullptr, tri_capacity,
                          n_tri, stats, timings_ms, device, stream, (unsigned char*)records_out);
@@ -1458,11 +1474,27 @@ extern "C" int sdfb200_shared_count(sdfb200_shared* s, int which, int64_t* n, vo
 extern "C" int sdfb200_generate_shared(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
                                        const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
                                        int zb_begin, int zb_end, sdfb200_shared* dst, int which, int64_t* n_tri_local,
-                                       int64_t stats[6], double timings_ms[7], int device, void* stream) {
+                                       int64_t stats[6], double timings_ms[8], int device, void* stream) {
     if (!dst || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "generate_shared: bad argument");
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, zb_begin, zb_end,
                          (float*)(dst->base + 256), dst->capacity, n_tri_local, stats, timings_ms, device, stream, nullptr,
                          (unsigned long long*)(dst->base + 8 * which));
+}
+
+extern "C" int sdfb200_generate_window(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
+                                       const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau,
+                                       int64_t ub_begin, int64_t ub_end, float* tri_out, int64_t tri_capacity,
+                                       sdfb200_shared* dst, int which, int64_t* n_tri, int64_t stats[6],
+                                       double timings_ms[8], int device, void* stream) {
+    if (ub_begin < 0 || ub_end < ub_begin) return fail(SDFB200_E_INVALID, "generate_window: bad window");
+    if (dst) {
+        if (which < 0 || which > 1) return fail(SDFB200_E_INVALID, "generate_window: bad cursor");
+        return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1,
+                             (float*)(dst->base + 256), dst->capacity, n_tri, stats, timings_ms, device, stream, nullptr,
+                             (unsigned long long*)(dst->base + 8 * which), ub_begin, ub_end);
+    }
+    return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, tri_out, tri_capacity,
+                         n_tri, stats, timings_ms, device, stream, nullptr, nullptr, ub_begin, ub_end);
 }
 
 extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {
@@ -1495,7 +1527,7 @@ extern "C" int sdfb200_skip_flags(sdfb200_prog* prog, const double* xs, int64_t 
     DeviceCtx* c; int rc = get_ctx(prog, device, &c); if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     GridDesc g;
-    rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, 0, -1, &g); if (rc) return rc;
+    rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, batch_size, 0, -1, -1, -1, &g); if (rc) return rc;
     const long long total_b = (long long)g.nbx * g.nby * g.nbz;
     const int pb = (int)((total_b * PREPASS_LANES + 127) / 128);
     if (cudaKernel_t jk = jit_get(prog, JK_SKIP, total_b >= 4096)) {

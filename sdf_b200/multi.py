@@ -7,8 +7,10 @@ batches do through the ``s + 1`` slice overlap, core.py:115-117) -- no halo exch
 data-path collective.  The only collective is one variable-length all-gather of the triangle
 buffers at the end (NCCL over NVLink/NVSwitch via torch.distributed; gloo on CPU in the tests).
 
-Slabs are whole Z batch layers, cut so that every rank gets about the same number of
-NON-SKIPPED batches (the skip pre-pass over the full lattice costs <= 9 samples per batch).
+A rank's share is a Z-slab: by default a WINDOW of the Z-major batch order (whole batch layers plus a
+ragged first / last layer, ``plan_windows``), cut so that every rank gets the same number of NON-SKIPPED
+batches even when the surface lives in fewer batch layers than there are ranks (the skip pre-pass over
+the full lattice costs <= 9 samples per batch); ``plan_slabs`` cuts at whole layers only.
 """
 import numpy as np
 
@@ -45,6 +47,47 @@ def plan_slabs(sdf, X, Y, Z, batch_size, world, device=None):
                          np.ascontiguousarray(Z, np.float64), batch_size, device=dev)
     active = (flags == 0).sum(axis=(0, 1))
     return partition_layers(active, world)
+
+
+def partition_windows(weights, world):
+    """Cut range(len(weights)) -- the batches in Z-MAJOR order, u = bz * (nbx * nby) + bx * nby + by -- into
+    ``world`` contiguous windows [u0, u1) of (nearly) equal weight.  Windows cover every batch, are disjoint
+    and ordered; a window may be empty."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    w = w + max(w.sum(), 1.0) * 1e-4 / max(n, 1)          # skipped batches are cheap, not free
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, cum[-1] * r / world, side='left'))
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def zmajor_active(flags):
+    """skip flags [nbx, nby, nbz] (core.py:119 order) -> activity per batch in Z-major order."""
+    return (np.asarray(flags) == 0).transpose(2, 0, 1).reshape(-1)
+
+
+def plan_windows(sdf, X, Y, Z, batch_size, world, device=None, rates=None):
+    """Run the skip pre-pass for the whole lattice and return the per-rank windows of the Z-major batch order,
+    balanced by non-skipped batches.  ``rates`` (optional, one per rank of a previous plan given as
+    ``(windows, seconds)``): measured time per active batch of each old window -- batches in costlier
+    regions (more surface per batch) then weigh more, so a second plan evens out what the first one measured."""
+    h, _ = core.program_handle(sdf)
+    dev = core.default_device() if device is None else device
+    flags = h.skip_flags(np.ascontiguousarray(X, np.float64), np.ascontiguousarray(Y, np.float64),
+                         np.ascontiguousarray(Z, np.float64), batch_size, device=dev)
+    w = zmajor_active(flags).astype(np.float64)
+    if rates is not None:
+        old, seconds = rates
+        for (u0, u1), t in zip(old, seconds):
+            act = w[u0:u1].sum()
+            if act > 0 and t > 0:
+                w[u0:u1] *= t / act
+        w *= len(w) / max(w.sum(), 1e-30)
+    return partition_windows(w, world)
 
 
 class _PinnedTorchPool:
@@ -152,15 +195,25 @@ class RootGather:
             self.shared.reset(1)
         dist.barrier(group)
 
-    def run(self, handle, X, Y, Z, batch_size, sparse, precision, tau, zb, stream=None):
-        """One step on this rank; returns (n_local, stats, timings, total) -- total only on rank 0."""
+    def run(self, handle, X, Y, Z, batch_size, sparse, precision, tau, zb, stream=None, window=None):
+        """One step on this rank (its Z-slab ``zb`` of whole layers, or its ``window`` of the Z-major batch order);
+        returns (n_local, stats, timings, total) -- total only on rank 0.
+
+        Contract: rank 0 must be done with ``view(total)`` of step N before any rank enters ``run`` of step
+        N + 1 -- the triangle region is not double-buffered, only the cursors are (``generate_distributed``
+        copies the view out and synchronises before it returns; a caller that keeps the view must add its own
+        barrier)."""
         import torch
         import torch.distributed as dist
         which = self.step & 1
         if self.rank == 0:
             self.shared.reset(which ^ 1, stream)          # next step's cursor: nobody touches it now
-        n_local, stats, timings = handle.generate_shared(X, Y, Z, batch_size, sparse, precision, tau, self.shared,
-                                                         which, zb=zb, device=self.device, stream=stream)
+        if window is not None:
+            n_local, stats, timings = handle.generate_window(X, Y, Z, batch_size, sparse, precision, tau, window,
+                                                             shared=self.shared, which=which, device=self.device, stream=stream)
+        else:
+            n_local, stats, timings = handle.generate_shared(X, Y, Z, batch_size, sparse, precision, tau, self.shared,
+                                                             which, zb=zb, device=self.device, stream=stream)
         dist.barrier(self.group)                          # every peer's kernel (and its NVLink stores) has retired
         total = self.shared.count(which, stream) if self.rank == 0 else None
         self.step += 1
@@ -179,38 +232,48 @@ class RootGather:
 
 def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batch_size=core.BATCH_SIZE,
                          sparse=True, precision='exact', plan=None, gather='host', group=None,
-                         compute=None, device=None):
+                         compute=None, device=None, partition=None):
     """SPMD entry: every rank calls this with the same arguments.
 
     Returns (points, info): ``points`` is the concatenated soup of ALL ranks -- a (3T,3) float32
-    ndarray for gather='host', a CUDA tensor (T,9) for gather='device', or only this rank's slab
-    for gather='none'.  ``compute(zb) -> (tris ndarray/tensor (n,9), info)`` can be injected (the
-    CPU gloo tests use the oracle there)."""
+    ndarray for gather='host' / 'root' (rank 0 only there), a CUDA tensor (T,9) for gather='device', or
+    only this rank's share for gather='none'.  ``partition``: 'window' (default on the GPU path: windows of
+    the Z-major batch order, ``plan_windows``) or 'slab' (whole Z batch layers, ``plan_slabs``); ``plan``
+    is the matching list of per-rank ranges.  ``compute(range) -> (tris ndarray/tensor (n,9), info)`` can
+    be injected (the CPU gloo tests use the oracle there; default partition 'slab')."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     bounds, _, (X, Y, Z) = core.make_lattice(sdf, step, bounds, samples)
+    if partition is None:
+        partition = 'slab' if compute is not None else 'window'
+    windowed = partition == 'window'
     if plan is None:
         if compute is not None:
-            nbz = (len(Z) + batch_size - 1) // batch_size
-            plan = partition_layers(np.ones(nbz), world)
+            nb = [(len(a) + batch_size - 1) // batch_size for a in (X, Y, Z)]
+            plan = (partition_windows(np.ones(nb[0] * nb[1] * nb[2]), world) if windowed
+                    else partition_layers(np.ones(nb[2]), world))
+        elif windowed:
+            plan = plan_windows(sdf, X, Y, Z, batch_size, world, device=device)
         else:
             plan = plan_slabs(sdf, X, Y, Z, batch_size, world, device=device)
-    zb = plan[rank]
+    mine = tuple(plan[rank])
+    zb, window = ((0, -1), mine) if windowed else (mine, None)
     if gather == 'root' and compute is None and world > 1:
         # fused gather: every rank's extraction kernel writes into rank 0's buffer over NVLink
         dev = core.default_device() if device is None else device
         h, key = core.program_handle(sdf)
         Xc, Yc, Zc = (np.ascontiguousarray(a, np.float64) for a in (X, Y, Z))
         tau = core.mixed_tau(h.program, Xc, Yc, Zc)
-        need, _ = _count(sdf, Xc, Yc, Zc, batch_size, sparse, precision, zb, dev)
-        rg = _root_gather(need, dev, group)
+        need, _ = _count(sdf, Xc, Yc, Zc, batch_size, sparse, precision, zb, dev, window)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        n_local, stats, timings, total = rg.run(h, Xc, Yc, Zc, batch_size, sparse, precision, tau, zb, stream=stream)
+        rg = _root_gather(need, dev, group)          # sized from the all-reduced per-rank counts of THIS lattice and plan
+        n_local, stats, timings, total = rg.run(h, Xc, Yc, Zc, batch_size, sparse, precision, tau, zb,
+                                                stream=stream, window=window)
         info = dict(triangles=n_local, skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
-                    evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]), zb=zb, rank=rank,
-                    world=world, triangles_total=total)
+                    evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]), zb=mine, rank=rank,
+                    world=world, triangles_total=total, partition=partition)
         if rank != 0:
             return np.zeros((0, 3), np.float32), info
         t, arr = _pinned.take(total * 9)
@@ -218,16 +281,32 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
         torch.cuda.current_stream(dev).synchronize()
         return arr[:total * 9].reshape(-1, 3), info
     if compute is not None:
-        tris, info = compute(zb)
+        tris, info = compute(mine)
         local = torch.as_tensor(np.ascontiguousarray(tris, np.float32).reshape(-1, 9))
     else:
         dev = core.default_device() if device is None else device
-        need, info = _count(sdf, X, Y, Z, batch_size, sparse, precision, zb, dev)
-        out = torch.empty((max(need, 1), 9), dtype=torch.float32, device=torch.device('cuda', dev))
-        tri, info = core.run_batches(sdf, X, Y, Z, batch_size, sparse, precision, zb=zb, device=dev, out=out,
-                                     stream=torch.cuda.current_stream(dev).cuda_stream)
-        local = tri
-    info = dict(info, zb=zb, rank=rank, world=world)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        need, info = _count(sdf, X, Y, Z, batch_size, sparse, precision, zb, dev, window)
+        for attempt in range(2):
+            out = torch.empty((max(need, 1), 9), dtype=torch.float32, device=torch.device('cuda', dev))
+            try:
+                if windowed:
+                    h, _ = core.program_handle(sdf)
+                    Xc, Yc, Zc = (np.ascontiguousarray(a, np.float64) for a in (X, Y, Z))
+                    n, st, _ = h.generate_window(Xc, Yc, Zc, batch_size, sparse, precision, core.mixed_tau(h.program, Xc, Yc, Zc),
+                                                 window, tri_out=out, capacity=out.shape[0], device=dev, stream=stream)
+                    local = out[:n]
+                    info = dict(triangles=n, skipped=int(st[0]), empty=int(st[1]), nonempty=int(st[2]),
+                                evaluated=int(st[3]), refined=int(st[4]), active_cubes=int(st[5]))
+                else:
+                    local, info = core.run_batches(sdf, X, Y, Z, batch_size, sparse, precision, zb=zb, device=dev, out=out,
+                                                   stream=stream)
+                break
+            except _abi_capacity_error() as e:           # a stale cached count: size from what the call reports
+                if attempt:
+                    raise
+                need = int(e.needed * 1.02) + 1024
+    info = dict(info, zb=mine, rank=rank, world=world, partition=partition)
     if gather == 'host' and world > 1 and local.is_cuda:
         # dense gather on the device, then one copy into a pinned (pooled) host array
         allt = allgather_triangles(local, group)
@@ -245,6 +324,11 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
     if gather == 'device':
         return allt, info
     return allt.cpu().numpy().reshape(-1, 3), info
+
+
+def _abi_capacity_error():
+    from . import _abi
+    return _abi.CapacityError
 
 
 _root_gathers = {}
@@ -266,13 +350,20 @@ def _root_gather(local_need, dev, group):
 _count_cache = {}
 
 
-def _count(sdf, X, Y, Z, batch_size, sparse, precision, zb, dev):
-    """Triangle count of a slab (count-only pass), cached per (program, lattice, slab)."""
+def _count(sdf, X, Y, Z, batch_size, sparse, precision, zb, dev, window=None):
+    """Triangle count of a rank's share (count-only pass), cached per (program, lattice axes, share)."""
+    import hashlib
     h, key = core.program_handle(sdf)
-    ck = (key, len(X), len(Y), len(Z), float(X[0]), float(X[-1]), batch_size, bool(sparse), precision, tuple(zb))
+    X, Y, Z = (np.ascontiguousarray(a, np.float64) for a in (X, Y, Z))
+    axes = hashlib.blake2b(X.tobytes() + Y.tobytes() + Z.tobytes(), digest_size=16).digest()      # the WHOLE lattice, not its ends
+    ck = (key, axes, batch_size, bool(sparse), precision, tuple(zb), tuple(window) if window is not None else None)
     if ck not in _count_cache:
+        if len(_count_cache) > 256:
+            _count_cache.clear()
         tau = core.mixed_tau(h.program, X, Y, Z)
-        n, _, _ = h.generate(np.ascontiguousarray(X), np.ascontiguousarray(Y), np.ascontiguousarray(Z), batch_size,
-                             sparse, precision, tau, None, 0, zb=zb, device=dev)
+        if window is not None:
+            n, _, _ = h.generate_window(X, Y, Z, batch_size, sparse, precision, tau, window, device=dev)
+        else:
+            n, _, _ = h.generate(X, Y, Z, batch_size, sparse, precision, tau, None, 0, zb=zb, device=dev)
         _count_cache[ck] = int(n * 1.02) + 1024
     return _count_cache[ck], {}

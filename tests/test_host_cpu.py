@@ -198,7 +198,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_abi.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdfb200_abi_version() == 1
+    assert lib.sdfb200_abi_version() == 2          # v2: timings_ms[8], sdfb200_generate_window
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():
@@ -397,3 +397,34 @@ def test_binary_stl_bytes_equal_the_reference_writer(golden_dir, tmp_path):
     with np.errstate(all='ignore'):
         stl.write_binary_stl(str(path), g['stl_points'].astype(np.float32).reshape(-1, 3))     # what generate() returns
     assert path.read_bytes() == g['stl_bytes'].tobytes()
+
+
+def test_guard_band_follows_the_amplification_of_the_tree():
+    """errbound.gain: the a-priori factor core.mixed_tau multiplies its guard band with.  The BASELINE
+    configurations do not amplify float32 rounding (gain ~ 1: their tau -- and their speed -- is what was
+    validated); a warp that divides by r1 - r0 = 1e-3, a huge twist rate, a steep easing widen the band; a
+    tree with a jump (square easing) sends every sample to float64."""
+    import math
+    from sdf_b200 import core, errbound
+    S = sdf_b200
+    for name, build in models.CONFIGS.items():
+        g = errbound.gain(ir.lower(build(S)), 2.75)
+        assert 1.0 <= g < 1.1, (name, g)
+    assert errbound.gain(ir.lower(S.box(1).bend_radial(1.0, 1.001, 0.5)), 2.5) > 50
+    assert errbound.gain(ir.lower(S.box(1).twist(200.0)), 2.5) > 20
+    assert errbound.gain(ir.lower(S.sphere(1).scale(0.001)), 2.5) < 2          # undone by its own MULC
+    mild = errbound.gain(ir.lower(S.box(1).bend_linear(S.X * -1, S.X, S.Z * 0.5, S.ease.in_quad)), 2.5)
+    steep = errbound.gain(ir.lower(S.box(1).bend_linear(S.X * -1, S.X, S.Z * 0.5, S.ease.in_out_elastic)), 2.5)
+    assert 1.0 < mild < steep, (mild, steep)
+    assert math.isinf(errbound.gain(ir.lower(S.box(1).bend_linear(S.X * -1, S.X, S.Z * 0.5, S.ease.in_square)), 2.5))
+    # every opcode has a rule (an unknown one would return inf and silently push everything to float64)
+    for name, f in models.build(S).items():
+        if 'square' in name or 'circ' in name:
+            continue
+        assert math.isfinite(errbound.gain(ir.lower(f), 2.5)), name
+    # mixed_tau = heuristic x gain
+    X = np.arange(-2.5, 2.5, 0.1)
+    f = S.box(1).bend_radial(1.0, 1.001, 0.5)
+    h, _ = core.program_handle(f)
+    h0, _ = core.program_handle(S.box(1).bend_radial(1.0, 2.0, 0.5))
+    assert core.mixed_tau(h.program, X, X, X) > 30 * core.mixed_tau(h0.program, X, X, X)

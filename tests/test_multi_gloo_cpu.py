@@ -68,3 +68,66 @@ def test_slab_split_and_allgather_equal_single_process(world):
         assert total * 3 == len(pts)
         rep = compare_soups(pts, ref_pts)
         assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], (rank, rep)
+
+
+def _window_batches(X, Y, Z, bs, window):
+    """Batch ids (core.py:119 order) of the window [u0, u1) of the Z-major order u = bz * (nbx * nby) + bx * nby + by."""
+    nb = [(len(a) + bs - 1) // bs for a in (X, Y, Z)]
+    out = []
+    for u in range(window[0], window[1]):
+        bz, r = divmod(u, nb[0] * nb[1])
+        bx, by = divmod(r, nb[1])
+        out.append((bx * nb[1] + by) * nb[2] + bz)
+    return out
+
+
+def _worker_windows(rank, world, port, step, L, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    f = models.cfg_csg(sdf_b200)
+    bounds = ((-L, -L, -L), (L, L, L))
+    _, _, (X, Y, Z) = core.make_lattice(f, step, bounds)
+
+    def compute(window):
+        pts, st = sdf_ref.generate(f, step=step, bounds=bounds, batch_subset=_window_batches(X, Y, Z, 32, window))
+        return pts.astype(np.float32).reshape(-1, 9), st
+    pts, info = multi.generate_distributed(f, step=step, bounds=bounds, gather='host', compute=compute, partition='window')
+    q.put((rank, pts, info['zb'], info['triangles_total']))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_window_split_cuts_inside_a_layer_and_equals_single_process():
+    """Windows of the Z-major batch order (slabs with ragged first / last layers): 27 batches over 2 ranks cut
+    INSIDE the middle layer; the gathered soup equals the single-process one."""
+    step, L, world = 2.0 / 96, 1.0, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_windows, args=(r, world, port, step, L, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    f = models.cfg_csg(sdf_b200)
+    ref_pts, _ = sdf_ref.generate(f, step=step, bounds=((-L,) * 3, (L,) * 3))
+    ranges = sorted(g[2] for g in got)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 27 and ranges[0][1] == ranges[1][0] and ranges[0][1] % 9 != 0
+    for rank, pts, window, total in got:
+        rep = compare_soups(pts, ref_pts)
+        assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], (rank, rep)
+
+
+def test_partition_windows_balances_active_batches():
+    w = np.zeros(32 * 32 * 32)
+    w[5000:9000] = 1                                  # the surface lives in 4 of 32 layers
+    wins = multi.partition_windows(w, 8)
+    assert wins[0][0] == 0 and wins[-1][1] == len(w) and all(wins[i][1] == wins[i + 1][0] for i in range(7))
+    act = [w[a:b].sum() for a, b in wins]
+    assert max(act) - min(act) <= 2, act
+    flags = np.zeros((4, 3, 2), np.uint8)
+    flags[1, 2, 0] = 1
+    assert list(np.nonzero(~multi.zmajor_active(flags))[0]) == [1 * 3 + 2]

@@ -36,7 +36,7 @@ def main():
                                   skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
                                   evaluated=int(stats[3]), refined=int(stats[4]), cubes=int(stats[5]),
                                   prepass_ms=round(best[0], 4), fused_ms=round(best[1], 4), tile_ms=round(best[4], 4),
-                                  refine_ms=round(best[5], 4), extract_ms=round(best[6], 4), plan=h.jit_plan(core._abi.PREC[prec]),
+                                  classify_ms=round(best[7], 4), refine_ms=round(best[5], 4), extract_ms=round(best[6], 4), plan=h.jit_plan(core._abi.PREC[prec]),
                                   frac_12B=round(stats[3] * 12.0 / (best[4] * 1e-3) / 6570.3e9, 4) if best[4] > 0 else None,
                                   gpts_eval_per_s=round(stats[3] / best[1] / 1e6, 2),
                                   gpts_covered_per_s=round(n ** 3 / best[2] / 1e6, 2),
