@@ -25,6 +25,7 @@ BATCH_SIZE = 32
 TAU_ULPS = 64.0          # guard band of the float32 pass, in float32 ulps of the largest magnitude in play
 TAU_ULPS_PER_WORD = 4.0  # ... plus this many per program word (rounding accumulates along the tree)
 
+_EPS32 = float(np.finfo(np.float32).eps)
 _handles = {}            # (code bytes, consts bytes) -> ProgramHandle
 _capacity_hint = {}      # (program key, lattice dims, batch, sparse) -> triangles needed last time
 
@@ -38,7 +39,22 @@ def default_device():
 
 
 def program_handle(sdf):
-    """Lower ``sdf`` (every call: ``.k()`` may have changed) and return a cached handle."""
+    """The lowered program of ``sdf`` and its device handle.  A tree is immutable except for ``.k()`` set after
+    construction (honoured like the reference does, dn.py:12): the lowering is cached on the root object and
+    redone only when some ``_k`` has changed since (ir.MUTATIONS)."""
+    from . import ir
+    cached = sdf.__dict__.get('_lowered')
+    if cached is not None and cached[0] == ir.MUTATIONS[0]:
+        return cached[1], cached[2]
+    h, key = _program_handle(sdf)
+    try:
+        object.__setattr__(sdf, '_lowered', (ir.MUTATIONS[0], h, key))
+    except AttributeError:
+        pass
+    return h, key
+
+
+def _program_handle(sdf):
     prog = lower(sdf)
     key = (prog.code.tobytes(), prog.consts.tobytes())
     h = _handles.get(key)
@@ -150,7 +166,7 @@ def mixed_tau(program, X, Y, Z):
     g = cache.get(key)
     if g is None:
         g = cache[key] = errbound.gain(program, cmax)
-    return ulps * float(np.finfo(np.float32).eps) * mag * g
+    return ulps * _EPS32 * mag * g
 
 
 def default_capacity(X, Y, Z):
@@ -218,12 +234,14 @@ def generate(
         print('max %g, %g, %g' % (x1, y1, z1))
         print('step %g, %g, %g' % (dx, dy, dz))
 
-    (nbx, nby, nbz), num_samples = batch_counts(X, Y, Z, batch_size)
-    num_batches = nbx * nby * nbz
+    num_batches = num_samples = None
+    if verbose or return_info:
+        (nbx, nby, nbz), num_samples = batch_counts(X, Y, Z, batch_size)
+        num_batches = nbx * nby * nbz
     if verbose:
         print('%d samples in %d batches with %d workers' % (num_samples, num_batches, workers))
 
-    bar = progress.Bar(num_batches, enabled=verbose)
+    bar = progress.Bar(num_batches or 0, enabled=verbose)
     tris, info = run_batches(sdf, X, Y, Z, batch_size, sparse, precision, device=device)
     bar.done()
     points = tris.reshape(-1, 3)

@@ -63,10 +63,38 @@ struct Counters {
     unsigned int work_cursor;
     unsigned int skipped, empty, nonempty;
     unsigned int n_slots, n_cubes, n_pts;       // per round: stored tiles, candidate cubes, queued samples
+    unsigned int extract_done;                  // per round: CTAs of the extraction kernel that have finished (its tail work)
     unsigned int max_cubes, max_pts;            // high-water marks over rounds (capacity check)
-    unsigned int extract_done;                  // CTAs of the last extraction kernel that have finished (stats tail)
     unsigned int pad_[1];
 };
+
+// What the host needs to know when a round of a pipelined call is done, written by the round's extraction kernel
+// into page-locked, device-mapped host memory: the host polls `done` and starts the copy of the round's triangles
+// without a stream synchronisation.
+struct RoundProgress {
+    unsigned long long tri_cursor;              // triangles produced so far (all rounds up to this one)
+    unsigned int max_cubes, max_pts;            // list high-water marks (overflow -> the host retries the call)
+    unsigned int done;                          // 0 -> 1, written last (after a system-scope fence)
+    unsigned int pad_[3];
+};
+
+// The tiles [wb, we) of the active list a kernel works on:
+//   work_end_arg == 0xffffffff              every active tile (the count is read from the pre-pass's counter)
+//   work_end_arg == 0xfffe0000 | R          round `work_begin` of R equal rounds of the active tiles (decided on the
+//                                           device: the host queues all rounds without knowing the count)
+//   otherwise                               [work_begin, work_end_arg) as given by the host
+__device__ __forceinline__ void work_range(const Counters* ctr, unsigned int subs3, unsigned int work_begin,
+                                           unsigned int work_end_arg, unsigned int* wb, unsigned int* we) {
+    if (work_end_arg == 0xffffffffu) { *wb = work_begin; *we = ctr->n_active * subs3; return; }
+    if ((work_end_arg & 0xffff0000u) == 0xfffe0000u) {
+        const unsigned int total = ctr->n_active * subs3, rounds = work_end_arg & 0xffffu;
+        const unsigned int per = (total + rounds - 1u) / rounds;
+        *wb = min(work_begin * per, total);
+        *we = min(*wb + per, total);
+        return;
+    }
+    *wb = work_begin; *we = work_end_arg;
+}
 
 // t-th batch of the call's window -> batch coordinates; the batch id keeps core.py:119's order (X-major)
 __device__ __forceinline__ unsigned int window_batch(const GridDesc& g, int t, int* bx, int* by, int* bz) {
@@ -373,7 +401,7 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 template <int TS, int PREC, int THREADS, class EV>
 __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, const float tau,
                                                const unsigned int* __restrict__ active_list,
-                                               const unsigned int work_begin, const unsigned int work_end_arg,
+                                               const unsigned int work_begin_arg, const unsigned int work_end_arg,
                                                const TileLists L, Counters* __restrict__ ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool F64 = (PREC == SDFB200_PREC_F64);
@@ -386,7 +414,8 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
     // work_end == ~0u: "every active batch" -- the count is read from the pre-pass's counter, so the
     // host does not have to synchronise between the two kernels
-    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
+    unsigned int work_begin, work_end;
+    work_range(ctr, subs3, work_begin_arg, work_end_arg, &work_begin, &work_end);
     unsigned long long my_pts = 0;
 
     // Every barrier below is executed unconditionally by every thread in every iteration: the
@@ -653,8 +682,9 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 // check, core.py:53-56), no tile store.
 //
 // (A'1) tile_sign_body -- evaluation by autonomous warps: no CTA barrier anywhere, every WARP is its own
-// worker.  It takes batches of SIGN_BATCH thread-runs of one tile from a global cursor (a tile = 13
-// batches, so the sparse, uneven work balances at 1/13 tile per warp).  In a thread-run a lane evaluates N
+// worker.  It takes batches of SIGN_BATCH thread-runs of one tile from a global cursor (a tile = 26
+// batches: the sparse, uneven work balances at 1/26 tile per warp; the next batch is claimed while the
+// current one computes, so the cursor's round trip is off the critical path).  In a thread-run a lane evaluates N
 // consecutive samples along the share axis S (they share their other two coordinates, i.e. registers:
 // the axis-sharing of the generated evaluator); the lane index is the coordinate along the lane axis U.
 // Lanes 0..31 cover samples 0..31 of a U-line; the 33rd sample of every line (the plane shared with the
@@ -667,7 +697,7 @@ __device__ __forceinline__ void tile_eval_body(const EV& ev, const GridDesc& g, 
 // was a serial, latency-bound tail (measured: profiles/r2_tile_gearlike_autonomous_v1.txt).
 #define SIGN_TP 33
 #define SIGN_LINES (SIGN_TP * SIGN_TP)
-#define SIGN_BATCH 8                                            // thread-runs per work item
+#define SIGN_BATCH 4                                            // thread-runs per work item
 #define SIGN_STRIDE 9856                                        // bytes of scratch per tile: 1089 x {u32, u32} + 1089 u8, padded
 #define SIGN_THREADS 256
 #define SIGN_BLOCKS_PER_SM 4
@@ -691,7 +721,7 @@ template <int SHARE> struct SignAxes {
 template <int TS, int THREADS, class EV>
 __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, const float tau,
                                                const unsigned int* __restrict__ active_list,
-                                               const unsigned int work_begin, const unsigned int work_end_arg,
+                                               const unsigned int work_begin_arg, const unsigned int work_end_arg,
                                                Counters* __restrict__ ctr, unsigned char* __restrict__ scratch) {
     static_assert(TS == 32, "one mask word per line");
     constexpr int TP = SIGN_TP;
@@ -703,14 +733,16 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
     const int lane = (int)(threadIdx.x & 31u);
     float* const sax = s_axis[threadIdx.x >> 5];
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
-    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
+    unsigned int work_begin, work_end;
+    work_range(ctr, subs3, work_begin_arg, work_end_arg, &work_begin, &work_end);
     const unsigned int n_items = (work_end > work_begin ? work_end - work_begin : 0u) * (unsigned int)SH::NB;
 
+    unsigned int q_next = 0;
+    if (lane == 0) q_next = atomicAdd(&ctr->work_cursor, 1u);
     for (;;) {
-        unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(&ctr->work_cursor, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        const unsigned int q = __shfl_sync(0xffffffffu, q_next, 0);
         if (q >= n_items) break;
+        if (lane == 0) q_next = atomicAdd(&ctr->work_cursor, 1u);       // the next batch: consumed at the top of the loop
         const unsigned int tw = q / (unsigned int)SH::NB;
         const int bb = (int)(q - tw * (unsigned int)SH::NB);
         const unsigned int w = work_begin + tw;
@@ -730,7 +762,6 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
         __syncwarp();                                             // (the previous batch is done with sax)
         sax[lane] = __ldg(axf[AS] + min(lane, ps - 1));
         if (lane < TP + 15 - 32) sax[32 + lane] = __ldg(axf[AS] + min(32 + lane, ps - 1));
-        const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);
         const float cu_main = __ldg(axf[AU] + min(lane, pu - 1));
         const float cu_last = __ldg(axf[AU] + (pu - 1));
         __syncwarp();
@@ -753,8 +784,8 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
             if (main_run) {
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
-                    const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f) & umask;
-                    const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau) & umask;
+                    const unsigned int bp = __ballot_sync(0xffffffffu, d[k] > 0.0f);         // (bits >= pu: clamped duplicates,
+                    const unsigned int bu = __ballot_sync(0xffffffffu, fabsf(d[k]) < tau);   //  masked off by the classifier)
                     if (lane == 0 && is0 + k < ps) masks[(is0 + k) * TP + iw] = make_uint2(bp, bu);
                 }
             } else if (on) {
@@ -777,7 +808,7 @@ struct ClassifySmem {
 // (A'2) one CTA per tile of the round (grid-stride); SHARE = the share axis the sign kernel ran with
 template <int TS, int SHARE>
 __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsigned int* __restrict__ active_list,
-                                                   const unsigned int work_begin, const unsigned int work_end_arg,
+                                                   const unsigned int work_begin_arg, const unsigned int work_end_arg,
                                                    const TileLists L, Counters* __restrict__ ctr,
                                                    const unsigned char* __restrict__ scratch) {
     constexpr int TP = SIGN_TP;
@@ -787,7 +818,8 @@ __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsi
     __shared__ ClassifySmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int subs3 = (unsigned int)(g.sub * g.sub * g.sub);
-    const unsigned int work_end = (work_end_arg == 0xffffffffu) ? ctr->n_active * subs3 : work_end_arg;
+    unsigned int work_begin, work_end;
+    work_range(ctr, subs3, work_begin_arg, work_end_arg, &work_begin, &work_end);
     const unsigned int n_tiles = work_end > work_begin ? work_end - work_begin : 0u;
     for (unsigned int tw = blockIdx.x; tw < n_tiles; tw += gridDim.x) {
         const unsigned int w = work_begin + tw;
@@ -802,6 +834,7 @@ __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsi
         const unsigned char* const hi = reinterpret_cast<const unsigned char*>(masks + SIGN_LINES);
         const bool has_hi = (pu == TP);
         const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
+        const unsigned int umask = pu >= 32 ? 0xffffffffu : ((1u << pu) - 1u);       // valid samples of a U-line
         // (1) one thread per (cs, cw) column of cubes: 32 cubes along U classified with word operations.
         //     A cube is a candidate when its corners are not all > 0 and not all <= 0, or one is uncertain.
         for (int col = tid; col < TS * TS; col += THREADS) {
@@ -815,8 +848,8 @@ __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsi
                 for (int j = 0; j < 4; ++j) {
                     const unsigned int h8 = has_hi ? (unsigned int)hi[ls[j]] : 0u;
                     const uint2 mk = masks[ls[j]];
-                    const unsigned long long p = (unsigned long long)mk.x | ((unsigned long long)(h8 & 1u) << 32);
-                    const unsigned long long u = (unsigned long long)mk.y | ((unsigned long long)((h8 >> 1) & 1u) << 32);
+                    const unsigned long long p = (unsigned long long)(mk.x & umask) | ((unsigned long long)(h8 & 1u) << 32);
+                    const unsigned long long u = (unsigned long long)(mk.y & umask) | ((unsigned long long)((h8 >> 1) & 1u) << 32);
                     allp &= p & (p >> 1); anyp |= p | (p >> 1); anyu |= u | (u >> 1);
                 }
                 W = (unsigned int)((anyp & ~allp) | anyu) & cumask;
@@ -835,7 +868,7 @@ __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsi
                 if (is > 0 && iw < TS) Wl |= sm.cand[((is - 1) << 5) | iw];
                 if (is > 0 && iw > 0) Wl |= sm.cand[((is - 1) << 5) | (iw - 1)];
                 const unsigned int h8 = has_hi ? (unsigned int)hi[ln] : 0u;
-                ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | (unsigned long long)masks[ln].y |
+                ref = (unsigned long long)Wl | ((unsigned long long)Wl << 1) | (unsigned long long)(masks[ln].y & umask) |
                       ((unsigned long long)((h8 >> 1) & 1u) << 32);
             }
             sm.refm[ln] = ref;
@@ -1030,7 +1063,8 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
                                              const unsigned long long tri_capacity,
                                              unsigned long long* __restrict__ ext_cursor,
                                              const McTablesSmem* __restrict__ tables,
-                                             const unsigned char* __restrict__ stats_flags) {
+                                             const unsigned char* __restrict__ stats_flags,
+                                             RoundProgress* __restrict__ progress) {
     __shared__ __align__(128) ExtractSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     load_mc_tables_async(&sm.mc, tables, &sm.tables_bar, tid);
@@ -1156,15 +1190,23 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
         atomicMax(&ctr->max_pts, ctr->n_pts);
     }
     if (!tables_ready) mbar_wait(&sm.tables_bar, 0u);          // never leave with a bulk copy in flight
-    if (stats_flags != nullptr) {
-        __threadfence();                                       // this CTA's batch_tris flags are visible device wide
+    if (stats_flags != nullptr || progress != nullptr) {
+        __threadfence();                                       // this CTA's batch_tris flags / triangles are visible device wide
         __syncthreads();
         if (tid == 0) {
             const unsigned int done = atomicAdd(&ctr->extract_done, 1u);
             sm.last_cta = (done == gridDim.x - 1u) ? 1u : 0u;
         }
         __syncthreads();
-        if (sm.last_cta) {
+        if (sm.last_cta && progress != nullptr && tid == 0) {
+            // a pipelined call: tell the host (mapped page-locked memory) that this round's triangles are complete
+            progress->tri_cursor = *((volatile unsigned long long*)&ctr->tri_cursor);
+            progress->max_cubes = *((volatile unsigned int*)&ctr->max_cubes);
+            progress->max_pts = *((volatile unsigned int*)&ctr->max_pts);
+            __threadfence_system();
+            *((volatile unsigned int*)&progress->done) = 1u;
+        }
+        if (sm.last_cta && stats_flags != nullptr) {
             __threadfence();
             const int total_b = g.ub1 - g.ub0;
             unsigned int ne = 0, nn = 0;

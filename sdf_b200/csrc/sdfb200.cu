@@ -32,6 +32,7 @@
 #include <new>
 #include <mutex>
 #include <future>
+#include <atomic>
 #include <chrono>
 #include <sstream>
 #include <string>
@@ -108,8 +109,8 @@ template <int TS>
 __global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_BLOCKS_PER_SM)
 extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
                const unsigned long long tri_capacity, unsigned long long* ext_cursor, const McTablesSmem* tables,
-               const unsigned char* stats_flags) {
-    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags);
+               const unsigned char* stats_flags, RoundProgress* progress) {
+    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags, progress);
 }
 
 // float32 copies of the lattice axes for the fast classification pass (same rounding as a host-side cast)
@@ -155,6 +156,8 @@ struct DeviceCtx {
     float* vol = nullptr; size_t slot_cap = 0; TileMeta* tile_meta = nullptr; size_t meta_cap = 0;
     unsigned char* scratch = nullptr; size_t scratch_cap = 0;       // tile_sign_kernel: per-tile mask blocks
     McTablesSmem* mc_tables = nullptr;                              // packed decision tables (one bulk copy per extraction CTA)
+    RoundProgress* progress = nullptr;                              // page-locked + device mapped: one slot per pipelined round
+    RoundProgress* progress_dev = nullptr;                          //   (the same memory as the device sees it)
     // the whole device-resident step as one CUDA graph, re-used while every launch parameter stays the same
     cudaStream_t cap_stream = nullptr;
     cudaGraphExec_t step_exec = nullptr;
@@ -703,6 +706,9 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     for (int i = 0; i < kMaxPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.pev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaHostAlloc((void**)&c.progress, sizeof(RoundProgress) * kMaxPipe, cudaHostAllocMapped));
+    memset(c.progress, 0, sizeof(RoundProgress) * kMaxPipe);
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&c.progress_dev, c.progress, 0));
     {   // the marching-cubes decision tables, packed exactly as the extraction kernel keeps them in shared memory
         std::unique_ptr<McTablesSmem> t(new McTablesSmem());
         memset(t.get(), 0, sizeof(McTablesSmem));
@@ -822,6 +828,7 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFreeHost(c.ctr_host); cudaFree(c.stage);
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
         cudaFree(c.scratch); cudaFree(c.mc_tables);
+        if (c.progress) cudaFreeHost(c.progress);
         if (c.step_exec) cudaGraphExecDestroy(c.step_exec);
         if (c.cap_stream) cudaStreamDestroy(c.cap_stream);
         for (int i = 0; i < 9; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
@@ -1082,7 +1089,12 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         // Host output: cut the work list into a few rounds so that the triangles of round k cross PCIe
         // while round k+1 is computed (the copy is the longer leg: 36 B per triangle at PCIe speed).
         int pipe = (tri_out && !out_dev && !stl_out && !ext_cursor && big) ? pipe_rounds() : 1;
-        const bool sync_free = upper <= max_round && pipe == 1;
+        if (upper < 2ull * c->sms) pipe = 1;                      // less than two tiles per SM: nothing to overlap
+        // Rounds are cut ON THE DEVICE (round k of `pipe` equal parts of the active tiles, work_range()): the host
+        // queues the whole call without knowing how many batches survive the pre-pass.
+        const unsigned long long round_tiles = (upper + pipe - 1) / pipe;
+        const bool sync_free = round_tiles <= max_round;
+        if (!sync_free) pipe = 1;                                 // (a lattice beyond the volume budget: host-cut rounds below)
 
         // every kernel of the step resolved up front (nothing may compile or load inside a stream capture)
         cudaKernel_t k_skip = jit_get(prog, JK_SKIP, big);
@@ -1118,7 +1130,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         };
         // one round = (A) evaluate + classify, (B) float64 refinement, (C) extraction [+ batch statistics when last]
         auto launch_round = [&](cudaStream_t s, bool captured, const TileLists& L, unsigned int wbu, unsigned int we,
-                                unsigned long long tiles, bool first, bool last) -> int {
+                                unsigned long long tiles, bool first, bool last, RoundProgress* progress) -> int {
             cudaError_t e = cudaSuccess;
             if (first) CUDA_TRY(rec(c->ev[4], s, captured));
             if (sign_path) {
@@ -1174,7 +1186,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             }
             if (first) CUDA_TRY(rec(c->ev[6], s, captured));
             extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, s>>>(
-                g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor, c->mc_tables, last ? c->flags : nullptr);
+                g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor, c->mc_tables, last ? c->flags : nullptr, progress);
             CUDA_TRY(cudaGetLastError());
             if (first) CUDA_TRY(rec(c->ev[7], s, captured));
             return 0;
@@ -1188,13 +1200,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             CUDA_TRY(cudaStreamSynchronize(stream));
             n_work = (unsigned long long)h.n_active * g.sub * g.sub * g.sub;
         }
-        unsigned int round = (unsigned int)std::min<unsigned long long>(n_work, max_round);
-        if (pipe > 1) {
-            // whole waves of the tile kernel per round; a job of less than two waves has nothing to overlap
-            const unsigned long long per = ((n_work + pipe - 1) / pipe + c->sms - 1) / c->sms * c->sms;
-            if (n_work < 2ull * c->sms || n_work > max_round) pipe = 1;
-            else round = (unsigned int)std::min<unsigned long long>(per, max_round);
-        }
+        const unsigned int round = (unsigned int)std::min<unsigned long long>(sync_free ? round_tiles : n_work, max_round);
         if (n_work > 0) {
             ran_pipeline = true;
             rc = grow(&c->vol, &c->slot_cap, (size_t)round * VOL_STRIDE); if (rc) return rc;
@@ -1224,25 +1230,37 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->empty, 0, 2 * sizeof(unsigned int), stream));
                     CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 6 * sizeof(unsigned int), stream));      // n_slots .. extract_done
                 }
-                if (sync_free && attempt == 0) {
+                if (sync_free) {
                     // ---- the whole step in one go: pre-pass, A, B, C + statistics, counters to the host
                     auto enqueue = [&](cudaStream_t s, bool captured) -> int {
-                        int r = launch_prepass(s); if (r) return r;
+                        int r = 0;
+                        if (attempt == 0) { r = launch_prepass(s); if (r) return r; }       // (a retry keeps the pre-pass results)
                         CUDA_TRY(rec(c->ev[1], s, captured));
-                        r = launch_round(s, captured, L, 0u, 0xffffffffu, n_work, true, true); if (r) return r;
+                        for (int k = 0; k < pipe; ++k) {
+                            if (k > 0) {         // (the first round starts from the zeroed counters)
+                                CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), s));
+                                CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 4 * sizeof(unsigned int), s));     // n_slots .. extract_done
+                            }
+                            const unsigned int wbu = pipe > 1 ? (unsigned int)k : 0u;
+                            const unsigned int we = pipe > 1 ? (0xfffe0000u | (unsigned int)pipe) : 0xffffffffu;
+                            r = launch_round(s, captured, L, wbu, we, round_tiles, k == 0, k == pipe - 1,
+                                             pipe > 1 ? c->progress_dev + k : nullptr);
+                            if (r) return r;
+                        }
                         CUDA_TRY(rec(c->ev[2], s, captured));
                         CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
                         if (!tail) CUDA_TRY(rec(c->ev[3], s, captured));
                         return 0;
                     };
+                    for (int k = 0; k < pipe; ++k) ((volatile RoundProgress*)c->progress)[k].done = 0u;
                     bool launched = false;
-                    if (graph_enabled()) {
+                    if (graph_enabled() && attempt == 0) {
                         // key: every value the launches above depend on
                         struct { GridDesc g; TileLists L; float tau; int sparse, precision, tail; float* dtri; unsigned long long cap, n_work;
                                  unsigned long long* ext; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr; } key;
                         memset(&key, 0, sizeof(key));
                         key.g = g; key.L = L; key.tau = tau; key.sparse = sparse; key.precision = precision; key.tail = tail ? 1 : 0;
-                        key.dtri = dtri; key.cap = cap; key.n_work = n_work; key.ext = ext_cursor;
+                        key.dtri = dtri; key.cap = cap; key.n_work = n_work * 64ull + (unsigned long long)pipe; key.ext = ext_cursor;
                         key.k0 = (void*)k_skip; key.k1 = (void*)k_tile; key.k2 = (void*)k_refine;
                         key.flags = c->flags; key.active = c->active; key.bt = c->batch_tris; key.ctr = c->ctr; key.ctrh = c->ctr_host;
                         key.scr = c->scratch;
@@ -1270,18 +1288,34 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         }
                     }
                     if (!launched) { rc = enqueue(stream, false); if (rc) return rc; }
-                } else {
-                    if (sync_free) {            // (a retry: the pre-pass results are still there)
-                        CUDA_TRY(cudaEventRecord(c->ev[1], stream));
+                    // pipelined host output: every round is queued; follow the rounds' progress words (mapped host
+                    // memory, written by each round's extraction kernel) and send a round's triangles over PCIe as
+                    // soon as it is complete, while the next rounds compute
+                    for (int k = 0; k < pipe && pipe > 1; ++k) {
+                        volatile RoundProgress* pr = c->progress + k;
+                        while (pr->done == 0u) {
+                            if (cudaStreamQuery(stream) != cudaErrorNotReady) break;      // finished or failed: the counters decide
+                        }
+                        std::atomic_thread_fence(std::memory_order_acquire);
+                        if (pr->done == 0u) break;
+                        if (pr->max_cubes > L.cube_cap || pr->max_pts > L.pt_cap) break;       // lists overflowed: retried below
+                        const unsigned long long produced = pr->tri_cursor;
+                        const unsigned long long upto = std::min<unsigned long long>(produced, cap);
+                        if (upto > copied) {
+                            CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(upto - copied) * 36,
+                                                     cudaMemcpyDeviceToHost, c->copy_stream));
+                            copied = upto;
+                        }
                     }
+                } else {
                     for (unsigned long long wb = 0; wb < n_work; wb += round) {
-                        const unsigned int we = sync_free ? 0xffffffffu : (unsigned int)std::min<unsigned long long>(n_work, wb + round);
+                        const unsigned int we = (unsigned int)std::min<unsigned long long>(n_work, wb + round);
                         if (wb > 0) {        // (the first round starts from the zeroed counters)
                             CUDA_TRY(cudaMemsetAsync(&c->ctr->work_cursor, 0, sizeof(unsigned int), stream));
-                            CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 3 * sizeof(unsigned int), stream));
+                            CUDA_TRY(cudaMemsetAsync(&c->ctr->n_slots, 0, 4 * sizeof(unsigned int), stream));     // n_slots .. extract_done
                         }
                         const unsigned long long tiles = std::min<unsigned long long>(n_work, wb + round) - wb;
-                        rc = launch_round(stream, false, L, (unsigned int)wb, we, tiles, wb == 0, wb + round >= n_work); if (rc) return rc;
+                        rc = launch_round(stream, false, L, (unsigned int)wb, we, tiles, wb == 0, wb + round >= n_work, nullptr); if (rc) return rc;
                         if (pipe > 1 && n_rounds < kMaxPipe) {
                             CUDA_TRY(cudaMemcpyAsync(c->ctr_host + 1 + n_rounds, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                             CUDA_TRY(cudaEventRecord(c->pev[n_rounds], stream));

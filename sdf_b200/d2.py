@@ -9,6 +9,7 @@ import functools
 import numpy as np
 
 from . import dn, ease
+from . import ir
 from .ir import Node
 
 ORIGIN = np.array((0, 0))
@@ -57,6 +58,13 @@ class SDF2:
     def k(self, k=None):
         self._k = k
         return self
+
+    def __setattr__(self, name, value):
+        # `_k` is the one attribute a tree can change after it has been built (d3.py:38-40 / dn.py:12): every
+        # change -- through k() or by assignment -- invalidates the lowered programs cached on the trees
+        if name == '_k':
+            ir.MUTATIONS[0] += 1
+        object.__setattr__(self, name, value)
 
 
 def _wrap(result, cls):

@@ -18,6 +18,7 @@ import functools
 import numpy as np
 
 from . import dn, ease
+from . import ir
 from .ir import Node
 
 # Constants (d3.py:9-17)
@@ -67,6 +68,13 @@ class SDF3:
     def k(self, k=None):
         self._k = k
         return self
+
+    def __setattr__(self, name, value):
+        # `_k` is the one attribute a tree can change after it has been built (d3.py:38-40 / dn.py:12): every
+        # change -- through k() or by assignment -- invalidates the lowered programs cached on the trees
+        if name == '_k':
+            ir.MUTATIONS[0] += 1
+        object.__setattr__(self, name, value)
 
     def generate(self, *args, **kwargs):
         from . import core

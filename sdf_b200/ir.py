@@ -101,6 +101,8 @@ OPNAME = {v: k for k, v in OPCODE.items()}
 FOLD_OPS = {'union': ('UNION', 'UNION_K'), 'difference': ('DIFFERENCE', 'DIFFERENCE_K'),
             'intersection': ('INTERSECTION', 'INTERSECTION_K')}
 
+MUTATIONS = [0]      # bumped whenever some SDF object's `_k` changes (d3.py / d2.py __setattr__): cached lowerings are stale
+
 MAX_CODE = 8192      # instruction words (the kernel-parameter image of the interpreter holds 512 / 1024;
 MAX_CONSTS = 32768   #  larger programs run only on the run-time specialised kernels)
 IMG_MAX_CODE = 512   # capacity of the interpreter's kernel-parameter program image

@@ -24,13 +24,14 @@ def main():
         f = models.CONFIGS[name](sdf_b200)
         _, L = models.CONFIG_GRIDS[name]
         bounds, step = ((-L, -L, -L), (L, L, L)), 2.0 * L / n
-        pts, info = multi.generate_distributed(f, step=step, bounds=bounds, gather='host', device=local)
         one, info1 = sdf_b200.generate(f, step=step, bounds=bounds, verbose=False, device=local, return_info=True)
-        rep = compare_soups(pts, one)
-        good = rep['count_equal'] and rep['exact_triangles'] == rep['n_ref']
-        ok = ok and good
-        print('rank %d %s: slab %s local %d total %d single %d identical=%s' % (
-            rank, name, info['zb'], info['triangles'], info['triangles_total'], info1['triangles'], good), flush=True)
+        for partition in ('window', 'slab'):
+            pts, info = multi.generate_distributed(f, step=step, bounds=bounds, gather='host', device=local, partition=partition)
+            rep = compare_soups(pts, one)
+            good = rep['count_equal'] and rep['exact_triangles'] == rep['n_ref']
+            ok = ok and good
+            print('rank %d %s: %s %s local %d total %d single %d identical=%s' % (
+                rank, name, partition, info['zb'], info['triangles'], info['triangles_total'], info1['triangles'], good), flush=True)
         # fused gather to rank 0 (NVLink peer writes from the extraction kernels)
         rpts, rinfo = multi.generate_distributed(f, step=step, bounds=bounds, gather='root', device=local)
         if rank == 0:
