@@ -155,6 +155,30 @@ int sdfb200_generate_window(sdfb200_prog* prog,
                             int64_t* n_tri, int64_t stats[6], double timings_ms[8], int device, void* stream);
 
 /*
+ * Replaces: core._marching_cubes + the world mapping of core._worker (sdf/core.py:16-18, 58-60) for ONE batch whose
+ * values the CALLER computed -- the route for a tree that holds a user-written numpy closure (README "writing your
+ * own SDFs"), which cannot be lowered to the CUDA evaluator: the host evaluates that closure on the batch's points
+ * exactly like the reference does (children that are library nodes still evaluate on the GPU), and hands the
+ * volume over.  volume: float32 [nx][ny][nz] in C order (skimage casts to float32 too), host or device,
+ * 1..33 samples per axis; xs / ys / zs: the batch's float64 axis slices (scale = xs[1] - xs[0], offset = xs[0]).
+ * A volume without a sign change, or thinner than 2 samples, yields 0 triangles (skimage raises; the reference
+ * maps that to an empty batch, core.py:53-56).  `prog` only lends its device context (any program).
+ */
+int sdfb200_mc_volume(sdfb200_prog* prog, const float* volume, int64_t nx, int64_t ny, int64_t nz,
+                      const double* xs, const double* ys, const double* zs, float* tri_out, int64_t tri_capacity,
+                      int64_t* n_tri, int device, void* stream);
+
+/*
+ * Replaces: core._mesh's  np.unique(points, axis=0, return_inverse=True)  (sdf/core.py:160-164), the welding
+ * between generate()'s vertex soup and an indexed mesh (meshio formats).  tris: n_tri x 9 float32 (host or device);
+ * verts_out: room for 3 * n_tri x 3 float32, receives the n_verts unique vertices in lexicographic (x, y, z) order
+ * (numpy's float comparison: -0.0 welds with +0.0); faces_out: n_tri x 3 int32, the unique-vertex index of every
+ * soup vertex (numpy's `inverse`).
+ */
+int sdfb200_weld(const float* tris, int64_t n_tri, float* verts_out, int32_t* faces_out, int64_t* n_verts,
+                 int device, void* stream);
+
+/*
  * Run-time specialisation check (needs no GPU): generate the straight-line evaluator of `prog` for
  * kernel id 0 (skip pre-pass), 1..4 (fused tile kernel, precision 0..3), 5/6 (streamed float32
  * evaluator accurate/fast), 7 (streamed float64) and compile it with NVRTC for sm_100a.  The other

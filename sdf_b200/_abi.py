@@ -20,7 +20,7 @@ EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
            'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
            'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
-           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared', 'sdfb200_generate_window']
+           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared', 'sdfb200_generate_window', 'sdfb200_mc_volume', 'sdfb200_weld']
 
 
 class SdfB200Error(RuntimeError):
@@ -76,6 +76,8 @@ def lib():
                                           vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_generate_window.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i64, i64,
                                           vp, i64, vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
+    L.sdfb200_mc_volume.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, i64, ctypes.POINTER(i64), i32, vp]
+    L.sdfb200_weld.argtypes = [vp, i64, vp, vp, ctypes.POINTER(i64), i32, vp]
     L.sdfb200_jit_probe.argtypes = [vp, i32, ctypes.POINTER(i64)]
     L.sdfb200_jit_plan.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(dbl)]
     L.sdfb200_skip_flags.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, vp, i32, vp]
@@ -102,6 +104,20 @@ def _ptr(obj):
     if isinstance(obj, np.ndarray):
         return obj.ctypes.data
     return obj.data_ptr()
+
+
+def weld(points, device=0, stream=None):
+    """np.unique(points, axis=0, return_inverse=True) of a (3T, 3) float32 vertex soup on the GPU
+    (include/sdfb200.h sdfb200_weld): (unique vertices (V, 3) float32 in lexicographic order, inverse (3T,) int32)."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    if len(pts) % 3:
+        raise ValueError('a triangle soup has 3 vertices per triangle')
+    n_tri = len(pts) // 3
+    verts = np.empty((max(len(pts), 1), 3), np.float32)
+    faces = np.empty(max(len(pts), 1), np.int32)
+    nv = ctypes.c_int64(0)
+    _check(lib().sdfb200_weld(pts.ctypes.data, n_tri, verts.ctypes.data, faces.ctypes.data, ctypes.byref(nv), device, stream))
+    return verts[:nv.value], faces[:len(pts)]
 
 
 class PinnedPool:
@@ -248,6 +264,24 @@ class ProgramHandle:
                                              int(zb[0]), int(zb[1]), shared._h, int(which), ctypes.byref(n_tri),
                                              stats.ctypes.data, timings.ctypes.data, device, stream))
         return n_tri.value, stats, timings
+
+    def mc_volume(self, volume, X, Y, Z, device=0, stream=None):
+        """Marching cubes + world mapping of one batch volume computed by the caller (include/sdfb200.h
+        sdfb200_mc_volume); returns a (T, 9) float32 ndarray."""
+        vol = np.ascontiguousarray(volume, np.float32)
+        X, Y, Z = (np.ascontiguousarray(a, np.float64) for a in (X, Y, Z))
+        assert vol.shape == (len(X), len(Y), len(Z)), (vol.shape, len(X), len(Y), len(Z))
+        cap = max(1, (len(X) - 1) * (len(Y) - 1) * (len(Z) - 1)) * 5
+        n_tri = ctypes.c_int64(0)
+        while True:
+            out = np.empty((cap, 9), np.float32)
+            rc = lib().sdfb200_mc_volume(self._h, vol.ctypes.data, len(X), len(Y), len(Z), X.ctypes.data, Y.ctypes.data,
+                                         Z.ctypes.data, out.ctypes.data, cap, ctypes.byref(n_tri), device, stream)
+            if rc == E_CAPACITY:
+                cap = int(n_tri.value) + 16
+                continue
+            _check(rc)
+            return out[:n_tri.value]
 
     def generate_window(self, X, Y, Z, batch_size, sparse, precision, tau, window, tri_out=None, capacity=0,
                         shared=None, which=0, device=0, stream=None):

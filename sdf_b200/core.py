@@ -16,7 +16,7 @@ import time
 import numpy as np
 
 from . import _abi, progress, stl
-from .ir import lower
+from .ir import NotLowerableError, lower
 
 WORKERS = multiprocessing.cpu_count()
 SAMPLES = 2 ** 22
@@ -66,14 +66,87 @@ def _program_handle(sdf):
     return h, key
 
 
+def _lowerable(obj):
+    try:
+        program_handle(obj)
+        return True
+    except NotLowerableError:
+        return False
+
+
+def _compose_around_closure(obj, p):
+    """``obj(p)`` for a tree that holds a user-written numpy closure somewhere below ``obj``.
+
+    A Python closure can only run on the host, so the nodes ABOVE it cannot be fused into the CUDA evaluator
+    either.  Every maximal sub-tree without a closure still evaluates on the GPU (one call each); the closure is
+    called as the reference calls it (d3.py:24-25); and the handful of composition nodes people put around their
+    own SDFs -- the CSG folds, blend, negate / dilate / erode / shell, translate / scale / rotate (dn.py:7-80,
+    d3.py:329-360) -- combine those fields on the host with the reference's formulas.  Any other node above a
+    closure raises NotLowerableError.  Lowered trees (everything the library itself builds) never come here."""
+    from .ir import node_of
+    from . import d2
+    n = node_of(obj)
+    if isinstance(obj, d2.SDF2) and p.shape[1] == 3:
+        p = p[:, :2]
+    if n.kind == 'opaque':
+        return np.asarray(obj.f(p), np.float64).reshape(-1)
+    if _lowerable(obj):
+        return np.asarray(obj(p), np.float64).reshape(-1)         # a closure-free sub-tree: one GPU evaluation
+    kids = n.children
+    if n.kind == 'fold' or n.kind == 'blend':
+        d1 = _compose_around_closure(kids[0], p)
+        for b in kids[1:]:
+            d2 = _compose_around_closure(b, p)
+            K = n.extra or getattr(b, '_k', None)
+            if n.kind == 'blend':                                        # dn.py:52-60
+                d1 = K * d2 + (1 - K) * d1
+            elif n.op == 'union':                                        # dn.py:7-20
+                if K is None:
+                    d1 = np.minimum(d1, d2)
+                else:
+                    h = np.clip(0.5 + 0.5 * (d2 - d1) / K, 0, 1)
+                    d1 = d2 + (d1 - d2) * h - K * h * (1 - h)
+            elif n.op == 'difference':                                   # dn.py:22-35
+                if K is None:
+                    d1 = np.maximum(d1, -d2)
+                else:
+                    h = np.clip(0.5 - 0.5 * (d2 + d1) / K, 0, 1)
+                    d1 = d1 + (-d2 - d1) * h + K * h * (1 - h)
+            else:                                                        # dn.py:37-50
+                if K is None:
+                    d1 = np.maximum(d1, d2)
+                else:
+                    h = np.clip(0.5 - 0.5 * (d2 - d1) / K, 0, 1)
+                    d1 = d2 + (d1 - d2) * h + K * h * (1 - h)
+        return d1
+    if n.kind == 'value' and n.op in ('NEGATE', 'ADDC', 'SHELL'):        # dn.py:62-80
+        d = _compose_around_closure(kids[0], p)
+        return -d if n.op == 'NEGATE' else (d + n.consts[0] if n.op == 'ADDC' else np.abs(d) - n.consts[0] / 2)
+    if n.kind == 'transform' and n.op == 'TRANSLATE':                    # d3.py:329-333
+        return _compose_around_closure(kids[0], p - np.array(n.consts[:p.shape[1]]))
+    if n.kind == 'transform' and n.op == 'ROTATE' and p.shape[1] == 3:   # d3.py:347-360
+        return _compose_around_closure(kids[0], np.dot(p, np.array(n.consts).reshape(3, 3)))
+    if n.kind == 'scale' and p.shape[1] == 3:                            # d3.py:335-345
+        return _compose_around_closure(kids[0], p / np.array(n.consts[:3])) * n.consts[3]
+    raise NotLowerableError('node %r sits above a Python closure: only CSG folds, blend, negate / dilate / erode / shell and '
+                            'translate / scale / rotate can be combined with user-written SDFs' % (n.label,))
+
+
 def evaluate(sdf, p, device=None):
     """``sdf(p)``: float64 points in, float64 distances out (d3.py:24-25), on the GPU.
 
     numpy in -> numpy out (staged through device memory inside the C-ABI call);
     a CUDA torch tensor in -> a CUDA tensor of the same dtype out (float32 uses
-    the streamed float32 evaluator).
+    the streamed float32 evaluator).  A tree that holds a user-written numpy closure is evaluated piecewise
+    (``_compose_around_closure``).
     """
-    h, _ = program_handle(sdf)
+    try:
+        h, _ = program_handle(sdf)
+    except NotLowerableError:
+        if hasattr(p, 'data_ptr'):
+            raise
+        pts = np.ascontiguousarray(p, dtype=np.float64)
+        return _compose_around_closure(sdf, pts.reshape(-1, pts.shape[-1]))
     if isinstance(p, np.ndarray) or not hasattr(p, 'data_ptr'):
         pts = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 3)
         out = np.empty(len(pts), np.float64)
@@ -211,6 +284,69 @@ def run_batches(sdf, X, Y, Z, batch_size=BATCH_SIZE, sparse=True, precision='exa
     return out[:n_tri], info
 
 
+def _skip_host(sdf, job):
+    """core.py:28-43 on the host (only for trees the CUDA evaluator cannot lower): |d(centre)| against the half
+    diagonal, then the eight corners in itertools.product order."""
+    import itertools
+    X, Y, Z = job
+    x0, x1, y0, y1, z0, z1 = X[0], X[-1], Y[0], Y[-1], Z[0], Z[-1]
+    x, y, z = (x0 + x1) / 2, (y0 + y1) / 2, (z0 + z1) / 2
+    r = abs(sdf(np.array([(x, y, z)])).reshape(-1)[0])
+    d = np.linalg.norm(np.array((x - x0, y - y0, z - z0)))
+    if r <= d:
+        return False
+    corners = np.array(list(itertools.product((x0, x1), (y0, y1), (z0, z1))))
+    values = sdf(corners).reshape(-1)
+    same = np.all(values > 0) if values[0] > 0 else np.all(values < 0)
+    return bool(same)
+
+
+def _generate_opaque(sdf, X, Y, Z, batch_size, sparse, device):
+    """The route for a tree that holds a user-written numpy closure (README "writing your own SDFs"; ir.py kind
+    'opaque'): the closure cannot run on the GPU, so each batch is evaluated by calling the tree exactly like the
+    reference does (core.py:45-52; library nodes below the closure still evaluate on the GPU through their own
+    ``__call__``), and the batch volume goes through marching cubes + world mapping on the device
+    (``sdfb200_mc_volume``).  Same batches, same _skip rule, same float32 cast as core.py / skimage."""
+    import itertools
+    if batch_size > 32:
+        raise ValueError('a tree with a Python closure is meshed batch by batch on the device: batch_size <= 32 (got %d)' % batch_size)
+    h, _ = program_handle(_context_sdf())
+    dev = default_device() if device is None else device
+    s = batch_size
+    Xs = [X[i:i + s + 1] for i in range(0, len(X), s)]
+    Ys = [Y[i:i + s + 1] for i in range(0, len(Y), s)]
+    Zs = [Z[i:i + s + 1] for i in range(0, len(Z), s)]
+    skipped = empty = nonempty = evaluated = 0
+    out = []
+    for job in itertools.product(Xs, Ys, Zs):
+        if sparse and _skip_host(sdf, job):
+            skipped += 1
+            continue
+        P = _cartesian_product(*job)
+        volume = np.asarray(sdf(P), np.float64).reshape((len(job[0]), len(job[1]), len(job[2])))
+        evaluated += volume.size
+        tris = h.mc_volume(volume, job[0], job[1], job[2], device=dev)
+        if len(tris) == 0:
+            empty += 1
+        else:
+            nonempty += 1
+            out.append(tris)
+    tris = np.concatenate(out) if out else np.zeros((0, 9), np.float32)
+    info = dict(triangles=len(tris), skipped=skipped, empty=empty, nonempty=nonempty, evaluated=evaluated, refined=0,
+                active_cubes=0, precision='f64 on the host (Python closure in the tree) + device marching cubes')
+    return tris, info
+
+
+_ctx_sdf = []
+
+
+def _context_sdf():
+    if not _ctx_sdf:
+        from . import d3
+        _ctx_sdf.append(d3.sphere(1))
+    return _ctx_sdf[0]
+
+
 def generate(
         sdf,
         step=None, bounds=None, samples=SAMPLES,
@@ -242,7 +378,10 @@ def generate(
         print('%d samples in %d batches with %d workers' % (num_samples, num_batches, workers))
 
     bar = progress.Bar(num_batches or 0, enabled=verbose)
-    tris, info = run_batches(sdf, X, Y, Z, batch_size, sparse, precision, device=device)
+    try:
+        tris, info = run_batches(sdf, X, Y, Z, batch_size, sparse, precision, device=device)
+    except NotLowerableError:
+        tris, info = _generate_opaque(sdf, X, Y, Z, batch_size, sparse, device)
     bar.done()
     points = tris.reshape(-1, 3)
 
@@ -272,7 +411,12 @@ def save_stl(path, sdf, step=None, bounds=None, samples=SAMPLES, workers=WORKERS
     (nbx, nby, nbz), num_samples = batch_counts(X, Y, Z, batch_size)
     if verbose:
         print('%d samples in %d batches with %d workers' % (num_samples, nbx * nby * nbz, workers))
-    h, key = program_handle(sdf)
+    try:
+        h, key = program_handle(sdf)
+    except NotLowerableError:           # a Python closure in the tree: batch-by-batch route, records built on the host
+        points = generate(sdf, step, bounds, samples, workers, batch_size, verbose, sparse, precision=precision, device=device)
+        stl.write_binary_stl(path, points)
+        return len(points) // 3
     X = np.ascontiguousarray(X, np.float64)
     Y = np.ascontiguousarray(Y, np.float64)
     Z = np.ascontiguousarray(Z, np.float64)
@@ -310,12 +454,18 @@ def save(path, *args, **kwargs):
     mesh.write(path)
 
 
+def weld(points, device=None):
+    """The welding step of core.py:160-164, ``np.unique(points, axis=0, return_inverse=True)``, on the GPU:
+    (unique vertices (V, 3) in lexicographic order, faces (T, 3) int32 indexing them)."""
+    verts, inverse = _abi.weld(points, device=default_device() if device is None else device)
+    return verts, inverse.reshape(-1, 3)
+
+
 def _mesh(points):
-    """core.py:160-164 (needs the optional ``meshio`` package, as in the reference)."""
+    """core.py:160-164 (needs the optional ``meshio`` package, as in the reference); welded on the GPU."""
     import meshio
-    points, cells = np.unique(points, axis=0, return_inverse=True)
-    cells = [('triangle', cells.reshape((-1, 3)))]
-    return meshio.Mesh(points, cells)
+    verts, faces = weld(points)
+    return meshio.Mesh(verts, [('triangle', faces)])
 
 
 def sample_slice(sdf, w=1024, h=1024, x=None, y=None, z=None, bounds=None):

@@ -56,6 +56,17 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// the same, for the other translation units of the library (sdfb200_weld.cu)
+int sdfb200_fail_(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
 #define CUDA_TRY(expr)                                                                      \
     do {                                                                                    \
         cudaError_t err__ = (expr);                                                         \
@@ -111,6 +122,24 @@ extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int*
                const unsigned long long tri_capacity, unsigned long long* ext_cursor, const McTablesSmem* tables,
                const unsigned char* stats_flags, RoundProgress* progress) {
     extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags, progress);
+}
+
+// Candidate cubes of ONE dense user volume (sdfb200_mc_volume): the volume sits in tile slot 0 in its own C-order
+// linearisation; a cube with mixed `v > 0` corners goes to the candidate list the extraction kernel walks.
+__global__ void volume_candidates_kernel(const TileLists L, Counters* ctr, int px, int py, int pz) {
+    const int n = (px - 1) * (py - 1) * (pz - 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cz = i % (pz - 1), cy = (i / (pz - 1)) % (py - 1), cx = i / ((pz - 1) * (py - 1));
+    const float* p = L.vol + (size_t)((cx * py + cy) * pz + cz);
+    const int pyz = py * pz;
+    const float f[8] = {p[0], p[1], p[pz + 1], p[pz], p[pyz], p[pyz + 1], p[pyz + pz + 1], p[pyz + pz]};
+    int pos = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pos += f[k] > 0.0f ? 1 : 0;
+    if (pos == 0 || pos == 8) return;
+    const unsigned int at = atomicAdd(&ctr->n_cubes, 1u);
+    if (at < L.cube_cap) L.cubes[at] = make_uint2(0u, (unsigned int)((cx << 10) | (cy << 5) | cz));
 }
 
 // float32 copies of the lattice axes for the fast classification pass (same rounding as a host-side cast)
@@ -1529,6 +1558,63 @@ extern "C" int sdfb200_generate_window(sdfb200_prog* prog, const double* xs, int
     }
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, tri_out, tri_capacity,
                          n_tri, stats, timings_ms, device, stream, nullptr, nullptr, ub_begin, ub_end);
+}
+
+// skimage.measure.marching_cubes(volume, 0) + world mapping for ONE batch volume supplied by the caller (the values
+// of an SDF the evaluator cannot lower: a user's own numpy closure) -- see include/sdfb200.h.
+extern "C" int sdfb200_mc_volume(sdfb200_prog* prog, const float* volume, int64_t nx, int64_t ny, int64_t nz,
+                                 const double* xs, const double* ys, const double* zs, float* tri_out, int64_t tri_capacity,
+                                 int64_t* n_tri, int device, void* stream_) {
+    if (!prog || !volume || !n_tri || !xs || !ys || !zs) return fail(SDFB200_E_INVALID, "mc_volume: NULL argument");
+    if (nx < 1 || ny < 1 || nz < 1 || nx > kTS + 1 || ny > kTS + 1 || nz > kTS + 1)
+        return fail(SDFB200_E_INVALID, "mc_volume: a batch volume has 1..%d samples per axis (got %lld x %lld x %lld)", kTS + 1,
+                    (long long)nx, (long long)ny, (long long)nz);
+    if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "mc_volume: negative capacity");
+    std::lock_guard<std::mutex> guard(prog->lock);
+    DeviceCtx* c; int rc = get_ctx(prog, device, &c); if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_tri = 0;
+    if (nx < 2 || ny < 2 || nz < 2) return 0;                    // skimage raises, the reference maps it to [] (core.py:53-56)
+    GridDesc g;
+    rc = setup_grid(c, stream, xs, nx, ys, ny, zs, nz, kTS, 0, -1, -1, -1, &g); if (rc) return rc;
+    rc = grow(&c->vol, &c->slot_cap, (size_t)VOL_STRIDE); if (rc) return rc;
+    rc = grow(&c->tile_meta, &c->meta_cap, (size_t)1); if (rc) return rc;
+    rc = grow(&c->cubes, &c->cube_cap, (size_t)kTS * kTS * kTS); if (rc) return rc;
+    TileLists L;
+    memset(&L, 0, sizeof(L));
+    L.vol = c->vol; L.tile_meta = c->tile_meta; L.cubes = c->cubes; L.pts = c->pts;
+    L.slot_cap = 1; L.cube_cap = (unsigned int)std::min<size_t>(c->cube_cap, 0xffffffffu); L.pt_cap = 0;
+    const size_t nvox = (size_t)nx * ny * nz;
+    CUDA_TRY(cudaMemcpyAsync(c->vol, volume, nvox * sizeof(float), cudaMemcpyDefault, stream));
+    TileMeta m;
+    memset(&m, 0, sizeof(m));
+    m.ext = (unsigned int)nx | ((unsigned int)ny << 8) | ((unsigned int)nz << 16);
+    CUDA_TRY(cudaMemcpyAsync(c->tile_meta, &m, sizeof(m), cudaMemcpyHostToDevice, stream));
+    const size_t nb = (size_t)g.nbx * g.nby * g.nbz;
+    CUDA_TRY(cudaMemsetAsync(c->batch_tris, 0, nb * sizeof(unsigned int), stream));
+    const int ncubes = (int)((nx - 1) * (ny - 1) * (nz - 1));
+    volume_candidates_kernel<<<(ncubes + 255) / 256, 256, 0, stream>>>(L, c->ctr, (int)nx, (int)ny, (int)nz);
+    CUDA_TRY(cudaGetLastError());
+    const int out_kind = tri_out ? mem_kind(tri_out) : 1;
+    float* dtri = tri_out;
+    if (tri_out && out_kind != 1) {
+        rc = ensure_stage(c, (size_t)tri_capacity * 36 + 256); if (rc) return rc;
+        dtri = (float*)c->stage;
+    }
+    extract_kernel<kTS><<<std::min(c->sms, (ncubes + EXTRACT_THREADS - 1) / EXTRACT_THREADS), EXTRACT_THREADS, 0, stream>>>(
+        g, L, c->ctr, c->batch_tris, dtri, tri_out ? (unsigned long long)tri_capacity : 0ull, nullptr, c->mc_tables, nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const Counters& h = *c->ctr_host;
+    *n_tri = (int64_t)h.tri_cursor;
+    if (tri_out && h.tri_cursor > (unsigned long long)tri_capacity)
+        return fail(SDFB200_E_CAPACITY, "triangle buffer too small: %lld needed, %lld given", (long long)h.tri_cursor, (long long)tri_capacity);
+    if (tri_out && out_kind != 1 && h.tri_cursor > 0) {
+        CUDA_TRY(cudaMemcpyAsync(tri_out, dtri, (size_t)h.tri_cursor * 36, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return 0;
 }
 
 extern "C" int sdfb200_jit_probe(sdfb200_prog* prog, int kernel, int64_t* cubin_bytes) {

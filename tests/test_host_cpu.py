@@ -428,3 +428,44 @@ def test_guard_band_follows_the_amplification_of_the_tree():
     h, _ = core.program_handle(f)
     h0, _ = core.program_handle(S.box(1).bend_radial(1.0, 2.0, 0.5))
     assert core.mixed_tau(h.program, X, X, X) > 30 * core.mixed_tau(h0.program, X, X, X)
+
+
+def test_user_closures_compose_with_the_library_combinators():
+    """README "writing your own SDFs": a tree that holds Python closures evaluates piecewise -- closures on the host, as
+    the reference calls them, combined by the reference's CSG / transform formulas (core._compose_around_closure).
+    Checked against the oracle on the equivalent library tree (all-closure trees need no GPU)."""
+    from oracle import sdf_ref
+    S = sdf_b200
+
+    @S.sdf3
+    def my_sphere(r):
+        def f(p):
+            return np.linalg.norm(p, axis=1) - r
+        return f
+
+    @S.sdf3
+    def my_box(h):
+        def f(p):
+            q = np.abs(p) - h
+            return np.linalg.norm(np.maximum(q, 0), axis=1) + np.minimum(np.max(q, axis=1), 0)
+        return f
+
+    a, b = my_sphere(0.8), my_box(0.6)
+    la, lb = S.sphere(0.8), S.box(1.2)
+    P = models.random_points(2000, seed=5)
+    cases = [
+        (a | b, la | lb), (a & b, la & lb), (a - b, la - lb),
+        (a.union(b, k=0.2), la.union(lb, k=0.2)), (a.difference(b.k(0.15)), la.difference(lb.k(0.15))),
+        (a.intersection(b, k=0.1), la.intersection(lb, k=0.1)), (a.blend(b, k=0.3), la.blend(lb, k=0.3)),
+        (a.negate(), la.negate()), (b.dilate(0.1), lb.dilate(0.1)), (b.erode(0.05), lb.erode(0.05)), (a.shell(0.1), la.shell(0.1)),
+        (b.translate((0.2, -0.1, 0.3)), lb.translate((0.2, -0.1, 0.3))), (b.rotate(0.7, (1, 2, 3)), lb.rotate(0.7, (1, 2, 3))),
+        (b.scale((1.5, 0.5, 2.0)), lb.scale((1.5, 0.5, 2.0))), ((a | b.translate(S.X * 0.5)).orient(S.Y) - a.scale(0.5), (la | lb.translate(S.X * 0.5)).orient(S.Y) - la.scale(0.5)),
+    ]
+    for k, (mine, lib) in enumerate(cases):
+        got = mine(P).reshape(-1)
+        ref = sdf_ref.evaluate(lib, P).reshape(-1)
+        assert np.max(np.abs(got - ref)) <= 1e-12, (k, np.max(np.abs(got - ref)))
+    with pytest.raises(ir.NotLowerableError):
+        a.twist(1.0)(P)                       # a warp above a closure: not one of the composition nodes
+    with pytest.raises(ir.NotLowerableError):
+        ir.lower(a | la)
