@@ -170,7 +170,6 @@ eval_stream_f64_kernel(const __grid_constant__ ProgramImage img, const double* x
 // ---------------------------------------------------------------------------------------
 // host side
 
-static constexpr int kMaxPipe = 16;
 
 struct DeviceCtx {
     int device = -1;
@@ -189,8 +188,9 @@ struct DeviceCtx {
     RoundProgress* progress_dev = nullptr;                          //   (the same memory as the device sees it)
     // the whole device-resident step as one CUDA graph, re-used while every launch parameter stays the same
     cudaStream_t cap_stream = nullptr;
-    cudaGraphExec_t step_exec = nullptr;
-    std::vector<unsigned char> step_key;
+    struct StepGraph { std::vector<unsigned char> key; cudaGraphExec_t exec = nullptr; unsigned long long used = 0; };
+    std::vector<StepGraph> step_graphs;                             // a few recent ones (the multi-GPU cursors ping-pong: two keys alternate)
+    unsigned long long step_clock = 0;
     uint2* cubes = nullptr; size_t cube_cap = 0;
     uint2* pts = nullptr; size_t pt_cap = 0;
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -199,12 +199,21 @@ struct DeviceCtx {
     cudaEvent_t pev[kMaxPipe] = {};
 };
 
-// Rounds the work list is cut into when the triangles go to HOST memory (env SDFB200_PIPE, 1 = one
-// round + one copy at the end).  Read on every call so tests can switch it.
-static int pipe_rounds() {
-    const char* e = getenv("SDFB200_PIPE");
-    const int v = e ? atoi(e) : 8;      // measured (profiles/): 8 rounds <= 4 rounds < 2 < 1 on every configuration
-    return v < 1 ? 1 : (v > kMaxPipe ? kMaxPipe : v);
+static constexpr int kMaxPipe = 16;
+
+// Rounds a call is cut into when the triangles go to HOST memory, so that the triangles of round k cross PCIe
+// while round k+1 computes.  SDFB200_PIPE fixes the number (1 = one round + one copy at the end; read on every
+// call so tests can switch it); by default it follows the expected output size -- every round costs four more
+// latency-bound kernels, which only pays while its copy (36 B per triangle at ~50 GB/s) is longer than that:
+// about one round per 12 MB.  Measured on B200 (profiles/r2_e2e_variants.jsonl): gearlike 512^3, 32 MB: 1 round
+// 0.85 ms, 3 rounds 0.77; blobby 768^3, 77 MB: 2.01 -> 1.73 (4); knurling 1024^3, 212 MB: 5.75 -> 4.43 (8).
+static int pipe_rounds(int64_t expected_triangles) {
+    int v;
+    if (const char* e = getenv("SDFB200_PIPE")) v = atoi(e);
+    else v = (int)((expected_triangles * 36 + (6ll << 20)) / (12ll << 20));
+    const int lo = getenv("SDFB200_PIPE") ? 1 : 2;
+    const int hi = getenv("SDFB200_PIPE") ? kMaxPipe : 8;
+    return v < lo ? lo : (v > hi ? hi : v);
 }
 
 enum JitKernel { JK_SKIP = 0, JK_TILE0 = 1, JK_STREAM_F32 = 5, JK_STREAM_F32_FAST = 6, JK_STREAM_F64 = 7, JK_REFINE = 8, JK_COUNT = 9 };
@@ -858,7 +867,7 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         cudaFree(c.vol); cudaFree(c.tile_meta); cudaFree(c.cubes); cudaFree(c.pts);
         cudaFree(c.scratch); cudaFree(c.mc_tables);
         if (c.progress) cudaFreeHost(c.progress);
-        if (c.step_exec) cudaGraphExecDestroy(c.step_exec);
+        for (auto& sg : c.step_graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
         if (c.cap_stream) cudaStreamDestroy(c.cap_stream);
         for (int i = 0; i < 9; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
         for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
@@ -1117,7 +1126,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
         const unsigned long long upper = (unsigned long long)total_b * g.sub * g.sub * g.sub;
         // Host output: cut the work list into a few rounds so that the triangles of round k cross PCIe
         // while round k+1 is computed (the copy is the longer leg: 36 B per triangle at PCIe speed).
-        int pipe = (tri_out && !out_dev && !stl_out && !ext_cursor && big) ? pipe_rounds() : 1;
+        int pipe = (tri_out && !out_dev && !stl_out && !ext_cursor && big) ? pipe_rounds(tri_capacity) : 1;
         if (upper < 2ull * c->sms) pipe = 1;                      // less than two tiles per SM: nothing to overlap
         // Rounds are cut ON THE DEVICE (round k of `pipe` equal parts of the active tiles, work_range()): the host
         // queues the whole call without knowing how many batches survive the pre-pass.
@@ -1293,26 +1302,37 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         key.k0 = (void*)k_skip; key.k1 = (void*)k_tile; key.k2 = (void*)k_refine;
                         key.flags = c->flags; key.active = c->active; key.bt = c->batch_tris; key.ctr = c->ctr; key.ctrh = c->ctr_host;
                         key.scr = c->scratch;
-                        const bool hit = c->step_exec && c->step_key.size() == sizeof(key) && memcmp(c->step_key.data(), &key, sizeof(key)) == 0;
-                        if (!hit) {
-                            if (c->step_exec) { cudaGraphExecDestroy(c->step_exec); c->step_exec = nullptr; }
-                            c->step_key.clear();
+                        cudaGraphExec_t exec = nullptr;
+                        for (auto& sg : c->step_graphs)
+                            if (sg.exec && sg.key.size() == sizeof(key) && memcmp(sg.key.data(), &key, sizeof(key)) == 0) {
+                                exec = sg.exec; sg.used = ++c->step_clock; break;
+                            }
+                        if (!exec) {
                             cudaGraph_t graph = nullptr;
                             if (cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                                 const int r = enqueue(c->cap_stream, true);
                                 const cudaError_t ee = cudaStreamEndCapture(c->cap_stream, &graph);
-                                if (r == 0 && ee == cudaSuccess && graph &&
-                                    cudaGraphInstantiate(&c->step_exec, graph, 0) == cudaSuccess) {
-                                    c->step_key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
-                                } else {
-                                    c->step_exec = nullptr;
-                                }
+                                if (r != 0 || ee != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
                                 if (graph) cudaGraphDestroy(graph);
                             }
                             cudaGetLastError();          // a failed capture falls back to plain launches below
+                            if (exec) {
+                                constexpr size_t kMaxGraphs = 4;
+                                if (c->step_graphs.size() >= kMaxGraphs) {          // evict the least recently used
+                                    size_t lru = 0;
+                                    for (size_t i = 1; i < c->step_graphs.size(); ++i)
+                                        if (c->step_graphs[i].used < c->step_graphs[lru].used) lru = i;
+                                    cudaGraphExecDestroy(c->step_graphs[lru].exec);
+                                    c->step_graphs.erase(c->step_graphs.begin() + (long)lru);
+                                }
+                                DeviceCtx::StepGraph sg;
+                                sg.key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+                                sg.exec = exec; sg.used = ++c->step_clock;
+                                c->step_graphs.push_back(std::move(sg));
+                            }
                         }
-                        if (c->step_exec) {
-                            CUDA_TRY(cudaGraphLaunch(c->step_exec, stream));
+                        if (exec) {
+                            CUDA_TRY(cudaGraphLaunch(exec, stream));
                             launched = true;
                         }
                     }
@@ -1384,7 +1404,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 if (getenv("SDFB200_DEBUG"))
                     fprintf(stderr, "[sdfb200] n_active=%u n_slots=%u n_cubes=%u n_pts=%u max=%u/%u caps=%u/%u tri=%llu f64=%llu graph=%d\n",
                             h.n_active, h.n_slots, h.n_cubes, h.n_pts, h.max_cubes, h.max_pts, L.cube_cap, L.pt_cap,
-                            h.tri_cursor, h.pts_f64, c->step_exec ? 1 : 0);
+                            h.tri_cursor, h.pts_f64, (int)c->step_graphs.size());
                 if (h.max_cubes <= L.cube_cap && h.max_pts <= L.pt_cap) break;
                 want_cubes = std::max<size_t>(want_cubes, (size_t)h.max_cubes + (h.max_cubes >> 3));
                 want_pts = std::max<size_t>(want_pts, (size_t)h.max_pts + (h.max_pts >> 3));

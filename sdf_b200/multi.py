@@ -214,12 +214,17 @@ class RootGather:
         else:
             n_local, stats, timings = handle.generate_shared(X, Y, Z, batch_size, sparse, precision, tau, self.shared,
                                                              which, zb=zb, device=self.device, stream=stream)
-        dist.barrier(self.group)                          # every peer's kernel (and its NVLink stores) has retired
-        total = self.shared.count(which, stream) if self.rank == 0 else None
+        # ONE collective per step: the sum of the local counts is the total, and its completion is the barrier -- a
+        # rank contributes only after its own kernels (and their NVLink stores into rank 0's buffer) have retired
+        if getattr(self, '_count', None) is None:
+            self._count = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', self.device))
+        self._count.fill_(int(n_local))
+        dist.all_reduce(self._count, group=self.group)
+        total = int(self._count.item())
         self.step += 1
-        if total is not None and total > self.capacity:
+        if total > self.capacity:
             raise RuntimeError('shared triangle buffer too small: %d needed, %d given' % (total, self.capacity))
-        return n_local, stats, timings, total
+        return n_local, stats, timings, (total if self.rank == 0 else None)
 
     def view(self, total):
         """(total, 9) float32 CUDA tensor over the root's buffer (rank 0 only)."""

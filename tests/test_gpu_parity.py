@@ -276,7 +276,10 @@ def test_save_stl_bytes_equal_the_reference_writer(sdf, ref, tmp_path):
     assert np.array_equal(sorted_records(raw[84:]), sorted_records(host.read_bytes()[84:]))
 
 
-def test_opaque_closure_is_callable_but_not_meshable(sdf):
+def test_user_closure_is_callable_and_meshable_but_never_lowered(sdf):
+    """README "writing your own SDFs": a Python closure cannot be lowered to the CUDA evaluator (`ir.lower` raises), yet
+    it stays callable, composes with library shapes, and generate() meshes it batch by batch with marching cubes on the
+    device (tests/test_gpu_closure.py compares that mesh with the library tree's)."""
     @sdf.sdf3
     def my_sphere(r):
         def f(p):
@@ -284,5 +287,10 @@ def test_opaque_closure_is_callable_but_not_meshable(sdf):
         return f
     s = my_sphere(1.0)
     assert abs(float(s(np.array([[2.0, 0, 0]]))[0, 0]) - 1.0) < 1e-15
+    u = s | sdf.sphere(0.5).translate((1.2, 0, 0))
+    from sdf_b200 import ir
     with pytest.raises(sdf.NotLowerableError):
-        (s | sdf.sphere(0.5)).generate(verbose=False)
+        ir.lower(u)
+    assert abs(float(u(np.array([[1.2, 0, 0]]))[0, 0]) + 0.5) < 1e-15          # the library sphere, evaluated on the GPU
+    pts, info = u.generate(step=0.1, bounds=((-1.2, -1.2, -1.2), (1.9, 1.2, 1.2)), verbose=False, return_info=True)
+    assert info['triangles'] > 500 and info['nonempty'] > 0
