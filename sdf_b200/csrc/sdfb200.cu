@@ -171,6 +171,8 @@ eval_stream_f64_kernel(const __grid_constant__ ProgramImage img, const double* x
 // host side
 
 
+static constexpr int kMaxPipe = 16;      // most rounds a pipelined (host output) call is cut into
+
 struct DeviceCtx {
     int device = -1;
     int sms = 0;
@@ -198,8 +200,6 @@ struct DeviceCtx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pev[kMaxPipe] = {};
 };
-
-static constexpr int kMaxPipe = 16;
 
 // Rounds a call is cut into when the triangles go to HOST memory, so that the triangles of round k cross PCIe
 // while round k+1 computes.  SDFB200_PIPE fixes the number (1 = one round + one copy at the end; read on every
@@ -1212,7 +1212,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e));
             if (first) CUDA_TRY(rec(c->ev[5], s, captured));
             if (refine) {
-                const int rgrid = c->sms * 8;
+                const int rgrid = c->sms * env_int("SDFB200_REFINE_BLOCKS", 8);      // (A/B hook; 128-thread CTAs per SM)
                 if (k_refine) {
                     Counters* ctrp = c->ctr;
                     void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
