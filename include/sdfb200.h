@@ -117,22 +117,29 @@ int sdfb200_generate_stl(sdfb200_prog* prog,
                          double timings_ms[8], int device, void* stream);
 
 /*
- * Fused multi-GPU gather (replaces nothing in the reference, which is single process): the ROOT rank
- * creates one triangle buffer + two cursors in its HBM and hands the 64-byte CUDA-IPC handle to the other
- * ranks (any transport; sdf_b200/multi.py uses torch.distributed), which map it.  Every rank then runs
- * sdfb200_generate_shared on its Z-slab: the extraction kernel reserves its output range with a
- * system-scope atomic on the root's cursor `which` and stores its triangles into the root's buffer over
- * NVLink as coalesced peer writes -- no collective follows, only a barrier before the root reads the
- * count.  Cursors ping-pong (`which` = step & 1): the root resets the next step's cursor while the
- * current step runs.  n_tri_local = triangles this rank contributed.
+ * Fused multi-GPU gather (replaces nothing in the reference, which is single process): the ROOT rank creates
+ * two triangle buffers (step parity) + a few flag words in its HBM and hands the 64-byte CUDA-IPC handle to the
+ * other ranks (any transport; sdf_b200/multi.py uses torch.distributed), which map it.  Every rank then runs
+ * sdfb200_generate_window / _shared on its share with `which` = step & 1: its extraction kernel reserves output
+ * ranges with system-scope atomics on the root's cursor and stores its triangles into the root's buffer over NVLink
+ * as coalesced peer writes.  There is NO collective and no host barrier per step -- the ranks meet through flag
+ * words in the root's memory:
+ *   - before a rank's extraction touches the buffer of parity p it waits (on the device) until the root has released
+ *     that buffer for this step (`ready[p]` equals the rank's own step counter for p, kept in its GPU's memory);
+ *   - when all of a rank's triangles are written its extraction kernel adds one to `done[p]`;
+ *   - the root: sdfb200_shared_wait (device wait for done[p] == world, then the triangle count), consume
+ *     sdfb200_shared_buffer(s, p), then sdfb200_shared_release (cursor and done reset, `ready[p]` += 2).
+ * A rank can therefore run at most two steps ahead of the root's consumption and never overwrites data in use.
+ * Waits give up (the kernel traps, the call returns SDFB200_E_CUDA) after about ten seconds.
+ * n_tri_local = triangles this rank contributed.  sdfb200_shared_reset / _count (ABI v1) are gone.
  */
 typedef struct sdfb200_shared sdfb200_shared;
 int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_shared** out, unsigned char handle_out[64]);
 int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_capacity, int device, sdfb200_shared** out);
 void sdfb200_shared_free(sdfb200_shared* s);
-void* sdfb200_shared_buffer(sdfb200_shared* s);
-int sdfb200_shared_reset(sdfb200_shared* s, int which, void* stream);
-int sdfb200_shared_count(sdfb200_shared* s, int which, int64_t* n, void* stream);
+void* sdfb200_shared_buffer(sdfb200_shared* s, int which);
+int sdfb200_shared_wait(sdfb200_shared* s, int which, int world, int64_t* n, void* stream);
+int sdfb200_shared_release(sdfb200_shared* s, int which, void* stream);
 int sdfb200_generate_shared(sdfb200_prog* prog,
                             const double* xs, int64_t nx, const double* ys, int64_t ny, const double* zs, int64_t nz,
                             int batch_size, int sparse, int precision, double tau, int zb_begin, int zb_end,

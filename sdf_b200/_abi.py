@@ -20,7 +20,7 @@ EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
            'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
            'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
-           'sdfb200_shared_reset', 'sdfb200_shared_count', 'sdfb200_generate_shared', 'sdfb200_generate_window', 'sdfb200_mc_volume', 'sdfb200_weld']
+           'sdfb200_shared_wait', 'sdfb200_shared_release', 'sdfb200_generate_shared', 'sdfb200_generate_window', 'sdfb200_mc_volume', 'sdfb200_weld']
 
 
 class SdfB200Error(RuntimeError):
@@ -68,10 +68,10 @@ def lib():
     L.sdfb200_shared_open.argtypes = [vp, i64, i32, ctypes.POINTER(vp)]
     L.sdfb200_shared_free.argtypes = [vp]
     L.sdfb200_shared_free.restype = None
-    L.sdfb200_shared_buffer.argtypes = [vp]
+    L.sdfb200_shared_buffer.argtypes = [vp, i32]
     L.sdfb200_shared_buffer.restype = vp
-    L.sdfb200_shared_reset.argtypes = [vp, i32, vp]
-    L.sdfb200_shared_count.argtypes = [vp, i32, ctypes.POINTER(i64), vp]
+    L.sdfb200_shared_wait.argtypes = [vp, i32, i32, ctypes.POINTER(i64), vp]
+    L.sdfb200_shared_release.argtypes = [vp, i32, vp]
     L.sdfb200_generate_shared.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i32, i32,
                                           vp, i32, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_generate_window.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl, i64, i64,
@@ -162,8 +162,8 @@ pinned_pool = PinnedPool()
 
 
 class SharedOutput:
-    """One triangle buffer in the root GPU's memory that every rank's extraction kernel writes into
-    (include/sdfb200.h "fused multi-GPU gather").  ``handle`` (64 bytes) is what the root broadcasts."""
+    """Two triangle buffers (step parity) + flag words in the root GPU's memory that every rank's extraction kernel
+    writes into (include/sdfb200.h "fused multi-GPU gather").  ``handle`` (64 bytes) is what the root broadcasts."""
 
     def __init__(self, capacity, device, handle=None):
         self._h = ctypes.c_void_p()
@@ -182,16 +182,19 @@ class SharedOutput:
         if h and _lib is not None:
             _lib.sdfb200_shared_free(h)
 
-    def buffer_ptr(self):
-        return lib().sdfb200_shared_buffer(self._h)
+    def buffer_ptr(self, which):
+        return lib().sdfb200_shared_buffer(self._h, int(which))
 
-    def reset(self, which, stream=None):
-        _check(lib().sdfb200_shared_reset(self._h, which, stream))
-
-    def count(self, which, stream=None):
+    def wait(self, which, world, stream=None):
+        """Root only: device-side wait until all ``world`` ranks have delivered the step of parity ``which``;
+        returns the triangle count (synchronises ``stream``)."""
         n = ctypes.c_int64(0)
-        _check(lib().sdfb200_shared_count(self._h, which, ctypes.byref(n), stream))
+        _check(lib().sdfb200_shared_wait(self._h, int(which), int(world), ctypes.byref(n), stream))
         return n.value
+
+    def release(self, which, stream=None):
+        """Root only: the buffer of parity ``which`` has been consumed; hands it to the step after next."""
+        _check(lib().sdfb200_shared_release(self._h, int(which), stream))
 
 
 class ProgramHandle:

@@ -1064,7 +1064,8 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
                                              unsigned long long* __restrict__ ext_cursor,
                                              const McTablesSmem* __restrict__ tables,
                                              const unsigned char* __restrict__ stats_flags,
-                                             RoundProgress* __restrict__ progress) {
+                                             RoundProgress* __restrict__ progress,
+                                             unsigned long long* __restrict__ done_signal) {
     __shared__ __align__(128) ExtractSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     load_mc_tables_async(&sm.mc, tables, &sm.tables_bar, tid);
@@ -1190,8 +1191,9 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
         atomicMax(&ctr->max_pts, ctr->n_pts);
     }
     if (!tables_ready) mbar_wait(&sm.tables_bar, 0u);          // never leave with a bulk copy in flight
-    if (stats_flags != nullptr || progress != nullptr) {
-        __threadfence();                                       // this CTA's batch_tris flags / triangles are visible device wide
+    if (stats_flags != nullptr || progress != nullptr || done_signal != nullptr) {
+        // this CTA's batch_tris flags / triangles are visible device wide -- system wide when they went to a peer GPU
+        if (done_signal != nullptr) __threadfence_system(); else __threadfence();
         __syncthreads();
         if (tid == 0) {
             const unsigned int done = atomicAdd(&ctr->extract_done, 1u);
@@ -1205,6 +1207,11 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             progress->max_pts = *((volatile unsigned int*)&ctr->max_pts);
             __threadfence_system();
             *((volatile unsigned int*)&progress->done) = 1u;
+        }
+        if (sm.last_cta && done_signal != nullptr && tid == 0) {
+            // fused multi-GPU gather: every triangle of this rank is in the root's buffer -- tell the root
+            __threadfence_system();
+            atomicAdd_system(done_signal, 1ull);
         }
         if (sm.last_cta && stats_flags != nullptr) {
             __threadfence();
@@ -1220,6 +1227,48 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             for (int o = 16; o > 0; o >>= 1) { ne += __shfl_xor_sync(0xffffffffu, ne, o); nn += __shfl_xor_sync(0xffffffffu, nn, o); }
             if (lane == 0) { if (ne) atomicAdd(&ctr->empty, ne); if (nn) atomicAdd(&ctr->nonempty, nn); }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fused multi-GPU gather: flags in the ROOT GPU's memory instead of a collective per step.
+//   ready[p]   sequence number of the step that may use buffer / cursor p (root: += 2 after it has consumed the buffer)
+//   done[p]    ranks whose triangles of the current step are all in buffer p (every rank's extraction tail: += 1)
+// A rank's step s (p = s & 1) waits for ready[p] == s before its extraction touches the shared cursor; the root
+// waits for done[p] == world before it reads the count.  No NCCL call, no host barrier: a rank only synchronises
+// with its own stream.  Spins give up (trap) after ~10 s so that a dead peer cannot hang the box.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void spin_until_equal(const unsigned long long* p, unsigned long long want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(p) != want) {
+        __nanosleep(256);
+        if (clock64() - t0 > 20000000000ll) __trap();          // ~10 s at 2 GHz
+    }
+}
+
+__device__ __forceinline__ void shared_wait_ready_body(const unsigned long long* ready, unsigned long long* my_seq) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long s = *my_seq;
+        spin_until_equal(ready, s);
+        *my_seq = s + 2ull;
+    }
+}
+
+__device__ __forceinline__ void shared_wait_done_body(const unsigned long long* done, unsigned long long world) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) spin_until_equal(done, world);
+}
+
+__device__ __forceinline__ void shared_release_body(unsigned long long* cursor, unsigned long long* done, unsigned long long* ready) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *cursor = 0ull;
+        *done = 0ull;
+        __threadfence_system();
+        atomicAdd_system(ready, 2ull);
     }
 }
 

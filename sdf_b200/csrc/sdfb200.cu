@@ -120,8 +120,14 @@ template <int TS>
 __global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_BLOCKS_PER_SM)
 extract_kernel(const GridDesc g, const TileLists L, Counters* ctr, unsigned int* batch_tris, float* tri_out,
                const unsigned long long tri_capacity, unsigned long long* ext_cursor, const McTablesSmem* tables,
-               const unsigned char* stats_flags, RoundProgress* progress) {
-    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags, progress);
+               const unsigned char* stats_flags, RoundProgress* progress, unsigned long long* done_signal) {
+    extract_body<TS>(g, L, ctr, batch_tris, tri_out, tri_capacity, ext_cursor, tables, stats_flags, progress, done_signal);
+}
+
+__global__ void shared_wait_ready_kernel(const unsigned long long* ready, unsigned long long* my_seq) { shared_wait_ready_body(ready, my_seq); }
+__global__ void shared_wait_done_kernel(const unsigned long long* done, unsigned long long world) { shared_wait_done_body(done, world); }
+__global__ void shared_release_kernel(unsigned long long* cursor, unsigned long long* done, unsigned long long* ready) {
+    shared_release_body(cursor, done, ready);
 }
 
 // Candidate cubes of ONE dense user volume (sdfb200_mc_volume): the volume sits in tile slot 0 in its own C-order
@@ -1052,6 +1058,14 @@ static cudaError_t prepare_tile_eval(int precision) {
 
 static const size_t kVolBudgetBytes = (size_t)24 << 30;      // tile volumes kept per round
 
+// the shared (root GPU) words a step of the fused multi-GPU gather works with
+struct SharedStep {
+    unsigned long long* cursor = nullptr;      // output ranges are reserved here (system-scope atomics)
+    unsigned long long* done = nullptr;        // += 1 when all of this rank's triangles are written
+    const unsigned long long* ready = nullptr; // == this rank's sequence number when the buffer may be used
+    unsigned long long* my_seq = nullptr;      // this rank's sequence number for the cursor (device memory of THIS GPU)
+};
+
 static bool graph_enabled() {
     const char* e = getenv("SDFB200_GRAPH");
     return e ? atoi(e) != 0 : true;
@@ -1069,8 +1083,9 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                          const double* zs, int64_t nz, int batch_size, int sparse, int precision, double tau_,
                          int zb_begin, int zb_end, float* tri_out, int64_t tri_capacity, int64_t* n_tri,
                          int64_t stats[6], double timings_ms[8], int device, void* stream_, unsigned char* stl_out,
-                         unsigned long long* ext_cursor = nullptr, int64_t ub_begin = -1, int64_t ub_end = -1) {
+                         const SharedStep* shared = nullptr, int64_t ub_begin = -1, int64_t ub_end = -1) {
     if (!prog || !n_tri) return fail(SDFB200_E_INVALID, "generate: NULL argument");
+    unsigned long long* const ext_cursor = shared ? shared->cursor : nullptr;
     if (precision < 0 || precision > 3) return fail(SDFB200_E_INVALID, "generate: precision %d", precision);
     if (tri_capacity < 0) return fail(SDFB200_E_INVALID, "generate: negative capacity");
     std::lock_guard<std::mutex> guard(prog->lock);
@@ -1223,8 +1238,13 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 }
             }
             if (first) CUDA_TRY(rec(c->ev[6], s, captured));
+            if (shared && first) {            // the shared buffer of this step's parity is free (the root has consumed its last use)
+                shared_wait_ready_kernel<<<1, 32, 0, s>>>(shared->ready, shared->my_seq);
+                CUDA_TRY(cudaGetLastError());
+            }
             extract_kernel<kTS><<<c->sms * EXTRACT_BLOCKS_PER_SM, EXTRACT_THREADS, 0, s>>>(
-                g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor, c->mc_tables, last ? c->flags : nullptr, progress);
+                g, L, c->ctr, c->batch_tris, dtri, cap, ext_cursor, c->mc_tables, last ? c->flags : nullptr, progress,
+                (shared && last) ? shared->done : nullptr);
             CUDA_TRY(cudaGetLastError());
             if (first) CUDA_TRY(rec(c->ev[7], s, captured));
             return 0;
@@ -1258,6 +1278,8 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                 L.vol = c->vol; L.tile_meta = c->tile_meta; L.cubes = c->cubes; L.pts = c->pts;
                 L.slot_cap = round; L.cube_cap = (unsigned int)std::min<size_t>(c->cube_cap, 0xffffffffu);
                 L.pt_cap = (unsigned int)std::min<size_t>(c->pt_cap, 0xffffffffu);
+                if (attempt > 0 && shared)
+                    return fail(SDFB200_E_CUDA, "work lists overflowed in a shared (multi-GPU) call: size them with a count-only pass of the same window first");
                 if (attempt > 0) {      // redo from a clean slate (the pre-pass results stay valid)
                     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
                     copied = 0;
@@ -1295,9 +1317,11 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                     if (graph_enabled() && attempt == 0) {
                         // key: every value the launches above depend on
                         struct { GridDesc g; TileLists L; float tau; int sparse, precision, tail; float* dtri; unsigned long long cap, n_work;
-                                 unsigned long long* ext; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr; } key;
+                                 unsigned long long* ext; const void *sh1, *sh2, *sh3; void *k0, *k1, *k2; void *flags, *active, *bt, *ctr, *ctrh, *scr; } key;
                         memset(&key, 0, sizeof(key));
                         key.g = g; key.L = L; key.tau = tau; key.sparse = sparse; key.precision = precision; key.tail = tail ? 1 : 0;
+                        key.sh1 = shared ? (const void*)shared->done : nullptr; key.sh2 = shared ? (const void*)shared->ready : nullptr;
+                        key.sh3 = shared ? (const void*)shared->my_seq : nullptr;
                         key.dtri = dtri; key.cap = cap; key.n_work = n_work * 64ull + (unsigned long long)pipe; key.ext = ext_cursor;
                         key.k0 = (void*)k_skip; key.k1 = (void*)k_tile; key.k2 = (void*)k_refine;
                         key.flags = c->flags; key.active = c->active; key.bt = c->batch_tris; key.ctr = c->ctr; key.ctrh = c->ctr_host;
@@ -1486,11 +1510,23 @@ extern "C" int sdfb200_generate_stl(sdfb200_prog* prog, const double* xs, int64_
 // address spaces with CUDA IPC, written by their extraction kernels over NVLink (sdfb200_generate_shared)
 
 struct sdfb200_shared {
-    unsigned char* base = nullptr;      // [0,256): two cursors (ping-pong); [256, ...): triangles
+    unsigned char* base = nullptr;      // [0,256): header words; then TWO triangle buffers of `capacity` (step parity)
+    unsigned long long* my_seq = nullptr;      // this process' sequence numbers for the two parities (its own GPU's memory)
     int64_t capacity = 0;
     int device = -1;
     bool owner = false;
 };
+
+// header: cursor[2] @ 0, done[2] @ 16, ready[2] @ 32 (unsigned long long each)
+static unsigned long long* shared_word(sdfb200_shared* s, int field, int which) { return (unsigned long long*)(s->base + 16 * field + 8 * which); }
+static float* shared_data(sdfb200_shared* s, int which) { return (float*)(s->base + 256 + (size_t)which * (size_t)s->capacity * 36); }
+
+static int shared_init_seq(sdfb200_shared* s) {
+    CUDA_TRY(cudaMalloc(&s->my_seq, 2 * sizeof(unsigned long long)));
+    const unsigned long long init[2] = {0ull, 1ull};
+    CUDA_TRY(cudaMemcpy(s->my_seq, init, sizeof(init), cudaMemcpyHostToDevice));
+    return 0;
+}
 
 extern "C" int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_shared** out, unsigned char handle_out[64]) {
     if (!out || !handle_out || tri_capacity <= 0) return fail(SDFB200_E_INVALID, "shared_create: bad argument");
@@ -1498,9 +1534,11 @@ extern "C" int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_s
     CUDA_TRY(cudaSetDevice(device));
     std::unique_ptr<sdfb200_shared> s(new (std::nothrow) sdfb200_shared());
     if (!s) return fail(SDFB200_E_INVALID, "out of host memory");
-    CUDA_TRY(cudaMalloc(&s->base, 256 + (size_t)tri_capacity * 36));
+    CUDA_TRY(cudaMalloc(&s->base, 256 + 2 * (size_t)tri_capacity * 36));
     cudaIpcMemHandle_t h;
-    cudaError_t e = cudaMemset(s->base, 0, 256);
+    unsigned long long header[32] = {0};
+    header[4] = 0ull; header[5] = 1ull;                  // ready[0] = 0, ready[1] = 1: steps 0 and 1 may start
+    cudaError_t e = cudaMemcpy(s->base, header, 256, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, s->base);
     if (e != cudaSuccess) {
         cudaFree(s->base);
@@ -1508,6 +1546,7 @@ extern "C" int sdfb200_shared_create(int64_t tri_capacity, int device, sdfb200_s
     }
     memcpy(handle_out, &h, 64);
     s->capacity = tri_capacity; s->device = device; s->owner = true;
+    int rc = shared_init_seq(s.get()); if (rc) { cudaFree(s->base); return rc; }
     *out = s.release();
     return 0;
 }
@@ -1522,6 +1561,7 @@ extern "C" int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_c
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->base = (unsigned char*)p; s->capacity = tri_capacity; s->device = device; s->owner = false;
+    int rc = shared_init_seq(s.get()); if (rc) { cudaIpcCloseMemHandle(p); return rc; }
     *out = s.release();
     return 0;
 }
@@ -1529,29 +1569,43 @@ extern "C" int sdfb200_shared_open(const unsigned char handle[64], int64_t tri_c
 extern "C" void sdfb200_shared_free(sdfb200_shared* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    cudaFree(s->my_seq);
     if (s->owner) cudaFree(s->base); else cudaIpcCloseMemHandle(s->base);
     delete s;
 }
 
-extern "C" void* sdfb200_shared_buffer(sdfb200_shared* s) { return s ? (void*)(s->base + 256) : nullptr; }
-
-// owner only: zero cursor `which` (0/1) for a coming step
-extern "C" int sdfb200_shared_reset(sdfb200_shared* s, int which, void* stream) {
-    if (!s || !s->owner || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "shared_reset: bad argument");
-    CUDA_TRY(cudaSetDevice(s->device));
-    CUDA_TRY(cudaMemsetAsync(s->base + 8 * which, 0, 8, (cudaStream_t)stream));
-    return 0;
+extern "C" void* sdfb200_shared_buffer(sdfb200_shared* s, int which) {
+    return (s && which >= 0 && which <= 1) ? (void*)shared_data(s, which) : nullptr;
 }
 
-// owner only: triangles accumulated under cursor `which` (synchronises `stream`)
-extern "C" int sdfb200_shared_count(sdfb200_shared* s, int which, int64_t* n, void* stream) {
-    if (!s || !s->owner || !n || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "shared_count: bad argument");
+// owner only: wait (on the device) until all `world` ranks have delivered the triangles of the step that uses parity
+// `which`, then read their number (synchronises `stream`)
+extern "C" int sdfb200_shared_wait(sdfb200_shared* s, int which, int world, int64_t* n, void* stream) {
+    if (!s || !s->owner || !n || which < 0 || which > 1 || world < 1) return fail(SDFB200_E_INVALID, "shared_wait: bad argument");
     CUDA_TRY(cudaSetDevice(s->device));
+    shared_wait_done_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(shared_word(s, 1, which), (unsigned long long)world);
+    CUDA_TRY(cudaGetLastError());
     unsigned long long v = 0;
-    CUDA_TRY(cudaMemcpyAsync(&v, s->base + 8 * which, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpyAsync(&v, shared_word(s, 0, which), 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     *n = (int64_t)v;
     return 0;
+}
+
+// owner only: the buffer of parity `which` has been consumed -- reset its cursor and hand it to the step after next
+extern "C" int sdfb200_shared_release(sdfb200_shared* s, int which, void* stream) {
+    if (!s || !s->owner || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "shared_release: bad argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    shared_release_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(shared_word(s, 0, which), shared_word(s, 1, which), shared_word(s, 2, which));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static SharedStep shared_step(sdfb200_shared* dst, int which) {
+    SharedStep st;
+    st.cursor = shared_word(dst, 0, which); st.done = shared_word(dst, 1, which); st.ready = shared_word(dst, 2, which);
+    st.my_seq = dst->my_seq + which;
+    return st;
 }
 
 extern "C" int sdfb200_generate_shared(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
@@ -1559,9 +1613,9 @@ extern "C" int sdfb200_generate_shared(sdfb200_prog* prog, const double* xs, int
                                        int zb_begin, int zb_end, sdfb200_shared* dst, int which, int64_t* n_tri_local,
                                        int64_t stats[6], double timings_ms[8], int device, void* stream) {
     if (!dst || which < 0 || which > 1) return fail(SDFB200_E_INVALID, "generate_shared: bad argument");
+    const SharedStep st = shared_step(dst, which);
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, zb_begin, zb_end,
-                         (float*)(dst->base + 256), dst->capacity, n_tri_local, stats, timings_ms, device, stream, nullptr,
-                         (unsigned long long*)(dst->base + 8 * which));
+                         shared_data(dst, which), dst->capacity, n_tri_local, stats, timings_ms, device, stream, nullptr, &st);
 }
 
 extern "C" int sdfb200_generate_window(sdfb200_prog* prog, const double* xs, int64_t nx, const double* ys, int64_t ny,
@@ -1572,9 +1626,10 @@ extern "C" int sdfb200_generate_window(sdfb200_prog* prog, const double* xs, int
     if (ub_begin < 0 || ub_end < ub_begin) return fail(SDFB200_E_INVALID, "generate_window: bad window");
     if (dst) {
         if (which < 0 || which > 1) return fail(SDFB200_E_INVALID, "generate_window: bad cursor");
+        const SharedStep st = shared_step(dst, which);
         return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1,
-                             (float*)(dst->base + 256), dst->capacity, n_tri, stats, timings_ms, device, stream, nullptr,
-                             (unsigned long long*)(dst->base + 8 * which), ub_begin, ub_end);
+                             shared_data(dst, which), dst->capacity, n_tri, stats, timings_ms, device, stream, nullptr, &st,
+                             ub_begin, ub_end);
     }
     return generate_impl(prog, xs, nx, ys, ny, zs, nz, batch_size, sparse, precision, tau, 0, -1, tri_out, tri_capacity,
                          n_tri, stats, timings_ms, device, stream, nullptr, nullptr, ub_begin, ub_end);
@@ -1622,7 +1677,7 @@ extern "C" int sdfb200_mc_volume(sdfb200_prog* prog, const float* volume, int64_
         dtri = (float*)c->stage;
     }
     extract_kernel<kTS><<<std::min(c->sms, (ncubes + EXTRACT_THREADS - 1) / EXTRACT_THREADS), EXTRACT_THREADS, 0, stream>>>(
-        g, L, c->ctr, c->batch_tris, dtri, tri_out ? (unsigned long long)tri_capacity : 0ull, nullptr, c->mc_tables, nullptr, nullptr);
+        g, L, c->ctr, c->batch_tris, dtri, tri_out ? (unsigned long long)tri_capacity : 0ull, nullptr, c->mc_tables, nullptr, nullptr, nullptr);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));

@@ -171,16 +171,19 @@ def allgather_triangles(local, group=None, compact=True):
 
 
 class RootGather:
-    """Fused gather to rank 0 (the B200 path): the extraction kernels of all ranks write into one buffer
-    in rank 0's HBM over NVLink (CUDA-IPC mapped, system-scope atomic cursor); no collective moves
-    triangles.  Per step: ``run()`` on every rank, then ONE barrier; rank 0 then owns ``total`` triangles
-    at ``view()``.  Two cursors ping-pong so that the reset of the next step's cursor is off the path."""
+    """Fused gather to rank 0 (the B200 path): the extraction kernels of all ranks write into a buffer in rank 0's
+    HBM over NVLink (CUDA-IPC mapped, system-scope atomic cursor); no collective moves triangles and NO collective or
+    host barrier synchronises a step -- the ranks meet through flag words in rank 0's memory (include/sdfb200.h):
+    a rank's extraction waits on the device until rank 0 has released the buffer of the step's parity, and signals
+    when its triangles are in; rank 0 waits on the device for all signals, reads the count, consumes ``view(total)``
+    and releases the buffer.  Two buffers ping-pong, so ranks run at most two steps ahead of rank 0's consumption."""
 
     def __init__(self, capacity, device, group=None):
         import torch.distributed as dist
         from . import _abi
         self.group, self.device = group, device
         self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
         self.capacity = int(capacity)
         box = [None]
         if self.rank == 0:
@@ -190,46 +193,41 @@ class RootGather:
         if self.rank != 0:
             self.shared = _abi.SharedOutput(self.capacity, device, handle=box[0])
         self.step = 0
-        if self.rank == 0:
-            self.shared.reset(0)
-            self.shared.reset(1)
-        dist.barrier(group)
+        self.last = None
+        dist.barrier(group)                               # (set-up only) every rank has the buffer mapped
 
-    def run(self, handle, X, Y, Z, batch_size, sparse, precision, tau, zb, stream=None, window=None):
+    def run(self, handle, X, Y, Z, batch_size, sparse, precision, tau, zb, stream=None, window=None, release=True):
         """One step on this rank (its Z-slab ``zb`` of whole layers, or its ``window`` of the Z-major batch order);
-        returns (n_local, stats, timings, total) -- total only on rank 0.
-
-        Contract: rank 0 must be done with ``view(total)`` of step N before any rank enters ``run`` of step
-        N + 1 -- the triangle region is not double-buffered, only the cursors are (``generate_distributed``
-        copies the view out and synchronises before it returns; a caller that keeps the view must add its own
-        barrier)."""
-        import torch
-        import torch.distributed as dist
+        returns (n_local, stats, timings, total) -- total only on rank 0.  ``release=False``: rank 0 keeps the
+        step's buffer (``view(total)``) until it calls ``release()`` itself."""
         which = self.step & 1
-        if self.rank == 0:
-            self.shared.reset(which ^ 1, stream)          # next step's cursor: nobody touches it now
         if window is not None:
             n_local, stats, timings = handle.generate_window(X, Y, Z, batch_size, sparse, precision, tau, window,
                                                              shared=self.shared, which=which, device=self.device, stream=stream)
         else:
             n_local, stats, timings = handle.generate_shared(X, Y, Z, batch_size, sparse, precision, tau, self.shared,
                                                              which, zb=zb, device=self.device, stream=stream)
-        # ONE collective per step: the sum of the local counts is the total, and its completion is the barrier -- a
-        # rank contributes only after its own kernels (and their NVLink stores into rank 0's buffer) have retired
-        if getattr(self, '_count', None) is None:
-            self._count = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', self.device))
-        self._count.fill_(int(n_local))
-        dist.all_reduce(self._count, group=self.group)
-        total = int(self._count.item())
+        total = None
+        if self.rank == 0:
+            total = self.shared.wait(which, self.world, stream)           # device-side wait for every rank's signal
+            if total > self.capacity:
+                raise RuntimeError('shared triangle buffer too small: %d needed, %d given' % (total, self.capacity))
+            self.last = which
+            if release:
+                self.release(stream)
         self.step += 1
-        if total > self.capacity:
-            raise RuntimeError('shared triangle buffer too small: %d needed, %d given' % (total, self.capacity))
-        return n_local, stats, timings, (total if self.rank == 0 else None)
+        return n_local, stats, timings, total
+
+    def release(self, stream=None):
+        """Rank 0: done with the buffer of the last step (its cursor is reset, the step after next may use it)."""
+        if self.rank == 0 and self.last is not None:
+            self.shared.release(self.last, stream)
+            self.last = None
 
     def view(self, total):
-        """(total, 9) float32 CUDA tensor over the root's buffer (rank 0 only)."""
+        """(total, 9) float32 CUDA tensor over the buffer of the last step (rank 0 only, before ``release()``)."""
         import torch
-        ptr = self.shared.buffer_ptr()
+        ptr = self.shared.buffer_ptr(self.last)
         iface = {'shape': (int(total), 9), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
         holder = type('CudaView', (), {'__cuda_array_interface__': iface})()
         return torch.as_tensor(holder, device=torch.device('cuda', self.device))
@@ -275,7 +273,7 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
         stream = torch.cuda.current_stream(dev).cuda_stream
         rg = _root_gather(need, dev, group)          # sized from the all-reduced per-rank counts of THIS lattice and plan
         n_local, stats, timings, total = rg.run(h, Xc, Yc, Zc, batch_size, sparse, precision, tau, zb,
-                                                stream=stream, window=window)
+                                                stream=stream, window=window, release=False)
         info = dict(triangles=n_local, skipped=int(stats[0]), empty=int(stats[1]), nonempty=int(stats[2]),
                     evaluated=int(stats[3]), refined=int(stats[4]), active_cubes=int(stats[5]), zb=mine, rank=rank,
                     world=world, triangles_total=total, partition=partition)
@@ -283,6 +281,7 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
             return np.zeros((0, 3), np.float32), info
         t, arr = _pinned.take(total * 9)
         t[:total * 9].copy_(rg.view(total).reshape(-1), non_blocking=True)
+        rg.release(stream)                                # (stream order: after the copy out of the shared buffer)
         torch.cuda.current_stream(dev).synchronize()
         return arr[:total * 9].reshape(-1, 3), info
     if compute is not None:
