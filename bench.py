@@ -317,23 +317,29 @@ class DeviceSeries:
             dist.all_reduce(needs)
             self.root_gather = multi.RootGather(int(needs.item() * 1.05) + 65536, self.local)
 
-    def rebalance(self):
-        """One measured re-plan: three untimed steps, per-rank device time of the pipeline, windows re-cut so that
-        batches in costlier regions weigh more (multi.plan_windows rates)."""
+    def rebalance(self, rounds=4, tolerance=1.04):
+        """Measured re-plan (at most ``rounds`` times): three untimed steps, per-rank device time of the step, windows
+        re-cut with the batches of slower ranks weighing more (multi.reweigh) until max/min <= ``tolerance``."""
         torch, dist = self.torch, self.dist
         from sdf_b200 import multi
         X, Y, Z = self.axes
-        ms = []
-        for _ in range(3):
-            _, _, timings, _ = self.step()
-            ms.append(float(timings[2]))
-        mine = torch.tensor([sorted(ms)[1]], dtype=torch.float64, device='cuda')
-        allt = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(allt, mine)
-        seconds = [float(t.item()) * 1e-3 for t in allt]
-        self.first_plan, self.first_plan_ms = self.plan, [t * 1e3 for t in seconds]
-        self.plan = multi.plan_windows(self.f, X, Y, Z, BATCH, self.world, device=self.local, rates=(self.plan, seconds))
-        self._size_buffers()
+        weights = multi.batch_weights(self.f, X, Y, Z, BATCH, device=self.local)
+        self.replans = []
+        for _ in range(rounds):
+            ms = []
+            for _ in range(3):
+                _, _, timings, _ = self.step()
+                ms.append(float(timings[2]))
+            mine = torch.tensor([sorted(ms)[1]], dtype=torch.float64, device='cuda')
+            allt = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allt, mine)
+            seconds = [float(t.item()) * 1e-3 for t in allt]
+            self.replans.append([round(t * 1e3, 4) for t in seconds])
+            if max(seconds) <= tolerance * min(seconds):
+                break
+            weights = multi.reweigh(weights, self.plan, seconds)
+            self.plan = multi.plan_windows(self.f, X, Y, Z, BATCH, self.world, device=self.local, weights=weights)
+            self._size_buffers()
 
     def step(self):
         torch, args = self.torch, self.args
@@ -386,14 +392,17 @@ class DeviceSeries:
         t_min = t_max.clone()
         agg = torch.tensor([float(n_tri), float(stats_acc[3]), float(stats_acc[4]), float(stats_acc[5]),
                             float(stats_acc[0]), float(stats_acc[1]), float(stats_acc[2])], dtype=torch.float64, device='cuda')
+        kmax = torch.tensor([sum(k[i] for k in kern_ms) / steps for i in range(4)] + [sum(prepass_ms) / steps], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
             dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
             dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
         return dict(ms_per_step=float(t_max[0].item()), fused_ms=float(t_max[1].item()), tile_ms=float(t_max[2].item()),
                     per_rank_min=dict(step_ms=float(t_min[0].item()), pipeline_ms=float(t_min[1].item()), tile_ms=float(t_min[2].item())),
                     per_rank_max=dict(step_ms=float(t_max[0].item()), pipeline_ms=float(t_max[1].item()), tile_ms=float(t_max[2].item())),
                     agg=[float(v) for v in agg.tolist()], prepass_ms=sum(prepass_ms) / steps,
+                    kern_max=dict(zip(('sign_eval', 'refine', 'extract', 'classify', 'prepass+setup'), [float(v) for v in kmax.tolist()])),
                     kern_ms=[sum(k[i] for k in kern_ms) / steps for i in range(4)],
                     gather_ms=(sum(gather_ms) / len(gather_ms)) if gather_ms else None, t0=t0, t1=t1)
 
@@ -498,7 +507,7 @@ def run_ours(args):
                   'mtris_per_s': rs['agg'][0] / (rs['ms_per_step'] / 1e3) / 1e6, 'triangles': int(rs['agg'][0]),
                   'per_rank_min_ms': rs['per_rank_min'], 'per_rank_max_ms': rs['per_rank_max'],
                   'windows': [list(p) for p in ss.plan] if ss.plan else None,
-                  'first_plan_per_rank_ms': getattr(ss, 'first_plan_ms', None)}
+                  'replans_per_rank_ms': getattr(ss, 'replans', None), 'kernel_ms_max_over_ranks': rs['kern_max']}
         del ss
 
     if rank == 0:
@@ -533,7 +542,7 @@ def run_ours(args):
                        'points': n_points, 'precision': args.precision,
                        'l2': 'flushed between timed iterations (768 MB memset, outside the per-step events)',
                        'parallelism': 'z-slab x%d (windows of the Z-major batch order, balanced by active batches%s)' % (
-                           world, ', one measured re-plan' if (world > 1 and not args.no_rebalance) else ''),
+                           world, ', measured re-plans' if (world > 1 and not args.no_rebalance) else ''),
                        'gather': (args.gather if world > 1 else None),
                        'sample_grouping': dict(zip(('share_axis', 'samples_per_thread', 'invariant_fraction'),
                                                    h.jit_plan({'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}[args.precision]))),

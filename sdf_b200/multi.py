@@ -70,24 +70,34 @@ def zmajor_active(flags):
     return (np.asarray(flags) == 0).transpose(2, 0, 1).reshape(-1)
 
 
-def plan_windows(sdf, X, Y, Z, batch_size, world, device=None, rates=None):
-    """Run the skip pre-pass for the whole lattice and return the per-rank windows of the Z-major batch order,
-    balanced by non-skipped batches.  ``rates`` (optional, one per rank of a previous plan given as
-    ``(windows, seconds)``): measured time per active batch of each old window -- batches in costlier
-    regions (more surface per batch) then weigh more, so a second plan evens out what the first one measured."""
+def batch_weights(sdf, X, Y, Z, batch_size, device=None):
+    """Per batch, in Z-major order: 1 for a non-skipped batch, 0 for a skipped one (the full-lattice pre-pass)."""
     h, _ = core.program_handle(sdf)
     dev = core.default_device() if device is None else device
     flags = h.skip_flags(np.ascontiguousarray(X, np.float64), np.ascontiguousarray(Y, np.float64),
                          np.ascontiguousarray(Z, np.float64), batch_size, device=dev)
-    w = zmajor_active(flags).astype(np.float64)
-    if rates is not None:
-        old, seconds = rates
-        for (u0, u1), t in zip(old, seconds):
-            act = w[u0:u1].sum()
-            if act > 0 and t > 0:
-                w[u0:u1] *= t / act
-        w *= len(w) / max(w.sum(), 1e-30)
-    return partition_windows(w, world)
+    return zmajor_active(flags).astype(np.float64)
+
+
+def reweigh(weights, windows, seconds):
+    """Measured re-plan: the batches of a window that took longer than the mean weigh more, the others less (the
+    cost of a batch depends on how much surface it holds, which the pre-pass cannot see).  Applied repeatedly the
+    windows converge to equal measured times."""
+    w = np.array(weights, dtype=np.float64)
+    t = np.asarray(seconds, dtype=np.float64)
+    mean = t.mean() if t.mean() > 0 else 1.0
+    for (u0, u1), tr in zip(windows, t):
+        if u1 > u0 and tr > 0:
+            w[u0:u1] *= tr / mean
+    return w
+
+
+def plan_windows(sdf, X, Y, Z, batch_size, world, device=None, weights=None):
+    """The per-rank windows of the Z-major batch order: balanced by non-skipped batches (a skip pre-pass over the
+    whole lattice), or by the given per-batch ``weights`` (``batch_weights`` refined by ``reweigh``)."""
+    if weights is None:
+        weights = batch_weights(sdf, X, Y, Z, batch_size, device)
+    return partition_windows(weights, world)
 
 
 class _PinnedTorchPool:

@@ -131,3 +131,22 @@ def test_partition_windows_balances_active_batches():
     flags = np.zeros((4, 3, 2), np.uint8)
     flags[1, 2, 0] = 1
     assert list(np.nonzero(~multi.zmajor_active(flags))[0]) == [1 * 3 + 2]
+
+
+def test_measured_replans_converge_to_equal_times():
+    """multi.reweigh: windows re-cut from measured per-rank times converge although the true cost of a batch (how
+    much surface it holds) is invisible to the pre-pass."""
+    rng = np.random.default_rng(3)
+    n, world = 32 * 32 * 32, 8
+    active = np.zeros(n)
+    active[6000:26000] = (rng.random(20000) < 0.3)
+    cost = active * (1.0 + 4.0 * np.exp(-((np.arange(n) - 15000) / 3000.0) ** 2))          # hidden: surface-heavy in the middle
+    weights = active.copy()
+    wins = multi.partition_windows(weights, world)
+    spread = []
+    for _ in range(4):
+        t = [cost[a:b].sum() + 50.0 for a, b in wins]                                      # + a fixed per-rank cost
+        spread.append(max(t) / min(t))
+        weights = multi.reweigh(weights, wins, t)
+        wins = multi.partition_windows(weights, world)
+    assert spread[0] > 1.5 and spread[-1] < 1.06, spread

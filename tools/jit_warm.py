@@ -49,12 +49,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--jobs', type=int, default=os.cpu_count() or 4)
     ap.add_argument('--kernels', default='0,1,2,3,4,5,6,7,8')
+    ap.add_argument('--only', default='', help='only models whose name starts with this prefix (e.g. cfg_: the five BASELINE configurations)')
     args = ap.parse_args()
     kernels = [int(k) for k in args.kernels.split(',')]
     import models
     import sdf_b200
     names = list(dict(models.build(sdf_b200)).keys()) + ['grp_cyl_x', 'grp_cyl_y'] + ['cfg_' + k for k in models.CONFIGS]
     names = list(dict.fromkeys(names))
+    if args.only:
+        names = [n for n in names if n.startswith(args.only)]
     forced = {'grp_cyl_x', 'grp_cyl_y', 'cfg_gearlike', 'cfg_knurling', 'gearlike', 'knurling'}
     items = [(n, kernels, n in forced) for n in names]
     with mp.Pool(args.jobs) as pool:
