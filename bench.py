@@ -8,8 +8,12 @@ examples/gearlike.py tree on a 512^3 lattice (bounds +-2.5, step 5/512), sparse 
 B200.  A "step" is one full pass of the hot path over the lattice: skip pre-pass, fused SDF
 evaluation, marching cubes, world mapping.  For N > 1 (torchrun, one rank per GPU) the lattice
 edge grows as 512 * N^(1/3) (rounded to a batch multiple) so every GPU keeps 512^3 samples
-("weak"); ranks take Z-slabs balanced by active batches and one NCCL all-gather concatenates the
-triangle buffers at the end of every step.
+("weak"); ranks take Z-slabs (windows of the Z-major batch order) balanced by active batches and
+re-planned from measured per-rank times.  `value` times the hot path with every rank's triangles
+resident in its own HBM ("excluding the final all-gather, which is reported
+separately"); the `gather` object reports the same series with the fused root gather (all
+extraction kernels writing into rank 0 over NVLink).  `strong_1024` is north_star's strong-scaling
+case (knurling, fixed 1024^3 lattice) measured the same two ways.
 
 Output: ONE JSON line on rank 0 (see the task contract): value = Mpoints/s of lattice samples
 covered (device-resident output), e2e = same through the public generate() with host output,
@@ -280,24 +284,27 @@ class DeviceSeries:
     """K timed passes of the hot path with device-resident output on this rank's Z-slab (barrier + synchronize on
     both sides, CUDA events per step on the launching stream, L2 flushed between steps, max over ranks)."""
 
-    def __init__(self, f, w, args, world, rank, local, flush):
+    def __init__(self, f, w, args, world, rank, local, flush, gather='none', plan=None):
+        """``gather``: 'none' = every rank keeps its slab's triangles in its own HBM (what `value` times: SURVEY.md
+        section 8d, "excluding the final all-gather, which is reported separately"); 'root' = the fused gather, every
+        extraction kernel writes into rank 0's buffer over NVLink; 'allgather' = NCCL send/recv after the step."""
         import torch
         import torch.distributed as dist
         from sdf_b200 import core, multi
         self.torch, self.dist, self.world, self.rank, self.args, self.flush = torch, dist, world, rank, args, flush
-        self.f, self.w = f, w
+        self.f, self.w, self.gather = f, w, gather
         _, _, (X, Y, Z) = core.make_lattice(f, w['step'], w['bounds'])
         self.axes = (X, Y, Z)
         self.n_points = len(X) * len(Y) * len(Z)
         self.stream = torch.cuda.current_stream().cuda_stream
-        self.plan = multi.plan_windows(f, X, Y, Z, BATCH, world, device=local) if world > 1 else None
+        self.plan = (plan if plan is not None else multi.plan_windows(f, X, Y, Z, BATCH, world, device=local)) if world > 1 else None
         self.h, _ = core.program_handle(f)
         self.tau = core.mixed_tau(self.h.program, X, Y, Z)
         self.local = local
         self.root_gather = None
         self._size_buffers()
         self.gather_events = []
-        if world > 1 and not args.no_rebalance:
+        if world > 1 and not args.no_rebalance and plan is None:
             self.rebalance()
 
     def _size_buffers(self):
@@ -311,7 +318,7 @@ class DeviceSeries:
         self.win = win
         self.cap = int(need * 1.02) + 1024
         self.out = torch.empty((self.cap, 9), dtype=torch.float32, device='cuda')
-        if self.world > 1 and args.gather == 'root' and self.root_gather is None:
+        if self.world > 1 and self.gather == 'root' and self.root_gather is None:
             from sdf_b200 import multi
             needs = torch.tensor([need], dtype=torch.int64, device='cuda')
             dist.all_reduce(needs)
@@ -350,7 +357,7 @@ class DeviceSeries:
         n_tri, stats, timings = self.h.generate_window(X, Y, Z, BATCH, True, args.precision, self.tau, self.win,
                                                        tri_out=self.out, capacity=self.cap, device=self.local, stream=self.stream)
         gathered = None
-        if self.world > 1:
+        if self.world > 1 and self.gather == 'allgather':
             from sdf_b200 import multi
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
@@ -494,6 +501,19 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # the same series with the triangles gathered: fused root gather (every extraction kernel writes into rank 0's HBM over
+    # NVLink) -- reported separately, `value` is the slab-resident series
+    gather = None
+    if world > 1:
+        sg = DeviceSeries(f, w, args, world, rank, local, flush, gather=args.gather, plan=series.plan)
+        rg = sg.run(max(3, min(args.steps, 10)), 3)
+        gather = {'kind': 'fused root gather: peer writes into rank 0 over NVLink, ready/done flag words, no collective' if args.gather == 'root'
+                  else 'NCCL send/recv all-gather after the step',
+                  'ms_per_step_with_gather': rg['ms_per_step'], 'value_with_gather': n_points / (rg['ms_per_step'] / 1e3) / 1e6,
+                  'output_mb': rg['agg'][0] * 36 / 1e6, 'kernel_ms_max_over_ranks': rg['kern_max'],
+                  'note': 'the whole soup lands in ONE GPU: bounded below by that GPU\'s NVLink ingress (output_mb / ~0.8 TB/s)'}
+        del sg
+
     # north_star's STRONG-scaling case next to the weak series the --gpus contract asks for: the knurling tree on a
     # FIXED 1024^3 lattice split over the ranks (compare this object's ms_per_step across the N = 1, 2, 4, 8 lines)
     strong = None
@@ -507,7 +527,14 @@ def run_ours(args):
                   'mtris_per_s': rs['agg'][0] / (rs['ms_per_step'] / 1e3) / 1e6, 'triangles': int(rs['agg'][0]),
                   'per_rank_min_ms': rs['per_rank_min'], 'per_rank_max_ms': rs['per_rank_max'],
                   'windows': [list(p) for p in ss.plan] if ss.plan else None,
-                  'replans_per_rank_ms': getattr(ss, 'replans', None), 'kernel_ms_max_over_ranks': rs['kern_max']}
+                  'replans_per_rank_ms': getattr(ss, 'replans', None), 'kernel_ms_max_over_ranks': rs['kern_max'],
+                  'output': 'every rank keeps its slab in its own HBM (gather reported separately)'}
+        if world > 1:
+            sgs = DeviceSeries(fs, ws, args, world, rank, local, flush, gather=args.gather, plan=ss.plan)
+            rgs = sgs.run(5, 3)
+            strong['with_root_gather'] = {'ms_per_step': rgs['ms_per_step'], 'output_mb': rgs['agg'][0] * 36 / 1e6,
+                                          'kernel_ms_max_over_ranks': rgs['kern_max']}
+            del sgs
         del ss
 
     if rank == 0:
@@ -543,7 +570,7 @@ def run_ours(args):
                        'l2': 'flushed between timed iterations (768 MB memset, outside the per-step events)',
                        'parallelism': 'z-slab x%d (windows of the Z-major batch order, balanced by active batches%s)' % (
                            world, ', measured re-plans' if (world > 1 and not args.no_rebalance) else ''),
-                       'gather': (args.gather if world > 1 else None),
+                       'gather': ('excluded from value (every rank keeps its slab; SURVEY.md 8d) -- see the `gather` object' if world > 1 else None),
                        'sample_grouping': dict(zip(('share_axis', 'samples_per_thread', 'invariant_fraction'),
                                                    h.jit_plan({'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}[args.precision]))),
                        'host_output_rounds': int(os.environ.get('SDFB200_PIPE', 8))},
@@ -558,7 +585,6 @@ def run_ours(args):
                           'extract_kernel(C)': res['kern_ms'][2],
                           'per_rank_min': res['per_rank_min'], 'per_rank_max': res['per_rank_max']},
             'gpu_launches': 5 * args.steps,
-            'allgather_ms_rank0': res['gather_ms'],
             'clocks': clocks,
             'e2e': {'value': n_points / e2e_s / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(8 * (len(X) + len(Y) + len(Z))),
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_s * 1e3, 'mtris_per_s': tri_total / e2e_s / 1e6,
@@ -573,6 +599,7 @@ def run_ours(args):
                                  'run; the kernel generates its samples in registers from the three lattice axes, so its real '
                                  'DRAM traffic is far below the algorithmic bytes and it is FP32/MUFU issue bound'},
             'strong_1024': strong,
+            'gather': gather,
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_port(w, args.cpu_seconds)
