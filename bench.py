@@ -487,7 +487,7 @@ def run_ours(args):
         t = time.perf_counter()
         if world > 1:
             pts, info = multi.generate_distributed(f, step=w['step'], bounds=w['bounds'], precision=args.precision,
-                                                   plan=plan, gather=('root' if args.gather == 'root' else 'host'))
+                                                   plan=plan, gather=args.e2e_gather)
         else:
             pts, info = sdf_b200.generate(f, step=w['step'], bounds=w['bounds'], verbose=False,
                                           precision=args.precision, device=local, return_info=True)
@@ -621,6 +621,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the knurling 1024^3 strong-scaling side series')
     ap.add_argument('--no-cold', action='store_true', help='skip the cold-start side measurement')
+    ap.add_argument('--e2e-gather', default='shm', choices=['shm', 'root', 'host'],
+                    help='N>1, public API leg: every rank copies its slab to one shared pinned host segment over its own PCIe link (default), '
+                         'fused root gather + one copy, or NCCL all-gather + copy')
     ap.add_argument('--no-rebalance', action='store_true', help='N>1: keep the plan balanced by active batches (no measured re-plan)')
     ap.add_argument('--gather', default='root', choices=['root', 'allgather'],
                     help='N>1: fused NVLink peer writes into rank 0 (default) or NCCL send/recv all-gather')

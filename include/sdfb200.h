@@ -55,6 +55,15 @@ int sdfb200_host_alloc(size_t bytes, void** out);
 void sdfb200_host_free(void* p);
 
 /*
+ * Multi-GPU host output (replaces nothing in the reference): page-lock caller-owned host memory -- sdf_b200/multi.py
+ * uses one POSIX shared-memory segment that every rank process maps -- and copy a rank's slab into it at its offset:
+ * N ranks move their triangles to the host over N PCIe links at once instead of funnelling them through one GPU.
+ */
+int sdfb200_host_register(void* p, size_t bytes);
+void sdfb200_host_unregister(void* p);
+int sdfb200_copy_to_host(void* dst_host, const void* src_device, size_t bytes, int device, void* stream);
+
+/*
  * Replaces: construction of the closure tree by the @sdf3/@op3 factories
  * (sdf/d3.py:48-63) -- the lowered program of sdf_b200/ir.py.
  *   code[n_code]     instruction words  op | a << 8 | const_index << 16

@@ -18,7 +18,7 @@ PREC = {'f32': 0, 'mixed': 1, 'f64': 2, 'exact': 3}
 EXPORTS = ['sdfb200_abi_version', 'sdfb200_last_error', 'sdfb200_device_count',
            'sdfb200_program_create', 'sdfb200_program_free', 'sdfb200_eval_f32', 'sdfb200_eval_f32_fast',
            'sdfb200_eval_f64', 'sdfb200_generate', 'sdfb200_skip_flags',
-           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
+           'sdfb200_host_alloc', 'sdfb200_host_free', 'sdfb200_host_register', 'sdfb200_host_unregister', 'sdfb200_copy_to_host', 'sdfb200_jit_probe', 'sdfb200_jit_plan', 'sdfb200_generate_stl',
            'sdfb200_shared_create', 'sdfb200_shared_open', 'sdfb200_shared_free', 'sdfb200_shared_buffer',
            'sdfb200_shared_wait', 'sdfb200_shared_release', 'sdfb200_generate_shared', 'sdfb200_generate_window', 'sdfb200_mc_volume', 'sdfb200_weld']
 
@@ -62,6 +62,10 @@ def lib():
     L.sdfb200_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.sdfb200_host_free.argtypes = [vp]
     L.sdfb200_host_free.restype = None
+    L.sdfb200_host_register.argtypes = [vp, ctypes.c_size_t]
+    L.sdfb200_host_unregister.argtypes = [vp]
+    L.sdfb200_host_unregister.restype = None
+    L.sdfb200_copy_to_host.argtypes = [vp, vp, ctypes.c_size_t, i32, vp]
     L.sdfb200_generate_stl.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, dbl,
                                        vp, i64, ctypes.POINTER(i64), vp, vp, i32, vp]
     L.sdfb200_shared_create.argtypes = [i64, i32, ctypes.POINTER(vp), vp]
@@ -104,6 +108,19 @@ def _ptr(obj):
     if isinstance(obj, np.ndarray):
         return obj.ctypes.data
     return obj.data_ptr()
+
+
+def host_register(address, nbytes):
+    _check(lib().sdfb200_host_register(address, nbytes))
+
+
+def host_unregister(address):
+    if _lib is not None:
+        _lib.sdfb200_host_unregister(address)
+
+
+def copy_to_host(dst_address, src_device_ptr, nbytes, device=0, stream=None):
+    _check(lib().sdfb200_copy_to_host(dst_address, src_device_ptr, nbytes, device, stream))
 
 
 def weld(points, device=0, stream=None):

@@ -826,6 +826,28 @@ extern "C" void sdfb200_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// Page-lock memory the caller owns (e.g. a POSIX shared-memory segment several rank processes write their slabs
+// into, each over its own PCIe link: sdf_b200/multi.py HostGather) so that device -> host copies into it run at
+// DMA speed; sdfb200_copy_to_host is that copy (asynchronous on `stream`, then synchronised).
+extern "C" int sdfb200_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(SDFB200_E_INVALID, "host_register: bad argument");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+extern "C" void sdfb200_host_unregister(void* p) {
+    if (p) { cudaHostUnregister(p); cudaGetLastError(); }
+}
+
+extern "C" int sdfb200_copy_to_host(void* dst_host, const void* src_device, size_t bytes, int device, void* stream) {
+    if (bytes == 0) return 0;
+    if (!dst_host || !src_device) return fail(SDFB200_E_INVALID, "copy_to_host: NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int sdfb200_program_create(const uint32_t* code, int n_code, const double* consts, int n_consts,
                                       sdfb200_prog** out) {
     if (!code || !out || n_code <= 0 || n_consts < 0 || (n_consts > 0 && !consts))

@@ -32,6 +32,13 @@ def main():
             ok = ok and good
             print('rank %d %s: %s %s local %d total %d single %d identical=%s' % (
                 rank, name, partition, info['zb'], info['triangles'], info['triangles_total'], info1['triangles'], good), flush=True)
+        # host output over every rank's own PCIe link (shared page-locked segment)
+        spts, sinfo = multi.generate_distributed(f, step=step, bounds=bounds, gather='shm', device=local)
+        if rank == 0:
+            srep = compare_soups(spts, one)
+            sgood = srep['count_equal'] and srep['exact_triangles'] == srep['n_ref']
+            ok = ok and sgood
+            print('rank 0 %s: SHM host gather total %d identical=%s' % (name, sinfo['triangles_total'], sgood), flush=True)
         # fused gather to rank 0 (NVLink peer writes from the extraction kernels)
         rpts, rinfo = multi.generate_distributed(f, step=step, bounds=bounds, gather='root', device=local)
         if rank == 0:
