@@ -1249,7 +1249,7 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             if (e != cudaSuccess) return fail(SDFB200_E_CUDA, "tile kernel launch failed: %s", cudaGetErrorString(e));
             if (first) CUDA_TRY(rec(c->ev[5], s, captured));
             if (refine) {
-                const int rgrid = c->sms * env_int("SDFB200_REFINE_BLOCKS", 8);      // (A/B hook; 128-thread CTAs per SM)
+                const int rgrid = c->sms * env_int("SDFB200_REFINE_BLOCKS", 16);      // (A/B hook; 128-thread CTAs per SM)
                 if (k_refine) {
                     Counters* ctrp = c->ctr;
                     void* args[] = {(void*)&g, (void*)&L, (void*)&ctrp};
