@@ -266,10 +266,22 @@ class HostGather:
         size = self.HEADER + 2 * self.capacity * 36
         box = [None]
         if self.rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=size)
-            np.ndarray((self.HEADER // 8,), np.uint64, buffer=self.shm.buf)[:] = 0
-            box[0] = self.shm.name
+            try:        # (a container with a small /dev/shm cannot hold the segment: every rank then falls back, see _host_gather)
+                import os
+                self.shm = shared_memory.SharedMemory(create=True, size=size)
+                os.posix_fallocate(self.shm._fd, 0, size)          # ENOSPC now, as an exception -- not SIGBUS at the first write
+                np.ndarray((self.HEADER // 8,), np.uint64, buffer=self.shm.buf)[:] = 0
+                box[0] = self.shm.name
+            except (OSError, ValueError) as e:
+                box[0] = 'ERROR: %s' % (e,)
+                try:
+                    self.shm.close(); self.shm.unlink()
+                except Exception:
+                    pass
+                self.shm = None
         dist.broadcast_object_list(box, src=0, group=group)
+        if isinstance(box[0], str) and box[0].startswith('ERROR'):
+            raise OSError('HostGather: no shared host segment of %d MB (%s)' % (size >> 20, box[0]))
         if self.rank != 0:
             self.shm = shared_memory.SharedMemory(name=box[0])
             try:        # (Python < 3.13 registers attached segments with the resource tracker, which would unlink them)
@@ -345,13 +357,16 @@ def _host_gather(local_need, dev, group, total=None):
     key = (dev, id(group))
     hg = _host_gathers.get(key)
     if hg is not None:
-        return hg
+        return hg                    # (False: this box cannot hold the segment)
     if total is None:
         t = torch.tensor([int(local_need)], dtype=torch.int64, device=torch.device('cuda', dev))
         dist.all_reduce(t, group=group)
         total = int(t.item())
     cap = 1 << max(16, (int(total * 1.05) - 1).bit_length())
-    hg = _host_gathers[key] = HostGather(cap, dev, group)
+    try:
+        hg = _host_gathers[key] = HostGather(cap, dev, group)
+    except OSError:              # raised on every rank together (the creation outcome is broadcast)
+        hg = _host_gathers[key] = False
     return hg
 
 
@@ -435,6 +450,8 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
                     raise
                 need = int(e.needed * 1.02) + 1024
     info = dict(info, zb=mine, rank=rank, world=world, partition=partition)
+    if gather == 'shm' and world > 1 and local.is_cuda and _host_gather(need, local.device.index, group) is False:
+        gather = 'host'              # no room in /dev/shm on this box: NCCL all-gather + one copy instead
     if gather == 'shm' and world > 1 and local.is_cuda:
         # every rank moves its slab to the host over its own PCIe link, into one shared page-locked segment
         hg = _host_gather(need, local.device.index, group)
@@ -442,6 +459,8 @@ def generate_distributed(sdf, step=None, bounds=None, samples=core.SAMPLES, batc
         if isinstance(res, int):                        # too small (a stale count): every rank sees the same total
             _host_gathers.pop((local.device.index, id(group))).close()
             hg = _host_gather(0, local.device.index, group, total=-res)
+            if hg is False:
+                raise RuntimeError('HostGather: /dev/shm cannot hold %d triangles' % -res)
             res = hg.run(local, torch.cuda.current_stream(local.device).cuda_stream)
         if rank != 0:
             return np.zeros((0, 3), np.float32), info
