@@ -799,6 +799,7 @@ __device__ __forceinline__ void tile_sign_body(const EV& ev, const GridDesc& g, 
 }
 
 struct ClassifySmem {
+    uint4 block[SIGN_STRIDE / 16];                              // the tile's mask block, staged by one coalesced copy
     unsigned int cand[32 * 32];                                 // per (cs, cw): bit cu <=> cube is a candidate
     unsigned long long refm[SIGN_LINES];                        // per (is, iw) line: bit iu <=> sample queued for float64
     unsigned int warp_sums[CLASSIFY_THREADS / 32];
@@ -830,7 +831,13 @@ __device__ __forceinline__ void tile_classify_body(const GridDesc& g, const unsi
         if (!valid || t.px < 2 || t.py < 2 || t.pz < 2) continue;        // (CTA uniform) thin tile: no cube, not evaluated
         const int ext[3] = {t.px, t.py, t.pz};
         const int pu = ext[AU], ps = ext[AS], pw = ext[AW];
-        const uint2* const masks = reinterpret_cast<const uint2*>(scratch + (size_t)tw * SIGN_STRIDE);
+        // the mask block comes in with ONE coalesced pass (616 x 16 B) instead of five dependent, scattered loads per thread
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(scratch + (size_t)tw * SIGN_STRIDE);
+            for (int i = tid; i < SIGN_STRIDE / 16; i += THREADS) sm.block[i] = src[i];
+        }
+        __syncthreads();
+        const uint2* const masks = reinterpret_cast<const uint2*>(sm.block);
         const unsigned char* const hi = reinterpret_cast<const unsigned char*>(masks + SIGN_LINES);
         const bool has_hi = (pu == TP);
         const unsigned int cumask = (pu - 1 >= 32) ? 0xffffffffu : ((1u << (pu - 1)) - 1u);
@@ -963,7 +970,7 @@ __device__ __forceinline__ void refine_points_body(const EV& ev, const GridDesc&
 //   1. one thread per CUBE: gather the 8 corner values (float64-confirmed by B), cube index, tiling
 //      selection (decision tables in shared memory; test_face / test_interior in non-contracted float64),
 //      triangle count; a CTA prefix sum reserves the output range with one global atomic;
-//   2. one thread per TRIANGLE (found by binary search in the prefix array): its three edge vertices
+//   2. one thread per TRIANGLE (its cube looked up in a small owner map): its three edge vertices
 //      (inverse-|value| weights, float64, rounded like the C restatement), world mapping (core.py:58-60),
 //      staged per warp in shared memory and written out as one contiguous, fully coalesced run -- to
 //      local HBM, or to the root GPU over NVLink in the multi-GPU case.
@@ -980,6 +987,7 @@ struct ExtractSmem {
     float cv[8][EXTRACT_THREADS];                   // corner values of this iteration's cubes
     int org[6][EXTRACT_THREADS];                    // batch origin (bx0, by0, bz0), Lewiner cube position (lx, ly, lz)
     unsigned int pre[EXTRACT_THREADS];              // exclusive prefix of the triangle counts
+    unsigned char owner[EXTRACT_THREADS * 12];      // triangle -> cube of this iteration (a cube yields <= 12 triangles)
     unsigned short toff[EXTRACT_THREADS];           // offset of the cube's tiling in tile_data
     float stage[EXTRACT_THREADS / 32][32 * 9];
     unsigned int warp_sums[EXTRACT_THREADS / 32];
@@ -1122,7 +1130,11 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             if (wi < warp) warp_off += sv;
             total += sv;
         }
-        sm.pre[tid] = warp_off + incl - nt;
+        {
+            const unsigned int first = warp_off + incl - nt;
+            sm.pre[tid] = first;
+            for (unsigned int k = 0; k < nt; ++k) sm.owner[first + k] = (unsigned char)tid;
+        }
         if (tid == 0) {
             unsigned long long base = 0ull;
             if (total) {
@@ -1144,12 +1156,7 @@ __device__ __forceinline__ void extract_body(const GridDesc& g, const TileLists 
             for (unsigned int j0 = 0; j0 < total; j0 += EXTRACT_THREADS) {
                 const unsigned int j = j0 + tid;
                 if (j < total) {
-                    int lo = 0, hi = EXTRACT_THREADS - 1;                               // last c with pre[c] <= j
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (sm.pre[mid] <= j) lo = mid; else hi = mid - 1;
-                    }
-                    const int c = lo;
+                    const int c = (int)sm.owner[j];
                     const unsigned int tri = j - sm.pre[c];
                     const unsigned char* ed = &sm.mc.tile_data[(unsigned int)sm.toff[c] + 3u * tri];
                     const int bx0 = sm.org[0][c], by0 = sm.org[1][c], bz0 = sm.org[2][c];
