@@ -150,3 +150,57 @@ def test_measured_replans_converge_to_equal_times():
         weights = multi.reweigh(weights, wins, t)
         wins = multi.partition_windows(weights, world)
     assert spread[0] > 1.5 and spread[-1] < 1.06, spread
+
+
+def _worker_hostgather(rank, world, port, q):
+    """HostGather's protocol (counts / completion through header words of one shared segment, offsets, two data regions)
+    with the two CUDA calls it makes replaced by host stand-ins: page-locking is a no-op, the DMA copy a memmove."""
+    import ctypes
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from sdf_b200 import _abi
+    _abi.host_register = lambda addr, n: None
+    _abi.host_unregister = lambda addr: None
+    _abi.copy_to_host = lambda dst, src, n, device=0, stream=None: ctypes.memmove(dst, src, n)
+    hg = multi.HostGather(1000, 0)
+    copies, views = [], []
+    for step in range(3):
+        n = 10 * (rank + 1) + step                       # different counts per rank and step
+        local = torch.full((n, 9), float(100 * step + rank), dtype=torch.float32)
+        res = hg.run(local)
+        if rank == 0:
+            views.append(res)                            # a VIEW of the shared segment
+            copies.append(np.array(res))
+    too_big = hg.run(torch.zeros((800, 9), dtype=torch.float32))          # 2 x 800 > capacity: every rank learns the total
+    if rank == 0:
+        # the view handed out by step 1 is intact after step 2 wrote the OTHER region (two regions alternate), and after the
+        # refused step; step 0's region was re-used by step 2, as documented
+        assert np.array_equal(views[1], copies[1]) and np.array_equal(views[2], copies[2])
+        assert not np.array_equal(np.array(views[0]), copies[0])
+        q.put((copies, too_big))
+    else:
+        q.put((None, too_big))
+    dist.barrier()
+    hg.close()
+    dist.destroy_process_group()
+
+
+def test_hostgather_protocol_world2():
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_hostgather, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    outs = [g for g in got if g[0] is not None][0][0]
+    for step, arr in enumerate(outs):
+        n0, n1 = 10 + step, 20 + step
+        assert arr.shape == (n0 + n1, 9)
+        assert np.all(arr[:n0] == 100 * step) and np.all(arr[n0:] == 100 * step + 1)          # rank order, right offsets
+    assert all(g[1] == -1600 for g in got)               # the segment was too small: the needed total, on every rank
