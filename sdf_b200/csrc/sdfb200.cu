@@ -204,7 +204,6 @@ struct DeviceCtx {
     cudaEvent_t ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // pipelined host output: the triangles of round k travel over PCIe while round k+1 computes
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t pev[kMaxPipe] = {};
 };
 
 // Rounds a call is cut into when the triangles go to HOST memory, so that the triangles of round k cross PCIe
@@ -745,9 +744,8 @@ static int get_ctx(sdfb200_prog* prog, int device, DeviceCtx** out) {
     c.device = device;
     CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c.ctr, sizeof(Counters)));
-    CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters) * (1 + kMaxPipe)));     // [0] final, [1 + k] after round k
+    CUDA_TRY(cudaMallocHost(&c.ctr_host, sizeof(Counters)));
     for (int i = 0; i < 9; ++i) CUDA_TRY(cudaEventCreate(&c.ev[i]));
-    for (int i = 0; i < kMaxPipe; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.pev[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaHostAlloc((void**)&c.progress, sizeof(RoundProgress) * kMaxPipe, cudaHostAllocMapped));
@@ -898,7 +896,6 @@ extern "C" void sdfb200_program_free(sdfb200_prog* prog) {
         for (auto& sg : c.step_graphs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
         if (c.cap_stream) cudaStreamDestroy(c.cap_stream);
         for (int i = 0; i < 9; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
-        for (int i = 0; i < kMaxPipe; ++i) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
         if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     }
     for (auto& e : prog->jit) if (e.lib) cudaLibraryUnload(e.lib);
@@ -1292,7 +1289,6 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
             size_t want_cubes = std::max<size_t>(c->cube_cap, std::min<size_t>((size_t)round * 32768, std::max<size_t>((size_t)1 << 20, est_tiles * 3072)));
             size_t want_pts = std::max<size_t>(c->pt_cap, precision == SDFB200_PREC_EXACT ? want_cubes * 3 : want_cubes);
             for (int attempt = 0; attempt < 3; ++attempt) {
-                int n_rounds = 0;
                 rc = grow(&c->cubes, &c->cube_cap, want_cubes); if (rc) return rc;
                 rc = grow(&c->pts, &c->pt_cap, want_pts); if (rc) return rc;
                 TileLists L;
@@ -1411,27 +1407,10 @@ static int generate_impl(sdfb200_prog* prog, const double* xs, int64_t nx, const
                         }
                         const unsigned long long tiles = std::min<unsigned long long>(n_work, wb + round) - wb;
                         rc = launch_round(stream, false, L, (unsigned int)wb, we, tiles, wb == 0, wb + round >= n_work, nullptr); if (rc) return rc;
-                        if (pipe > 1 && n_rounds < kMaxPipe) {
-                            CUDA_TRY(cudaMemcpyAsync(c->ctr_host + 1 + n_rounds, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                            CUDA_TRY(cudaEventRecord(c->pev[n_rounds], stream));
-                            ++n_rounds;
-                        }
                     }
                     CUDA_TRY(cudaEventRecord(c->ev[2], stream));
                     CUDA_TRY(cudaMemcpyAsync(c->ctr_host, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
                     if (!tail) CUDA_TRY(cudaEventRecord(c->ev[3], stream));     // nothing follows on the device
-                    // every round is queued; follow them and send each round's triangles as soon as it is done
-                    for (int k = 0; k < n_rounds; ++k) {
-                        CUDA_TRY(cudaEventSynchronize(c->pev[k]));
-                        const Counters& hk = c->ctr_host[1 + k];
-                        if (hk.max_cubes > L.cube_cap || hk.max_pts > L.pt_cap) break;       // lists overflowed: retried below
-                        const unsigned long long upto = std::min<unsigned long long>(hk.tri_cursor, cap);
-                        if (upto > copied) {
-                            CUDA_TRY(cudaMemcpyAsync(tri_out + copied * 9, dtri + copied * 9, (size_t)(upto - copied) * 36,
-                                                     cudaMemcpyDeviceToHost, c->copy_stream));
-                            copied = upto;
-                        }
-                    }
                 }
                 CUDA_TRY(cudaStreamSynchronize(stream));
                 have_counters = true;
