@@ -11,7 +11,7 @@ from .d2 import *              # noqa: F401,F403
 
 from .d3 import *              # noqa: F401,F403
 
-from .texture import (         # noqa: F401  (names only: out of scope, raise on use)
+from .texture import (         # noqa: F401  (text / image are host nodes; Mesh needs pyopenvdb and raises)
     Mesh,
     image,
     measure_image,

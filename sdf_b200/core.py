@@ -80,8 +80,9 @@ def _compose_around_closure(obj, p):
     A Python closure can only run on the host, so the nodes ABOVE it cannot be fused into the CUDA evaluator
     either.  Every maximal sub-tree without a closure still evaluates on the GPU (one call each); the closure is
     called as the reference calls it (d3.py:24-25); and the handful of composition nodes people put around their
-    own SDFs -- the CSG folds, blend, negate / dilate / erode / shell, translate / scale / rotate (dn.py:7-80,
-    d3.py:329-360) -- combine those fields on the host with the reference's formulas.  Any other node above a
+    own SDFs and around text() / image() -- the CSG folds, blend, negate / dilate / erode / shell, translate /
+    scale / rotate in 2-D and 3-D, extrude / extrude_to / revolve (dn.py:7-80, d3.py:329-360, d2.py:211-287) --
+    combine those fields on the host with the reference's formulas.  Any other node above a
     closure raises NotLowerableError.  Lowered trees (everything the library itself builds) never come here."""
     from .ir import node_of
     from . import d2
@@ -122,14 +123,38 @@ def _compose_around_closure(obj, p):
     if n.kind == 'value' and n.op in ('NEGATE', 'ADDC', 'SHELL'):        # dn.py:62-80
         d = _compose_around_closure(kids[0], p)
         return -d if n.op == 'NEGATE' else (d + n.consts[0] if n.op == 'ADDC' else np.abs(d) - n.consts[0] / 2)
-    if n.kind == 'transform' and n.op == 'TRANSLATE':                    # d3.py:329-333
-        return _compose_around_closure(kids[0], p - np.array(n.consts[:p.shape[1]]))
-    if n.kind == 'transform' and n.op == 'ROTATE' and p.shape[1] == 3:   # d3.py:347-360
-        return _compose_around_closure(kids[0], np.dot(p, np.array(n.consts).reshape(3, 3)))
-    if n.kind == 'scale' and p.shape[1] == 3:                            # d3.py:335-345
-        return _compose_around_closure(kids[0], p / np.array(n.consts[:3])) * n.consts[3]
-    raise NotLowerableError('node %r sits above a Python closure: only CSG folds, blend, negate / dilate / erode / shell and '
-                            'translate / scale / rotate can be combined with user-written SDFs' % (n.label,))
+    dim = p.shape[1]
+    if n.kind == 'transform' and n.op == 'TRANSLATE':                    # d3.py:329-333, d2.py:211-215
+        return _compose_around_closure(kids[0], p - np.array(n.consts[:dim]))
+    if n.kind == 'transform' and n.op == 'ROTATE':                       # d3.py:347-360, d2.py:228-238
+        return _compose_around_closure(kids[0], np.dot(p, np.array(n.consts).reshape(3, 3)[:dim, :dim]))
+    if n.kind == 'scale':                                                # d3.py:335-345, d2.py:217-226
+        return _compose_around_closure(kids[0], p / np.array(n.consts[:dim])) * n.consts[3]
+    if n.kind == 'extrude' or n.op == 'EXTRUDE_TO':                      # d2.py:261-279
+        if n.kind == 'extrude':
+            h = n.consts[0]
+            d = _compose_around_closure(kids[0], p[:, :2])
+        else:
+            (_, (h,)), ease_id = n.extra[0], n.extra[1]
+            d1 = _compose_around_closure(kids[0], p[:, :2])
+            d2_ = _compose_around_closure(kids[1], p[:, :2])
+            d = d1 + (d2_ - d1) * _ease_by_id(ease_id)(np.clip(p[:, 2] / h, -0.5, 0.5) + 0.5)
+        w = np.stack([d, np.abs(p[:, 2]) - h / 2], axis=-1)
+        return np.minimum(np.maximum(w[:, 0], w[:, 1]), 0) + np.linalg.norm(np.maximum(w, 0), axis=1)
+    if n.kind == 'transform' and n.op == 'REVOLVE':                      # d2.py:281-287
+        q = np.stack([np.linalg.norm(p[:, :2], axis=1) - n.consts[0], p[:, 2]], axis=-1)
+        return _compose_around_closure(kids[0], q)
+    raise NotLowerableError('node %r sits above a Python closure: only CSG folds, blend, negate / dilate / erode / shell, '
+                            'translate / scale / rotate and extrude / extrude_to / revolve can be combined with '
+                            'user-written SDFs and text() / image()' % (n.label,))
+
+
+def _ease_by_id(ease_id):
+    from . import ease
+    for name, i in ease.EASE_ID.items():
+        if i == ease_id:
+            return getattr(ease, name)
+    raise ValueError('unknown easing id %r' % (ease_id,))
 
 
 def evaluate(sdf, p, device=None):
@@ -462,9 +487,14 @@ def weld(points, device=None):
 
 
 def _mesh(points):
-    """core.py:160-164 (needs the optional ``meshio`` package, as in the reference); welded on the GPU."""
-    import meshio
+    """core.py:160-164: the soup welded into an indexed mesh (on the GPU) as a ``meshio.Mesh`` -- or, where the
+    optional meshio package is missing, as the built-in stand-in that writes .obj / .ply / .off (mesh_io.py)."""
     verts, faces = weld(points)
+    try:
+        import meshio
+    except ImportError:
+        from . import mesh_io
+        return mesh_io.IndexedMesh(verts, [('triangle', faces)])
     return meshio.Mesh(verts, [('triangle', faces)])
 
 

@@ -222,18 +222,20 @@ def test_runtime_specialisation_compiles_without_a_gpu():
 
 
 def test_star_export_surface_matches_the_reference():
-    """sdf/__init__.py:1-27: every public name a `from sdf import *` script may rely on exists; the texture
-    nodes (out of scope) import cleanly and raise on use."""
+    """sdf/__init__.py:1-27: every public name a `from sdf import *` script may rely on exists; text / image are
+    host nodes that fail like the reference's on a missing font / file (Pillow's OSError), Mesh (pyopenvdb) raises."""
     import sdf
     for name in ('np', 'pi', 'degrees', 'radians', 'X', 'Y', 'Z', 'ORIGIN', 'UP', 'ease', 'd2', 'd3', 'Mesh', 'text', 'image',
                  'measure_text', 'measure_image', 'generate', 'save', 'sample_slice', 'show_slice', 'write_binary_stl',
                  'sdf2', 'sdf3', 'op2', 'op3', 'op23', 'op32', 'SDF2', 'SDF3', 'sphere', 'box', 'circle', 'union', 'repeat'):
         assert hasattr(sdf, name), name
     assert sdf.X is sdf_b200.d3.X and len(sdf.X) == 3            # the 3-D constants win (sdf/__init__.py:5-7)
-    for call in (lambda: sdf.text('Arial', 'x'), lambda: sdf.image('a.png'), lambda: sdf.Mesh.from_file('a.stl'),
-                 lambda: sdf.measure_text('Arial', 'x')):
-        with pytest.raises(NotImplementedError):
+    for call in (lambda: sdf.text('no-such-font', 'x'), lambda: sdf.image('no-such-file.png'),
+                 lambda: sdf.measure_text('no-such-font', 'x')):
+        with pytest.raises(OSError):
             call()
+    with pytest.raises(NotImplementedError):
+        sdf.Mesh.from_file('a.stl')
 
 
 def test_sample_grouping_plan_follows_the_tree_structure():
