@@ -10,7 +10,8 @@ The evaluator has no opcode for a texture fetch, so these are HOST nodes of kind
 on the device (``core._generate_opaque``).  Pillow and scipy are imported on first use, as optional as they are for
 the reference.
 
-``Mesh`` needs pyopenvdb (absent here as it is for the reference) and raises.
+``Mesh`` keeps its container half (loading, bounding box, affine helpers); ``Mesh.sdf`` needs pyopenvdb (absent
+here as it is for the reference) and raises.
 """
 import numpy as np
 
@@ -139,17 +140,55 @@ def image(thing, width=None, height=None, pixels=PIXELS):
 
 
 class Mesh:
-    """sdf/mesh.py:9 (a triangle mesh turned into an SDF through pyopenvdb)."""
+    """sdf/mesh.py:9: a triangle mesh as an SDF source.  The container half -- loading, bounding box, the affine
+    helpers (sdf/mesh.py:10-64) -- works; ``sdf()`` builds its level set with pyopenvdb in the reference
+    (sdf/mesh.py:66-112), which exists neither here nor in the reference's own environment, and raises."""
 
-    def __init__(self, *args, **kwargs):
-        self._unavailable('Mesh')
+    def __init__(self, points, triangles):
+        self.points = np.asarray(points)
+        self.triangles = np.asarray(triangles)
 
-    @staticmethod
-    def from_file(*args, **kwargs):
-        Mesh._unavailable('Mesh.from_file')
+    @classmethod
+    def from_file(cls, path):
+        try:
+            import meshio
+        except ImportError:
+            from . import mesh_io
+            m = mesh_io.read(path)
+            return cls(m.points, m.faces)
+        m = meshio.read(path)
+        return cls(m.points, m.cells[0].data)
 
-    @staticmethod
-    def _unavailable(name):
+    @property
+    def bounding_box(self):
+        return tuple(self.points.min(axis=0).tolist()), tuple(self.points.max(axis=0).tolist())
+
+    @property
+    def size(self):
+        lo, hi = self.bounding_box
+        return tuple((np.array(hi) - np.array(lo)).tolist())
+
+    def transformed(self, matrix):
+        """Homogeneous 4 x 4 (or 3 x 4) ``matrix`` applied to every vertex."""
+        m = np.array(matrix, dtype=np.float64)
+        return Mesh(self.points @ m[:3, :3].T + m[:3, 3], self.triangles)
+
+    def scaled(self, scale):
+        s = np.empty(3)
+        s[...] = scale
+        return self.transformed(np.hstack([np.diag(s), np.zeros((3, 1))]))
+
+    def translated(self, offset):
+        return self.transformed(np.hstack([np.eye(3), np.reshape(np.asarray(offset, np.float64), (3, 1))]))
+
+    def positioned(self, position, anchor):
+        lo, hi = (np.array(v) for v in self.bounding_box)
+        return self.translated(np.asarray(position) - (lo + (hi - lo) * np.asarray(anchor)))
+
+    def centered(self):
+        return self.positioned((0, 0, 0), (0.5, 0.5, 0.5))
+
+    def sdf(self, voxel_size, half_width=None):
         raise NotImplementedError(
-            '%s() is not provided by sdf_b200: it samples an OpenVDB level set (pyopenvdb), which is outside the '
-            'GPU mesh-generation path' % name)
+            'Mesh.sdf() is not provided by sdf_b200: the reference builds the level set with pyopenvdb '
+            '(sdf/mesh.py:66-82), which is outside the GPU mesh-generation path')

@@ -223,7 +223,7 @@ def test_runtime_specialisation_compiles_without_a_gpu():
 
 def test_star_export_surface_matches_the_reference():
     """sdf/__init__.py:1-27: every public name a `from sdf import *` script may rely on exists; text / image are
-    host nodes that fail like the reference's on a missing font / file (Pillow's OSError), Mesh (pyopenvdb) raises."""
+    host nodes that fail like the reference's on a missing font / file (Pillow's OSError), Mesh.sdf (pyopenvdb) raises."""
     import sdf
     for name in ('np', 'pi', 'degrees', 'radians', 'X', 'Y', 'Z', 'ORIGIN', 'UP', 'ease', 'd2', 'd3', 'Mesh', 'text', 'image',
                  'measure_text', 'measure_image', 'generate', 'save', 'sample_slice', 'show_slice', 'write_binary_stl',
@@ -235,7 +235,7 @@ def test_star_export_surface_matches_the_reference():
         with pytest.raises(OSError):
             call()
     with pytest.raises(NotImplementedError):
-        sdf.Mesh.from_file('a.stl')
+        sdf.Mesh(np.zeros((3, 3)), np.array([[0, 1, 2]])).sdf(0.25)
 
 
 def test_sample_grouping_plan_follows_the_tree_structure():

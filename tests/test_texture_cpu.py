@@ -105,8 +105,28 @@ def test_nodes_that_cannot_sit_above_a_texture_say_so(gold):
     f = S.image(gold['mask_blobs']).extrude(0.3)
     with pytest.raises(ir.NotLowerableError, match='sits above a Python closure'):
         f.twist(1.0)(gold['p3'])
-    with pytest.raises(NotImplementedError):
-        S.Mesh.from_file('x.obj')
+
+
+def test_mesh_container_follows_the_reference(tmp_path):
+    """sdf/mesh.py:10-64 (the half of Mesh that needs no pyopenvdb): values from the formulas there, by hand."""
+    from sdf_b200 import mesh_io
+    pts = np.array([[0, 0, 0], [2, 0, 0], [0, 4, 0], [0, 0, 6]], np.float64)
+    tris = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]])
+    m = S.Mesh(pts, tris)
+    assert m.size == (2.0, 4.0, 6.0) and m.bounding_box == ((0.0, 0.0, 0.0), (2.0, 4.0, 6.0))
+    assert m.centered().bounding_box == ((-1.0, -2.0, -3.0), (1.0, 2.0, 3.0))
+    assert m.scaled(2).size == (4.0, 8.0, 12.0) and m.scaled((1, 0.5, 2)).size == (2.0, 2.0, 12.0)
+    assert m.translated((1, 2, 3)).bounding_box[0] == (1.0, 2.0, 3.0)
+    assert m.positioned((10, 10, 10), (1, 1, 1)).bounding_box[1] == (10.0, 10.0, 10.0)
+    swap = [[0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 5], [0, 0, 0, 1]]
+    assert m.transformed(swap).bounding_box == ((0.0, 0.0, 5.0), (4.0, 2.0, 11.0))
+    assert m.transformed(swap).triangles is m.triangles or np.array_equal(m.transformed(swap).triangles, tris)
+    path = str(tmp_path / 't.ply')
+    mesh_io.IndexedMesh(pts, [('triangle', tris)]).write(path)
+    back = S.Mesh.from_file(path)
+    assert np.array_equal(back.points, pts) and np.array_equal(back.triangles, tris)
+    with pytest.raises(NotImplementedError, match='pyopenvdb'):
+        m.sdf(voxel_size=0.25)
 
 
 def test_skip_rule_and_bounds_run_on_texture_trees(gold):
