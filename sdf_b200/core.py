@@ -331,10 +331,10 @@ def _generate_opaque(sdf, X, Y, Z, batch_size, sparse, device):
     'opaque'): the closure cannot run on the GPU, so each batch is evaluated by calling the tree exactly like the
     reference does (core.py:45-52; library nodes below the closure still evaluate on the GPU through their own
     ``__call__``), and the batch volume goes through marching cubes + world mapping on the device
-    (``sdfb200_mc_volume``).  Same batches, same _skip rule, same float32 cast as core.py / skimage."""
+    (``sdfb200_mc_volume``).  Same batches, same _skip rule, same float32 cast as core.py / skimage; a batch of
+    more than 33 samples per axis is meshed in pieces (each mapped to world space from its own first sample, which
+    can differ from the reference's batch-relative mapping in the last float32 bit)."""
     import itertools
-    if batch_size > 32:
-        raise ValueError('a tree with a Python closure is meshed batch by batch on the device: batch_size <= 32 (got %d)' % batch_size)
     h, _ = program_handle(_context_sdf())
     dev = default_device() if device is None else device
     s = batch_size
@@ -350,12 +350,19 @@ def _generate_opaque(sdf, X, Y, Z, batch_size, sparse, device):
         P = _cartesian_product(*job)
         volume = np.asarray(sdf(P), np.float64).reshape((len(job[0]), len(job[1]), len(job[2])))
         evaluated += volume.size
-        tris = h.mc_volume(volume, job[0], job[1], job[2], device=dev)
-        if len(tris) == 0:
-            empty += 1
-        else:
+        found = 0
+        # the device meshes volumes of up to 33^3 samples: a larger batch goes in pieces that share a plane --
+        # marching cubes is per cube, so the pieces' soups add up to the batch's
+        for ix, iy, iz in itertools.product(*(range(0, max(len(a) - 1, 1), 32) for a in job)):
+            piece = volume[ix:ix + 33, iy:iy + 33, iz:iz + 33]
+            tris = h.mc_volume(piece, job[0][ix:ix + 33], job[1][iy:iy + 33], job[2][iz:iz + 33], device=dev)
+            if len(tris):
+                found += 1
+                out.append(tris)
+        if found:
             nonempty += 1
-            out.append(tris)
+        else:
+            empty += 1
     tris = np.concatenate(out) if out else np.zeros((0, 9), np.float32)
     info = dict(triangles=len(tris), skipped=skipped, empty=empty, nonempty=nonempty, evaluated=evaluated, refined=0,
                 active_cubes=0, precision='f64 on the host (Python closure in the tree) + device marching cubes')

@@ -175,6 +175,14 @@ def test_generate_flow_on_a_texture_tree_with_device_stand_ins(gold, simulated_e
     w, h = S.measure_image(m)
     f = S.rounded_box((w * 1.1, h * 1.1, 0.1), 0.05) | (S.image(m).extrude(1) & S.slab(z0=0, z1=0.075))
     kw = dict(step=0.0127, bounds=((-0.41, -0.61, -0.11), (0.413, 0.6, 0.13)))
+    # a batch larger than the device's 33^3 volume is meshed in pieces: same soup as the oracle's big batches
+    big, ib = S.generate(f, verbose=False, return_info=True, batch_size=48, **kw)
+    rbig, sb = sdf_ref.generate(f, batch_size=48, **kw)
+    assert ib['batches'] == sb['batches'] == 4 and (ib['skipped'], ib['empty'], ib['nonempty']) == (sb['skipped'], sb['empty'], sb['nonempty'])
+    from util_cmp import compare_soups
+    rep = compare_soups(big, rbig)
+    # (a piece is mapped to world space from its own first sample: vertices may differ in the last float32 bit)
+    assert rep['count_equal'] and rep['max_vertex_dist'] <= 2e-7 and rep['exact_triangles'] >= 0.9 * rep['n_ref'], rep
     got, info = S.generate(f, verbose=False, return_info=True, **kw)
     ref, st = sdf_ref.generate(f, **kw)
     assert info['dims'] == (65, 96, 19) and info['batches'] == 9
