@@ -471,3 +471,17 @@ def test_user_closures_compose_with_the_library_combinators():
         a.twist(1.0)(P)                       # a warp above a closure: not one of the composition nodes
     with pytest.raises(ir.NotLowerableError):
         ir.lower(a | la)
+
+
+def test_plain_c_client_binds_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/sdfb200.h is C99 (no C++, no CUDA, no torch types), a C program links the library, malformed input is
+    refused with a message, and without a device the generate call returns SDFB200_E_NOGPU -- no CPU fallback."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present: tests/test_gpu_cabi_client.py runs the client for real')
+    from util_cabi import build_c_client
+    exe = build_c_client(tmp_path)
+    out = subprocess.run([exe, '64', '32'], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith('NOGPU error=') and 'no CPU fallback' in out.stdout, out.stdout
