@@ -3,7 +3,7 @@
  * What a binder in any host language does: build a program image by hand (sphere(1), d3.py:92-96 -- opcode
  * numbers from csrc/sdf_opcodes.h), the float64 axes as np.arange produces them (core.py:110-112), then the
  * count pass, a page-locked result buffer and the real call.  Used by tests/test_host_cpu.py (no GPU: the call
- * must fail with SDFB200_E_NOGPU and say so) and tests/test_gpu_cabi_client.py (result == the Python path's).
+ * must fail with SDFB200_E_NOGPU and say so) and tests/test_gpu_zzz_cabi_client.py (result == the Python path's).
  *
  *   cabi_client <n> <batch_size>      lattice of n^3 samples over [-1.25, 1.25)^3
  */

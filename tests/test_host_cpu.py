@@ -479,7 +479,7 @@ def test_plain_c_client_binds_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
     import subprocess
     import torch
     if torch.cuda.is_available():
-        pytest.skip('a GPU is present: tests/test_gpu_cabi_client.py runs the client for real')
+        pytest.skip('a GPU is present: tests/test_gpu_zzz_cabi_client.py runs the client for real')
     from util_cabi import build_c_client
     exe = build_c_client(tmp_path)
     out = subprocess.run([exe, '64', '32'], capture_output=True, text=True, timeout=120)

@@ -142,7 +142,7 @@ def test_skip_rule_and_bounds_run_on_texture_trees(gold):
 
 def test_oracle_evaluates_texture_trees_bit_identically(gold):
     """The oracle (numpy restatement of every library node) calls a texture node like any other closure, so it can
-    check the GPU route for these trees (tests/test_gpu_texture.py): pin it on the same vectors first."""
+    check the GPU route for these trees (tests/test_gpu_zzz_texture.py): pin it on the same vectors first."""
     from oracle import sdf_ref
     blobs, bars, p3 = gold['mask_blobs'], gold['mask_bars'], gold['p3']
     trees = {
@@ -160,7 +160,7 @@ def test_generate_flow_on_a_texture_tree_with_device_stand_ins(gold, simulated_e
     """generate() on an examples/image.py-shaped tree, with the two device calls of that route replaced by host
     stand-ins (evaluator -> register-machine simulator, sdfb200_mc_volume -> the oracle's marching cubes + the
     world mapping of core.py:58-60): batches, the skip rule, the one-plane tail batch and the counters must come
-    out as the oracle's generate() has them.  The same tree runs on the real device in tests/test_gpu_texture.py."""
+    out as the oracle's generate() has them.  The same tree runs on the real device in tests/test_gpu_zzz_texture.py."""
     from oracle import sdf_ref
 
     def mc_volume(self, volume, X, Y, Z, device=0, stream=None):
