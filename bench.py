@@ -24,7 +24,9 @@ CPU oracle port (numpy closures + C Lewiner MC) on the same lattice.
 baseline/_ref (its numpy closure tree, _skip, _worker and ThreadPool, core.py:84-150) on all host
 threads, with the one call it cannot make here -- skimage.measure.marching_cubes, scikit-image is
 not installable -- served by oracle/mc_lewiner.c through a shim module ("reference eval + restated
-MC"; the eval+skip-only time, which is purely the reference's code, is reported next to it).
+MC"; the eval+skip-only time, which is purely the reference's code, is reported next to it).  For N > 1 the
+lattice is N times larger and a step is a bounded sample of it: a seeded 1/N of its batches through the
+reference's _worker + ThreadPool, the time extrapolated by N (rank 0 only; the other ranks exit).
 """
 import argparse
 import json
@@ -218,6 +220,36 @@ def import_reference():
     return ref
 
 
+def reference_sample_pass(ref, f, w, cores, frac, seed=20260923):
+    """A pass over a seeded 1/frac of the workload's batches with the reference's own per-batch pipeline.
+
+    The lattice and the batch list are built as core.generate builds them (core.py:110-119); every sampled batch
+    goes through ``ref.core._worker`` on ``ThreadPool(cores).imap`` and the results are consumed as core.py:131-141
+    consumes them (the Python-level ``points.extend`` included).  Returns (callable -> triangles in the sample,
+    number of sampled batches)."""
+    import itertools
+    from functools import partial
+    from multiprocessing.pool import ThreadPool
+    (x0, y0, z0), (x1, y1, z1) = w['bounds']
+    d = w['step']
+    X, Y, Z = np.arange(x0, x1, d), np.arange(y0, y1, d), np.arange(z0, z1, d)
+    cut = lambda A: [A[i:i + BATCH + 1] for i in range(0, len(A), BATCH)]      # noqa: E731
+    batches = list(itertools.product(cut(X), cut(Y), cut(Z)))
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(len(batches), max(1, len(batches) // frac), replace=False))
+    sample = [batches[i] for i in pick]
+    work = partial(ref.core._worker, f, step=(d, d, d), sparse=True)
+
+    def one_pass():
+        points = []
+        with ThreadPool(cores) as pool:
+            for result in pool.imap(work, sample):
+                if result is not None and len(result):
+                    points.extend(result)
+        return len(points) // 3
+    return one_pass, len(sample)
+
+
 def run_reference(args):
     """The reference's own multiprocessing CPU path on this box's host cores: its core.generate with
     workers = all host threads, on the same workload as our arm."""
@@ -235,15 +267,29 @@ def run_reference(args):
     except ImportError as e:
         ref, kind, how = None, 'port', 'baseline/_ref unavailable (%s): oracle port, ThreadPool(%d)' % (e, cores)
     times, tris, eval_only = [], 0, None
+    n_batches = ((w['n'] + BATCH - 1) // BATCH) ** 3
+    sample_note = 'the whole lattice per step (%d batches)' % n_batches
     if ref is not None:
         f = models.CONFIGS[w['model']](ref)
+        if args.gpus > 1:
+            # N > 1: the lattice is N times the single-GPU one; a step is a BOUNDED sample of it -- a seeded 1/N of
+            # its batches through the reference's own _worker (core.py:45-60) and ThreadPool, consumed like
+            # core.generate consumes them (core.py:131-141) -- and the step time is extrapolated by N
+            one_pass, n_sample = reference_sample_pass(ref, f, w, cores, args.gpus)
+            scale = n_batches / n_sample
+            sample_note = ('a seeded sample of %d of %d batches per step through the reference\'s _worker + ThreadPool, '
+                           'time extrapolated x %.3f' % (n_sample, n_batches, scale))
+        else:
+            def one_pass():
+                return len(ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores, verbose=False)) // 3
+            scale = 1.0
         for it in range(args.warmup + args.steps):
             t = time.time()
-            pts = ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores, verbose=False)
-            dt = time.time() - t
+            n = one_pass()
+            dt = (time.time() - t) * scale
             if it >= args.warmup:
                 times.append(dt)
-                tris = len(pts) // 3
+                tris = int(round(n * scale))
         # the same pass with marching cubes stubbed out: the part that is PURELY the reference's code
         saved = sys.modules['skimage.measure'].marching_cubes
 
@@ -251,8 +297,8 @@ def run_reference(args):
             raise RuntimeError('marching cubes stubbed out')
         ref.core.measure.marching_cubes = no_mc
         t = time.time()
-        ref.generate(f, step=w['step'], bounds=w['bounds'], workers=cores, verbose=False)
-        eval_only = time.time() - t
+        one_pass()
+        eval_only = (time.time() - t) * scale
         ref.core.measure.marching_cubes = saved
     else:
         import sdf_b200
@@ -273,7 +319,7 @@ def run_reference(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(w), 'points': w['n'] ** 3, 'precision': 'f64 (the reference arithmetic)'},
             'cpu_baseline': {'value': val, 'unit': 'Mpoints/s', 'cores': cores, 'kind': kind,
-                             'sample': 'the whole lattice per step (%d batches); %s' % (((w['n'] + BATCH - 1) // BATCH) ** 3, how),
+                             'sample': '%s; %s' % (sample_note, how),
                              'eval_and_skip_only_mpoints_per_s': (covered / eval_only / 1e6) if eval_only else None},
             'mtris_per_s': tris / (ms / 1e3) / 1e6, 'triangles': tris,
             'e2e': {'value': val, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
