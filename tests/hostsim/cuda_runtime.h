@@ -1,0 +1,331 @@
+// Host stand-in for <cuda_runtime.h>: TEST INFRASTRUCTURE, never part of the product.
+//
+// The device code of this repository (sdf_b200/csrc/sdf_ops.cuh, sdf_kernels.cuh) is written as
+// templated `__device__` bodies.  tests/util_hostsim.py compiles those very files with g++ against
+// this header, so that the CPU test suite (no GPU in the build container) executes the kernels' own
+// source: CUDA threads become fibers (ucontext) of one host thread, a CTA is a set of fibers run
+// round-robin, `__syncthreads` / warp collectives are rendezvous points between fibers, atomics are
+// plain read-modify-writes (one host thread), `__shared__` is function-static storage (CTAs run one
+// after another), a TMA bulk copy is a memcpy that completes its mbarrier at once.
+//
+// What this does NOT model: memory ordering, bank conflicts, MUFU approximation error (the FAST math
+// policy runs its own formulas -- Cody-Waite reduction, polynomial atan2, the rotation form of the
+// circular array -- on correctly rounded host functions, optionally perturbed: HOSTSIM_FAST_ULPS),
+// timing.  It checks the LOGIC of the kernels: index arithmetic, masks, compaction, list protocols,
+// table look-ups, the marching-cubes arithmetic.
+#pragma once
+#include <algorithm>
+#include <float.h>
+#include <functional>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <vector>
+
+#define HOSTSIM 1
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __constant__ static
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define __launch_bounds__(...)
+#define __grid_constant__
+
+struct uint2 { unsigned int x, y; };
+struct uint3 { unsigned int x, y, z; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct float3 { float x, y, z; };
+struct dim3 { unsigned int x, y, z; dim3(unsigned int a = 1, unsigned int b = 1, unsigned int c = 1) : x(a), y(b), z(c) {} };
+static inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 r; r.x = x; r.y = y; return r; }
+
+namespace hostsim {
+
+struct Warp {
+    uint32_t alive = 0, arrived = 0, gen = 0;
+    uint64_t buf[2][32];
+    uint32_t part[2] = {0, 0};          // lanes that took part in the collective of buffer 0 / 1
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    bool done = false;
+};
+
+struct State {
+    uint3 thread_idx{0, 0, 0}, block_idx{0, 0, 0}, block_dim{1, 1, 1}, grid_dim{1, 1, 1};
+    int cur = -1;
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    std::vector<char*> stacks;
+    unsigned alive = 0, bar_arrived = 0, bar_gen = 0;
+    Warp warps[32];
+    unsigned long progress = 0;
+    unsigned char* dyn = nullptr;
+    size_t dyn_cap = 0;
+    std::function<void()> body;
+    unsigned long launches = 0, switches = 0;
+    // FAST-policy error injection: relative perturbation of approximate div / sqrt / sin / cos results, in units
+    // of 2^-23 (0 = none); a deterministic hash of the operands picks the sign and magnitude
+    double fast_ulps = 0.0;
+};
+
+inline State S;
+static constexpr size_t kStackBytes = 256 * 1024;
+
+inline void die(const char* what) {
+    fprintf(stderr, "hostsim: %s (block %u, thread %u)\n", what, S.block_idx.x, S.thread_idx.x);
+    abort();
+}
+
+inline void yield() {
+    ++S.switches;
+    Fiber& f = S.fibers[(size_t)S.cur];
+    swapcontext(&f.ctx, &S.sched);
+}
+
+inline void release_block_barrier() { S.bar_arrived = 0; ++S.bar_gen; ++S.progress; }
+inline void release_warp(Warp& w) { w.part[w.gen & 1u] = w.alive; w.arrived = 0; ++w.gen; ++S.progress; }
+
+inline void sync_block() {
+    const unsigned g = S.bar_gen;
+    ++S.bar_arrived; ++S.progress;
+    if (S.bar_arrived == S.alive) { release_block_barrier(); return; }
+    while (S.bar_gen == g) yield();
+    ++S.progress;
+}
+
+// every live lane of the warp deposits a 64-bit word; returns the buffer all of them can read until the
+// warp's next collective has completed (two buffers alternate)
+inline const uint64_t* warp_gather(unsigned mask, uint64_t v, uint32_t* alive_out = nullptr) {
+    if (mask != 0xffffffffu) die("warp collectives are modelled for the full mask only");
+    const unsigned tid = S.thread_idx.x;
+    Warp& w = S.warps[tid >> 5];
+    const uint32_t g = w.gen;
+    uint64_t* b = w.buf[g & 1u];
+    b[tid & 31u] = v;
+    ++w.arrived; ++S.progress;
+    if (w.arrived == (uint32_t)__builtin_popcount(w.alive)) release_warp(w);
+    else {
+        while (w.gen == g) yield();
+        ++S.progress;
+    }
+    if (alive_out) *alive_out = w.part[g & 1u];       // (not w.alive: lanes resumed earlier may have exited since)
+    return b;
+}
+
+inline void fiber_exit() {
+    const unsigned tid = S.thread_idx.x;
+    Fiber& f = S.fibers[(size_t)S.cur];
+    f.done = true;
+    --S.alive; ++S.progress;
+    Warp& w = S.warps[tid >> 5];
+    w.alive &= ~(1u << (tid & 31u));
+    // an exited thread no longer takes part: barriers the others wait at may now be complete
+    if (w.arrived != 0 && w.arrived == (uint32_t)__builtin_popcount(w.alive)) release_warp(w);
+    if (S.bar_arrived != 0 && S.bar_arrived == S.alive) release_block_barrier();
+    swapcontext(&f.ctx, &S.sched);
+    die("resumed a finished fiber");
+}
+
+inline void trampoline() {
+    S.body();
+    fiber_exit();
+}
+
+inline unsigned char* dyn_smem() { return S.dyn; }
+
+// Run `body` as a grid of `grid` CTAs of `block` threads (1-D), CTA after CTA.
+inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::function<void()> body) {
+    if (block == 0 || block > 1024) die("bad block size");
+    if (dyn_bytes > S.dyn_cap) {
+        free(S.dyn);
+        S.dyn = (unsigned char*)aligned_alloc(128, (dyn_bytes + 127) & ~(size_t)127);
+        S.dyn_cap = dyn_bytes;
+    }
+    while (S.stacks.size() < block) {
+        void* p = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+        if (p == MAP_FAILED) die("fiber stack allocation failed");
+        S.stacks.push_back((char*)p);
+    }
+    ++S.launches;
+    S.body = std::move(body);
+    S.grid_dim = uint3{grid, 1, 1};
+    S.block_dim = uint3{block, 1, 1};
+    S.fibers.resize(block);
+    for (unsigned b = 0; b < grid; ++b) {
+        S.block_idx = uint3{b, 0, 0};
+        S.alive = block; S.bar_arrived = 0;
+        for (unsigned wi = 0; wi < 32; ++wi) {
+            Warp& w = S.warps[wi];
+            const unsigned lo = wi * 32;
+            const unsigned n = lo >= block ? 0u : std::min(32u, block - lo);
+            w.alive = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            w.arrived = 0;
+        }
+        for (unsigned t = 0; t < block; ++t) {
+            Fiber& f = S.fibers[t];
+            f.done = false;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = S.stacks[t];
+            f.ctx.uc_stack.ss_size = kStackBytes;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())trampoline, 0);
+        }
+        for (;;) {
+            const unsigned long before = S.progress;
+            bool any = false;
+            for (unsigned t = 0; t < block; ++t) {
+                Fiber& f = S.fibers[t];
+                if (f.done) continue;
+                any = true;
+                S.cur = (int)t;
+                S.thread_idx = uint3{t, 0, 0};
+                swapcontext(&S.sched, &f.ctx);
+            }
+            if (!any) break;
+            if (S.progress == before) die("deadlock: a full pass over the CTA's threads changed nothing");
+        }
+    }
+    S.cur = -1;
+    S.body = nullptr;
+}
+
+template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+
+// deterministic pseudo-random relative perturbation in [-ulps, +ulps] * 2^-23 (FAST-policy error injection)
+inline float perturb(float r, float a, float b) {
+    if (S.fast_ulps == 0.0 || !isfinite(r)) return r;
+    uint32_t h = (uint32_t)to_bits(a) * 0x9e3779b1u ^ ((uint32_t)to_bits(b) + 0x7f4a7c15u) * 0x85ebca6bu;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    const double u = ((double)(h & 0xffffffu) / (double)0x7fffff) - 1.0;           // [-1, 1]
+    return (float)((double)r * (1.0 + u * S.fast_ulps * 1.1920928955078125e-07));
+}
+inline float perturb_abs(float r, float a, double abs_err) {
+    if (S.fast_ulps == 0.0 || !isfinite(r)) return r;
+    uint32_t h = (uint32_t)to_bits(a) * 0x9e3779b1u + 0x165667b1u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    const double u = ((double)(h & 0xffffffu) / (double)0x7fffff) - 1.0;
+    return (float)((double)r + u * abs_err);
+}
+inline float sqrt_approx(float x) { return perturb(sqrtf(x), x, 0.5f); }
+
+// mbarrier + TMA bulk copy: the 64-bit barrier word counts completed phases; a bulk copy is a memcpy that
+// completes the phase at once
+inline void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
+inline void mbar_expect_tx(uint64_t*, unsigned) {}
+inline void mbar_wait(uint64_t* bar, unsigned parity) {
+    while ((unsigned)(*bar & 1u) == (parity & 1u)) yield();
+    ++S.progress;
+}
+inline void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    if ((bytes & 15u) != 0 || ((uintptr_t)dst & 15u) != 0 || ((uintptr_t)src & 15u) != 0) die("cp.async.bulk: 16-byte alignment / size");
+    memcpy(dst, src, bytes);
+    *bar += 1; ++S.progress;
+}
+
+}  // namespace hostsim
+
+#define threadIdx (hostsim::S.thread_idx)
+#define blockIdx (hostsim::S.block_idx)
+#define blockDim (hostsim::S.block_dim)
+#define gridDim (hostsim::S.grid_dim)
+
+// ------------------------------------------------------------------------------- synchronisation, collectives
+static inline void __syncthreads() { hostsim::sync_block(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { hostsim::warp_gather(mask, 0); }
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline void __threadfence_block() {}
+
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
+    return hostsim::from_bits<T>(hostsim::warp_gather(mask, hostsim::to_bits(v))[src & 31]);
+}
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask) {
+    const unsigned lane = threadIdx.x & 31u;
+    return hostsim::from_bits<T>(hostsim::warp_gather(mask, hostsim::to_bits(v))[(lane ^ (unsigned)lanemask) & 31u]);
+}
+template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t* b = hostsim::warp_gather(mask, hostsim::to_bits(v));
+    return lane >= delta ? hostsim::from_bits<T>(b[lane - delta]) : v;
+}
+static inline unsigned __ballot_sync(unsigned mask, bool pred) {
+    uint32_t alive = 0;
+    const uint64_t* b = hostsim::warp_gather(mask, pred ? 1u : 0u, &alive);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if (((alive >> i) & 1u) && b[i]) r |= 1u << i;
+    return r;
+}
+static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
+static inline bool __all_sync(unsigned mask, bool pred) { return __ballot_sync(mask, !pred) == 0u; }
+
+// ------------------------------------------------------------------------------- atomics (one host thread)
+template <class T> static inline T hostsim_rmw_add(T* p, T v) { const T o = *p; *p = (T)(o + v); return o; }
+static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return hostsim_rmw_add(p, v); }
+static inline int atomicAdd(int* p, int v) { return hostsim_rmw_add(p, v); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return hostsim_rmw_add(p, v); }
+static inline unsigned long long atomicAdd_system(unsigned long long* p, unsigned long long v) { return hostsim_rmw_add(p, v); }
+static inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned int atomicMax(unsigned int* p, unsigned int v) { const unsigned int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned int atomicOr(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o | v; return o; }
+
+// ------------------------------------------------------------------------------- loads, bit tricks
+template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
+static inline int __float_as_int(float f) { return hostsim::from_bits<int>(hostsim::to_bits(f)); }
+static inline unsigned int __float_as_uint(float f) { return hostsim::from_bits<unsigned int>(hostsim::to_bits(f)); }
+static inline float __int_as_float(int i) { return hostsim::from_bits<float>(hostsim::to_bits(i)); }
+static inline double __longlong_as_double(long long v) { return hostsim::from_bits<double>(hostsim::to_bits(v)); }
+static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) { hostsim::yield(); }
+static inline void __trap() { hostsim::die("__trap"); }
+
+// ------------------------------------------------------------------------------- arithmetic with fixed rounding
+// (the translation unit is compiled with -ffp-contract=off: a plain operation IS the _rn intrinsic)
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __drcp_rn(double a) { return 1.0 / a; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+// approximate units of the FAST math policy
+static inline float __fdividef(float a, float b) { return hostsim::perturb(a / b, a, b); }
+static inline void hostsim_fast_sincosf(float a, float* s, float* c) {
+    float ss, cc;
+    sincosf(a, &ss, &cc);
+    *s = hostsim::perturb_abs(ss, a, 4.0e-7 * (hostsim::S.fast_ulps > 0 ? 1.0 : 0.0));
+    *c = hostsim::perturb_abs(cc, -a, 4.0e-7 * (hostsim::S.fast_ulps > 0 ? 1.0 : 0.0));
+}
+
+#define __sincosf hostsim_fast_sincosf          // (glibc declares a __sincosf of its own)
+
+// CUDA's global min / max overloads
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? a : b; }
+static inline unsigned int max(unsigned int a, unsigned int b) { return a > b ? a : b; }
+static inline unsigned int min(int a, unsigned int b) { return (unsigned int)a < b ? (unsigned int)a : b; }
+static inline unsigned int min(unsigned int a, int b) { return a < (unsigned int)b ? a : (unsigned int)b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
