@@ -9,7 +9,19 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
         sys.path.insert(0, p)
 
 
+def pytest_addoption(parser):
+    parser.addoption('--hostsim', action='store_true', default=False,
+                     help='TEST INFRASTRUCTURE: run against the C-ABI library compiled for the HOST (tests/hostsim/: kernels on a '
+                          'SIMT stand-in, no GPU) instead of sdf_b200/libsdfb200.so -- how tests/test_hostsim_library_cpu.py '
+                          'runs a selection of the -m gpu tests where there is no GPU')
+
+
 def pytest_configure(config):
+    if config.getoption('--hostsim'):
+        import util_hostsim
+        from sdf_b200 import _abi
+        _abi.LIB_PATH = util_hostsim.build_library()            # before the first _abi.lib() call of this process
+        os.environ.setdefault('SDFB200_JIT', '0')                # no run-time compiled kernels on the host
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
     config.addinivalue_line('markers', 'fullsize: GPU parity at the sizes BASELINE.json states (minutes of CPU oracle time; also marked gpu)')
 

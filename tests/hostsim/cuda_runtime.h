@@ -329,3 +329,140 @@ static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+// =====================================================================================================
+// Host API stand-in: what sdfb200.cu / sdfb200_weld.cu call.  Everything executes at call time (a stream is a
+// label), device memory is host memory kept in a registry so that cudaPointerGetAttributes can tell it from
+// the caller's buffers, one fake device with HOSTSIM_SMS "SMs" (default 3: small grids, fast emulation).
+// Stream capture and loading run-time compiled cubins are refused, which sends the library down
+// its documented fallbacks (plain launches instead of a graph; interpreter kernels instead of NVRTC output).
+#include <chrono>
+#include <map>
+#include <tuple>
+#include <utility>
+
+typedef int cudaError_t;
+enum {
+    cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100,
+    cudaErrorInvalidDevice = 101, cudaErrorNotReady = 600, cudaErrorNotSupported = 801
+};
+struct hostsim_stream_ { int id; };
+struct hostsim_event_ { std::chrono::steady_clock::time_point t; };
+typedef hostsim_stream_* cudaStream_t;
+typedef hostsim_event_* cudaEvent_t;
+typedef struct hostsim_graph_* cudaGraph_t;
+typedef struct hostsim_graph_exec_* cudaGraphExec_t;
+typedef struct hostsim_kernel_* cudaKernel_t;
+typedef struct hostsim_library_* cudaLibrary_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2, cudaHostRegisterPortable = 1,
+       cudaEventRecordExternal = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1,
+       cudaStreamCaptureModeThreadLocal = 1, cudaDevAttrMultiProcessorCount = 16,
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+
+namespace hostsim {
+struct Region { size_t bytes; cudaMemoryType type; bool owned; };
+inline std::map<uintptr_t, Region>& regions() { static std::map<uintptr_t, Region> r; return r; }
+inline const Region* find_region(const void* p, uintptr_t* base = nullptr) {
+    auto& r = regions();
+    auto it = r.upper_bound((uintptr_t)p);
+    if (it == r.begin()) return nullptr;
+    --it;
+    if ((uintptr_t)p >= it->first + it->second.bytes) return nullptr;
+    if (base) *base = it->first;
+    return &it->second;
+}
+inline cudaError_t alloc(void** out, size_t bytes, cudaMemoryType type) {
+    void* p = aligned_alloc(256, (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255);
+    if (!p) return cudaErrorMemoryAllocation;
+    memset(p, 0xcd, std::max<size_t>(bytes, 1));                // device memory is not zero on arrival
+    regions()[(uintptr_t)p] = Region{std::max<size_t>(bytes, 1), type, true};
+    *out = p;
+    return cudaSuccess;
+}
+inline int device_count() { const char* e = getenv("HOSTSIM_DEVICES"); return e ? atoi(e) : 1; }
+inline int sm_count() { const char* e = getenv("HOSTSIM_SMS"); return e && atoi(e) > 0 ? atoi(e) : 3; }
+
+template <class... KA, class... A>
+inline void launch_kernel(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t, A&&... args) {
+    std::tuple<std::decay_t<KA>...> held(std::forward<A>(args)...);       // kernel parameters are copied at launch
+    launch(grid, block, smem, [&] { std::apply(k, held); });
+}
+}  // namespace hostsim
+
+static inline const char* cudaGetErrorString(cudaError_t e) {
+    switch (e) {
+        case cudaSuccess: return "no error";
+        case cudaErrorMemoryAllocation: return "out of memory";
+        case cudaErrorNotSupported: return "operation not supported (host execution)";
+        case cudaErrorNotReady: return "not ready";
+        default: return "error (host execution)";
+    }
+}
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = hostsim::device_count(); return *n > 0 ? cudaSuccess : cudaErrorNoDevice; }
+static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < hostsim::device_count() ? cudaSuccess : cudaErrorInvalidDevice; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
+    *v = attr == cudaDevAttrMultiProcessorCount ? hostsim::sm_count() : 0;
+    return cudaSuccess;
+}
+template <class P> static inline cudaError_t cudaMalloc(P** p, size_t bytes) { return hostsim::alloc((void**)p, bytes, cudaMemoryTypeDevice); }
+template <class P> static inline cudaError_t cudaMallocHost(P** p, size_t bytes) { return hostsim::alloc((void**)p, bytes, cudaMemoryTypeHost); }
+static inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return hostsim::alloc(p, bytes, cudaMemoryTypeHost); }
+static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    auto it = hostsim::regions().find((uintptr_t)p);
+    if (it == hostsim::regions().end() || !it->second.owned) return cudaErrorInvalidValue;
+    hostsim::regions().erase(it);
+    free(p);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+static inline cudaError_t cudaHostRegister(void* p, size_t bytes, unsigned) {
+    hostsim::regions()[(uintptr_t)p] = hostsim::Region{bytes, cudaMemoryTypeHost, false};
+    return cudaSuccess;
+}
+static inline cudaError_t cudaHostUnregister(void* p) { hostsim::regions().erase((uintptr_t)p); return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+    const hostsim::Region* r = hostsim::find_region(p);
+    a->type = r ? r->type : cudaMemoryTypeUnregistered;
+    a->device = 0; a->devicePointer = (void*)p; a->hostPointer = (void*)p;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new hostsim_stream_{1}; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new hostsim_event_(); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new hostsim_event_(); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t, unsigned) { return cudaEventRecord(e); }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaLibraryLoadData(cudaLibrary_t*, const void*, void*, void*, unsigned, void*, void*, unsigned) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaLibraryUnload(cudaLibrary_t) { return cudaSuccess; }
+static inline cudaError_t cudaLibraryGetKernel(cudaKernel_t*, cudaLibrary_t, const char*) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaKernelSetAttributeForDevice(cudaKernel_t, int, int, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// one process, one address space: an IPC handle is the pointer itself (several "ranks" of a test share a process)
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -60,6 +60,81 @@ def patched_sources(dst):
     open(os.path.join(dst, 'sdf_kernels.cuh'), 'w').write(k)
 
 
+def rewrite_launches(text):
+    """`kernel<targs><<<grid, block, smem, stream>>>(args);` -> `hostsim::launch_kernel(kernel<targs>, grid, block, smem,
+    stream, args);` (the one piece of CUDA syntax a host compiler cannot parse).  Returns (text, launches rewritten)."""
+    out, pos, count = [], 0, 0
+    while True:
+        k = text.find('<<<', pos)
+        if k < 0:
+            break
+        # the kernel expression: identifier, optionally followed by a template argument list
+        b = k
+        if text[b - 1] == '>':
+            depth = 0
+            while True:
+                b -= 1
+                depth += {'>': 1, '<': -1}.get(text[b], 0)
+                if depth == 0:
+                    break
+        while b > 0 and (text[b - 1].isalnum() or text[b - 1] in '_:'):
+            b -= 1
+        e = text.index('>>>', k)
+        assert text[e + 3] == '(', text[k - 40:e + 10]
+        depth, a = 0, e + 3
+        while True:
+            depth += {'(': 1, ')': -1}.get(text[a], 0)
+            if depth == 0:
+                break
+            a += 1
+        args = text[e + 4:a].strip()
+        out.append(text[pos:b])
+        out.append('hostsim::launch_kernel(%s, %s%s)' % (text[b:k], text[k + 3:e], ', ' + args if args else ''))
+        pos = a + 1
+        count += 1
+    out.append(text[pos:])
+    return ''.join(out), count
+
+
+def patched_library_sources(dst):
+    """sdfb200.cu / sdfb200_weld.cu for the host compiler: launches rewritten, nothing else touched."""
+    patched_sources(dst)
+    shutil.copy(os.path.join(CSRC, 'sdf_jit_entry.cuh'), os.path.join(dst, 'sdf_jit_entry.cuh'))
+    expected = {'sdfb200.cu': 20, 'sdfb200_weld.cu': 4}
+    for f, n_expected in expected.items():
+        text = open(os.path.join(CSRC, f)).read()
+        text, n = rewrite_launches(text)
+        assert n == n_expected, '%s: %d launches rewritten, expected %d: the host source changed' % (f, n, n_expected)
+        text = text.replace('#include "../../include/sdfb200.h"', '#include "%s"' % os.path.join(ROOT, 'include', 'sdfb200.h'))
+        open(os.path.join(dst, f.replace('.cu', '.cpp')), 'w').write(text)
+
+
+def build_library():
+    """The WHOLE C-ABI library (sdfb200.cu + sdfb200_weld.cu + the kernels) compiled for the host: same exports as
+    sdf_b200/libsdfb200.so, kernels executed by the SIMT stand-in, CUDA runtime calls by its host API stand-in."""
+    if shutil.which('g++') is None:
+        pytest.skip('no g++')
+    srcs = [os.path.join(CSRC, f) for f in ('sdf_ops.cuh', 'sdf_kernels.cuh', 'sdf_opcodes.h', 'mc_tables.inc', 'sdfb200.cu',
+                                            'sdfb200_weld.cu', 'sdf_jit_entry.cuh')]
+    srcs += [os.path.join(HS, 'cuda_runtime.h'), os.path.join(HS, 'cub', 'device', 'device_radix_sort.cuh'),
+             os.path.join(HS, 'cub', 'device', 'device_scan.cuh'), os.path.join(ROOT, 'include', 'sdfb200.h'),
+             os.path.abspath(__file__)]
+    key = _digest(*srcs)
+    so = os.path.join(BUILD, 'libsdfb200_hostsim_%s.so' % key)
+    if os.path.exists(so):
+        return so
+    work = os.path.join(BUILD, 'lib_%s' % key)
+    patched_library_sources(work)
+    flags = ['-std=c++17', '-O1', '-fPIC', '-shared', '-ffp-contract=off', '-fno-strict-aliasing', '-Wno-unknown-pragmas',
+             '-I', work, '-I', HS]
+    tmp = so + '.%d.tmp' % os.getpid()
+    r = subprocess.run(['g++'] + flags + [os.path.join(work, 'sdfb200.cpp'), os.path.join(work, 'sdfb200_weld.cpp'), '-o', tmp,
+                                          '-ldl', '-lpthread'], capture_output=True, text=True)
+    assert r.returncode == 0, 'hostsim library build failed:\n' + r.stderr[-8000:]
+    os.replace(tmp, so)
+    return so
+
+
 def _digest(*paths, extra=''):
     h = hashlib.sha256(extra.encode())
     for p in paths:
