@@ -1,0 +1,117 @@
+"""Host-orchestration paths of sdfb200.cu that small lattices do not reach on their own, driven on the host-compiled
+library (run by tests/test_hostsim_library_cpu.py in a child process started with --hostsim; not collected directly).
+
+  * rounds cut by the HOST: tile volumes beyond the budget (24 GB on the GPU, a few tiles here)
+  * the retry after a work-list overflow (lists start at 1 M entries on the GPU, at 64 here)
+  * host output pipelined over device-cut rounds (SDFB200_PIPE): progress words, partial copies
+  * device-resident output, count-only calls, a Z-slab of whole batch layers
+"""
+import os
+
+import numpy as np
+import pytest
+
+import models
+from util_cmp import compare_soups
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def case():
+    import sdf_b200 as S
+    from oracle import sdf_ref
+    from sdf_b200 import core
+    f = models.cfg_csg(S)
+    bounds, step = ((-1, -1, -1), (1, 1, 1)), 2.0 / 96
+    _, _, (X, Y, Z) = core.make_lattice(f, step, bounds)
+    h, _ = core.program_handle(f)
+    tau = core.mixed_tau(h.program, X, Y, Z)
+    rpts, rst = sdf_ref.generate(f, step=step, bounds=bounds)
+    return dict(S=S, f=f, h=h, X=X, Y=Y, Z=Z, tau=tau, rpts=rpts, rst=rst, step=step, bounds=bounds)
+
+
+def _run(case, precision='exact', zb=(0, -1)):
+    h = case['h']
+    n, stats, _ = h.generate(case['X'], case['Y'], case['Z'], 32, True, precision, case['tau'], None, 0, zb=zb)
+    out = np.empty((n + 8, 9), np.float32)
+    out[n:] = -777.0
+    n2, stats2, _ = h.generate(case['X'], case['Y'], case['Z'], 32, True, precision, case['tau'], out, n, zb=zb)
+    assert n2 == n and tuple(stats2[:3]) == tuple(stats[:3]) and np.all(out[n:] == -777.0)
+    return out[:n], stats2
+
+
+def _same_as_oracle(case, tris, stats):
+    rst = case['rst']
+    assert tuple(int(v) for v in stats[:3]) == (rst['skipped'], rst['empty'], rst['nonempty']), (stats, rst)
+    rep = compare_soups(tris.reshape(-1, 3), case['rpts'])
+    assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'] and rep['n_ref'] > 50000, rep
+
+
+def _debug_lines(capfd):
+    """The library's SDFB200_DEBUG line per attempt: counters after the last round of the attempt."""
+    import re
+    out = []
+    for line in capfd.readouterr().err.splitlines():
+        m = re.match(r'\[sdfb200\] n_active=(\d+) n_slots=(\d+) n_cubes=(\d+) n_pts=(\d+) max=(\d+)/(\d+) caps=(\d+)/(\d+)', line)
+        if m:
+            out.append(dict(zip(('n_active', 'n_slots', 'n_cubes', 'n_pts', 'max_cubes', 'max_pts', 'cube_cap', 'pt_cap'),
+                                (int(v) for v in m.groups()))))
+    return out
+
+
+@pytest.mark.parametrize('precision', ['exact', 'f64'])
+def test_host_cut_rounds(case, precision, monkeypatch, capfd):
+    """Tile volumes beyond the budget: the host reads the active count after the pre-pass and runs rounds of
+    `budget` tiles over the same lists (27 batches, 2 tiles per round here)."""
+    monkeypatch.setenv('HOSTSIM_VOL_BUDGET', str(2 * 35968 * 4))
+    monkeypatch.setenv('SDFB200_DEBUG', '1')
+    tris, stats = _run(case, precision)
+    _same_as_oracle(case, tris, stats)
+    dbg = _debug_lines(capfd)
+    assert dbg and all(d['n_slots'] <= 2 and d['n_active'] > 10 for d in dbg), dbg       # the last round held <= 2 tiles
+
+
+def test_work_list_overflow_is_retried(case, monkeypatch, capfd):
+    """Lists that start far too small: the call notices the high-water marks, grows the lists and starts over from a
+    clean slate (the pre-pass results stay valid); the result is the one of a call that never overflowed."""
+    monkeypatch.setenv('HOSTSIM_MIN_CUBES', '64')
+    monkeypatch.setenv('SDFB200_DEBUG', '1')
+    from sdf_b200 import _abi
+    h = _abi.ProgramHandle(case['h'].program)    # a fresh handle: its device context has no lists yet
+    c = dict(case, h=h)
+    tris, stats = _run(c)
+    _same_as_oracle(case, tris, stats)
+    dbg = _debug_lines(capfd)
+    assert dbg[0]['max_cubes'] > dbg[0]['cube_cap'] == 64, dbg                           # first attempt: overflow
+    assert dbg[1]['max_cubes'] <= dbg[1]['cube_cap'] and dbg[1]['max_pts'] <= dbg[1]['pt_cap'], dbg
+    assert len(dbg) == 3, dbg                                                             # the second call fits at once
+
+
+@pytest.mark.parametrize('rounds', [1, 3, 16])
+def test_pipelined_host_output(case, rounds, monkeypatch):
+    """Host output of a big enough lattice is cut into rounds ON THE DEVICE; each round's extraction reports through
+    mapped progress words and its triangles are copied while the next round runs."""
+    monkeypatch.setenv('SDFB200_PIPE', str(rounds))
+    S = case['S']
+    f = models.cfg_gearlike(S)
+    L, n = 2.5, 128                              # 2^21 samples: the smallest lattice that pipelines
+    pts, info = S.generate(f, step=2 * L / n, bounds=((-L, -L, -L), (L, L, L)), verbose=False, return_info=True)
+    from oracle import sdf_ref
+    rpts, rst = sdf_ref.generate(f, step=2 * L / n, bounds=((-L, -L, -L), (L, L, L)))
+    assert (info['skipped'], info['empty'], info['nonempty']) == (rst['skipped'], rst['empty'], rst['nonempty'])
+    rep = compare_soups(pts, rpts)
+    assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'] and rep['n_ref'] > 30000, rep
+
+
+def test_z_slabs_add_up(case):
+    """Whole batch layers [zb0, zb1): the slabs' soups and statistics add up to the whole call's."""
+    whole, st = _run(case)
+    parts, tot = [], np.zeros(3, np.int64)
+    for zb in ((0, 1), (1, 2), (2, 3)):
+        t, s = _run(case, zb=zb)
+        parts.append(t)
+        tot += np.asarray(s[:3])
+    assert tuple(tot) == tuple(st[:3])
+    rep = compare_soups(np.concatenate(parts).reshape(-1, 3), whole.reshape(-1, 3))
+    assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], rep

@@ -23,6 +23,8 @@ SELECTIONS = {
     'closures_textures_c_client': (['tests/test_gpu_zzz_texture.py', 'tests/test_gpu_closure.py', 'tests/test_gpu_zzz_cabi_client.py'], ''),
     'weld_windows': (['tests/test_gpu_weld.py', 'tests/test_gpu_windows.py'], 'sphere or csg'),
     'guardband': (['tests/test_gpu_guardband.py'], 'twist_fast or scaled_up or square_jump'),
+    # paths of sdfb200.cu's orchestration that only sizes beyond any emulation reach on a GPU (tests/hostsim_paths.py)
+    'host_cut_rounds_overflow_retry_pipelined_output_slabs': (['tests/hostsim_paths.py'], ''),
 }
 
 

@@ -106,6 +106,16 @@ def patched_library_sources(dst):
         text, n = rewrite_launches(text)
         assert n == n_expected, '%s: %d launches rewritten, expected %d: the host source changed' % (f, n, n_expected)
         text = text.replace('#include "../../include/sdfb200.h"', '#include "%s"' % os.path.join(ROOT, 'include', 'sdfb200.h'))
+        if f == 'sdfb200.cu':
+            # two sizing constants become knobs of the host build, so that a 64^3 lattice can drive the paths a GPU only
+            # takes at sizes no emulation reaches: rounds cut by the HOST (tile volumes beyond the 24 GB budget) and the
+            # retry after a work-list overflow ($HOSTSIM_VOL_BUDGET bytes, $HOSTSIM_MIN_CUBES entries)
+            text = _sub(text, r'static const size_t kVolBudgetBytes = \(size_t\)24 << 30;',
+                        '#define kVolBudgetBytes (getenv("HOSTSIM_VOL_BUDGET") ? (size_t)atoll(getenv("HOSTSIM_VOL_BUDGET")) '
+                        ': (size_t)24 << 30)', 1)
+            text = _sub(text, r'std::max<size_t>\(\(size_t\)1 << 20, est_tiles \* 3072\)',
+                        'std::max<size_t>(getenv("HOSTSIM_MIN_CUBES") ? (size_t)atoll(getenv("HOSTSIM_MIN_CUBES")) : (size_t)1 << 20, '
+                        '(getenv("HOSTSIM_MIN_CUBES") ? (size_t)0 : est_tiles * 3072))', 1)
         open(os.path.join(dst, f.replace('.cu', '.cpp')), 'w').write(text)
 
 
