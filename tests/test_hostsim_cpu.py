@@ -348,3 +348,24 @@ def test_stl_record_kernel_bytes_equal_the_reference_writer(S, sims, tmp_path):
         raw = path.read_bytes()
         assert int(np.frombuffer(raw[80:84], '<u4')[0]) == n
         assert rec.tobytes() == raw[84:], n
+
+
+# ------------------------------------------------------------------------------------------ memcheck
+
+def test_kernels_are_clean_under_address_and_undefined_behaviour_sanitizers():
+    """tests/hostsim/sanitize_run.py: every kernel body (all four precisions, ragged lattices, sub-tiled batches, the
+    stream evaluators' ring and fallback path, a too-small result buffer, caller volumes, STL records) with ASan +
+    UBSan instrumentation: no out-of-bounds access to a shared array, a work list or a staged table, no undefined shift."""
+    import os
+    import subprocess
+    import sys
+    pre = U.sanitizer_preload()
+    if pre is None:
+        pytest.skip('no libasan / libubsan next to g++')
+    env = dict(os.environ, LD_PRELOAD=pre, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0',
+               UBSAN_OPTIONS='print_stacktrace=1')
+    r = subprocess.run([sys.executable, os.path.join(U.HS, 'sanitize_run.py')], env=env, capture_output=True, text=True,
+                       timeout=1500)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0 and 'SANITIZED RUN COMPLETE' in r.stdout, tail
+    assert 'ERROR: AddressSanitizer' not in r.stderr and 'runtime error:' not in r.stderr, tail

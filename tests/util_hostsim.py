@@ -119,8 +119,9 @@ def patched_library_sources(dst):
         open(os.path.join(dst, f.replace('.cu', '.cpp')), 'w').write(text)
 
 
-def build_library():
-    """The WHOLE C-ABI library (sdfb200.cu + sdfb200_weld.cu + the kernels) compiled for the host: same exports as
+def build_library(sanitize=None):
+    """``sanitize`` (default: $HOSTSIM_SANITIZE): ASan + UBSan instrumentation; the process must preload libasan.
+    The WHOLE C-ABI library (sdfb200.cu + sdfb200_weld.cu + the kernels) compiled for the host: same exports as
     sdf_b200/libsdfb200.so, kernels executed by the SIMT stand-in, CUDA runtime calls by its host API stand-in."""
     if shutil.which('g++') is None:
         pytest.skip('no g++')
@@ -129,7 +130,9 @@ def build_library():
     srcs += [os.path.join(HS, 'cuda_runtime.h'), os.path.join(HS, 'cub', 'device', 'device_radix_sort.cuh'),
              os.path.join(HS, 'cub', 'device', 'device_scan.cuh'), os.path.join(ROOT, 'include', 'sdfb200.h'),
              os.path.abspath(__file__)]
-    key = _digest(*srcs)
+    if sanitize is None:
+        sanitize = bool(os.environ.get('HOSTSIM_SANITIZE'))
+    key = _digest(*srcs, extra='asan' if sanitize else '')
     so = os.path.join(BUILD, 'libsdfb200_hostsim_%s.so' % key)
     if os.path.exists(so):
         return so
@@ -137,6 +140,8 @@ def build_library():
     patched_library_sources(work)
     flags = ['-std=c++17', '-O1', '-fPIC', '-shared', '-ffp-contract=off', '-fno-strict-aliasing', '-Wno-unknown-pragmas',
              '-I', work, '-I', HS]
+    if sanitize:
+        flags += ['-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-fno-omit-frame-pointer']
     tmp = so + '.%d.tmp' % os.getpid()
     r = subprocess.run(['g++'] + flags + [os.path.join(work, 'sdfb200.cpp'), os.path.join(work, 'sdfb200_weld.cpp'), '-o', tmp,
                                           '-ldl', '-lpthread'], capture_output=True, text=True)
@@ -152,13 +157,25 @@ def _digest(*paths, extra=''):
     return h.hexdigest()[:16]
 
 
-def build(spec_text=None):
-    """The harness as a shared library; with ``spec_text`` (a `struct SpecEval {...};`) the specialised evaluator."""
+def sanitizer_preload():
+    """LD_PRELOAD value for a process that loads a harness built with ``sanitize=True`` (None when gcc has no libasan)."""
+    libs = []
+    for name in ('libasan.so', 'libubsan.so'):
+        path = subprocess.run(['g++', '-print-file-name=' + name], capture_output=True, text=True).stdout.strip()
+        if not os.path.isabs(path) or not os.path.exists(path):
+            return None
+        libs.append(path)
+    return ':'.join(libs)
+
+
+def build(spec_text=None, sanitize=False):
+    """The harness as a shared library; with ``spec_text`` (a `struct SpecEval {...};`) the specialised evaluator;
+    ``sanitize``: AddressSanitizer + UndefinedBehaviorSanitizer instrumentation (the memcheck of this execution)."""
     if shutil.which('g++') is None:
         pytest.skip('no g++')
     srcs = [os.path.join(CSRC, f) for f in ('sdf_ops.cuh', 'sdf_kernels.cuh', 'sdf_opcodes.h', 'mc_tables.inc')]
     srcs += [os.path.join(HS, 'cuda_runtime.h'), os.path.join(HS, 'harness.cpp'), os.path.abspath(__file__)]
-    key = _digest(*srcs, extra=spec_text or '')
+    key = _digest(*srcs, extra=(spec_text or '') + ('|asan' if sanitize else ''))
     so = os.path.join(BUILD, 'hostsim_%s.so' % key)
     if os.path.exists(so):
         return so
@@ -169,6 +186,8 @@ def build(spec_text=None):
     if spec_text is not None:
         open(os.path.join(work, 'spec_eval.inc'), 'w').write(spec_text)
         flags.append('-DHOSTSIM_SPEC="spec_eval.inc"')
+    if sanitize:
+        flags += ['-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-fno-omit-frame-pointer']
     tmp = so + '.%d.tmp' % os.getpid()
     r = subprocess.run(['g++'] + flags + [os.path.join(HS, 'harness.cpp'), '-o', tmp], capture_output=True, text=True)
     assert r.returncode == 0, 'hostsim build failed:\n' + r.stderr[-6000:]
@@ -207,8 +226,8 @@ def spec_eval_text(program, kernel=4, env=None):
 class HostSim:
     """ctypes front end of the harness for one lowered program (``sdf_b200.ir.lower`` output)."""
 
-    def __init__(self, program, spec_text=None):
-        self.lib = ctypes.CDLL(build(spec_text))
+    def __init__(self, program, spec_text=None, sanitize=False):
+        self.lib = ctypes.CDLL(build(spec_text, sanitize))
         self.code = np.ascontiguousarray(program.code, np.uint32)
         self.consts = np.ascontiguousarray(program.consts, np.float64)
         if len(self.consts) == 0:
