@@ -115,3 +115,34 @@ def test_z_slabs_add_up(case):
     assert tuple(tot) == tuple(st[:3])
     rep = compare_soups(np.concatenate(parts).reshape(-1, 3), whole.reshape(-1, 3))
     assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], rep
+
+
+def test_fused_root_gather_protocol(case, monkeypatch):
+    """The multi-GPU C-ABI surface with three "ranks" played by one process (the stand-in runtime has HOSTSIM_DEVICES
+    devices and an IPC handle is the pointer itself): every rank's extraction reserves its range in the ROOT's buffer
+    through the shared cursor and signals `done`; the root waits for all signals, reads the count, consumes, releases;
+    two buffers alternate by step parity and a rank's step s waits for `ready[s & 1] == s`.  Four steps: both buffers
+    used twice.  (Between real GPUs the same calls run in tools/gpu_multi_check.py, one process per GPU.)"""
+    import ctypes
+    from sdf_b200 import _abi
+    monkeypatch.setenv('HOSTSIM_DEVICES', '3')
+    world, cap = 3, 100000
+    root = _abi.SharedOutput(cap, 0)
+    shared = [root] + [_abi.SharedOutput(cap, r, handle=root.handle) for r in (1, 2)]
+    handles = [_abi.ProgramHandle(case['h'].program) for _ in range(world)]
+    whole, st = _run(case)
+    for step in range(4):
+        which = step & 1
+        local = {}
+        for r in (2, 1, 0):                                   # the root last: its wait finds every signal in place
+            n_local, stats, _ = handles[r].generate_shared(case['X'], case['Y'], case['Z'], 32, True, 'exact', case['tau'],
+                                                           shared[r], which, zb=(r, r + 1), device=r)
+            local[r] = (n_local, tuple(int(v) for v in stats[:3]))
+        total = root.wait(which, world)
+        assert total == sum(n for n, _ in local.values()) == len(whole), (step, total, local)
+        assert tuple(np.sum([s for _, s in local.values()], axis=0)) == tuple(int(v) for v in st[:3])
+        buf = (ctypes.c_float * (total * 9)).from_address(root.buffer_ptr(which))
+        got = np.frombuffer(buf, np.float32).reshape(-1, 9).copy()
+        rep = compare_soups(got.reshape(-1, 3), whole.reshape(-1, 3))
+        assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], (step, rep)
+        root.release(which)
