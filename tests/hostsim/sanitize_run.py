@@ -17,7 +17,7 @@ from sdf_b200 import core                        # noqa: E402
 from sdf_b200.ir import lower                    # noqa: E402
 
 total = 0
-CASES = (('sphere', 33, 32, ('exact', 'f64')), ('csg', 65, 32, ('exact', 'f32')), ('gearlike', 70, 40, ('exact', 'mixed')))
+CASES = (('sphere', 33, 32, ('exact', 'f64')), ('csg', 65, 32, ('exact', 'f32')), ('gearlike', 70, 40, ('mixed',)))
 for name, n, bs, precisions in CASES:
     prog = lower(models.CONFIGS[name](S))
     hs = U.HostSim(prog, sanitize=True)

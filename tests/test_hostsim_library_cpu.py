@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SELECTIONS = {
     'engine': (['tests/test_gpu_parity.py'],
                'interp and (edge_cases or stl_bytes or user_closure or sparse_off or (generate_matches_oracle and sphere) '
-               'or (exact_mode_equals and csg) or auto_bounds or skip_flags)'),
+               'or (exact_mode_equals and csg) or skip_flags)'),
     'closures_textures_c_client': (['tests/test_gpu_zzz_texture.py', 'tests/test_gpu_closure.py', 'tests/test_gpu_zzz_cabi_client.py'], ''),
     'weld_windows': (['tests/test_gpu_weld.py', 'tests/test_gpu_windows.py'], 'sphere or csg'),
     'guardband': (['tests/test_gpu_guardband.py'], 'twist_fast or scaled_up or square_jump'),
