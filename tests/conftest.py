@@ -21,7 +21,13 @@ def pytest_configure(config):
         import util_hostsim
         from sdf_b200 import _abi
         _abi.LIB_PATH = util_hostsim.build_library()            # before the first _abi.lib() call of this process
-        os.environ.setdefault('SDFB200_JIT', '0')                # no run-time compiled kernels on the host
+        # run-time specialisation: the interpreter kernels unless a test asks (SDFB200_JIT=2); then the library's own
+        # generated source is compiled for the host by a stand-in NVRTC (tests/hostsim/fake_nvrtc.cpp)
+        os.environ.setdefault('SDFB200_JIT', '0')
+        nvrtc, inc = util_hostsim.build_fake_nvrtc()
+        os.environ['HOSTSIM_NVRTC'] = nvrtc
+        os.environ['HOSTSIM_JIT_INCLUDE'] = inc
+        os.environ['HOSTSIM_DIR'] = util_hostsim.HS
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
     config.addinivalue_line('markers', 'fullsize: GPU parity at the sizes BASELINE.json states (minutes of CPU oracle time; also marked gpu)')
 

@@ -336,6 +336,8 @@ static inline unsigned long long max(unsigned long long a, unsigned long long b)
 // the caller's buffers, one fake device with HOSTSIM_SMS "SMs" (default 3: small grids, fast emulation).
 // Stream capture and loading run-time compiled cubins are refused, which sends the library down
 // its documented fallbacks (plain launches instead of a graph; interpreter kernels instead of NVRTC output).
+#include <dlfcn.h>
+#include <unistd.h>
 #include <chrono>
 #include <map>
 #include <tuple>
@@ -390,6 +392,16 @@ template <class... KA, class... A>
 inline void launch_kernel(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t, A&&... args) {
     std::tuple<std::decay_t<KA>...> held(std::forward<A>(args)...);       // kernel parameters are copied at launch
     launch(grid, block, smem, [&] { std::apply(k, held); });
+}
+// cudaLaunchKernel's `void** args` unpacked with the parameter types of the kernel's own signature
+template <class... KA, size_t... I>
+inline void launch_args_impl(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args, std::index_sequence<I...>) {
+    std::tuple<std::decay_t<KA>...> held(*(std::decay_t<KA>*)args[I]...);
+    launch(grid, block, smem, [&] { std::apply(k, held); });
+}
+template <class... KA>
+inline void launch_args(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args) {
+    launch_args_impl(k, grid, block, smem, args, std::index_sequence_for<KA...>());
 }
 }  // namespace hostsim
 
@@ -456,10 +468,38 @@ static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, un
 static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaLibraryLoadData(cudaLibrary_t*, const void*, void*, void*, unsigned, void*, void*, unsigned) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaLibraryUnload(cudaLibrary_t) { return cudaSuccess; }
-static inline cudaError_t cudaLibraryGetKernel(cudaKernel_t*, cudaLibrary_t, const char*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return cudaErrorNotSupported; }
+// Run-time compiled kernels: a real cubin (NVRTC output) cannot be loaded -- the library then runs its interpreter
+// kernels; the "cubin" of tests/hostsim/fake_nvrtc.cpp is a host shared object and is dlopen'ed.
+static inline cudaError_t cudaLibraryLoadData(cudaLibrary_t* lib, const void* image, void*, void*, unsigned, void*, void*, unsigned) {
+    const unsigned char* e = (const unsigned char*)image;
+    if (memcmp(e, "\x7f" "ELF", 4) != 0 || e[4] != 2 || e[16] != 3) return cudaErrorNotSupported;      // not a 64-bit ET_DYN image
+    if (*(const uint16_t*)(e + 18) != 62) return cudaErrorNotSupported;                                 // not x86-64: a real cubin
+    uint64_t shoff; uint16_t shentsize, shnum;
+    memcpy(&shoff, e + 40, 8); memcpy(&shentsize, e + 58, 2); memcpy(&shnum, e + 60, 2);
+    const size_t bytes = (size_t)shoff + (size_t)shentsize * shnum;                                      // section headers close the file
+    char path[] = "/tmp/hostsim_lib_XXXXXX";
+    const int fd = mkstemp(path);
+    if (fd < 0) return cudaErrorInvalidValue;
+    const bool ok = write(fd, image, bytes) == (ssize_t)bytes;
+    close(fd);
+    void* h = ok ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : nullptr;
+    unlink(path);
+    if (!h) { fprintf(stderr, "hostsim: dlopen of a host-compiled kernel failed: %s\n", ok ? dlerror() : "short write"); return cudaErrorInvalidValue; }
+    *lib = (cudaLibrary_t)h;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaLibraryUnload(cudaLibrary_t lib) { if (lib) dlclose((void*)lib); return cudaSuccess; }
+static inline cudaError_t cudaLibraryGetKernel(cudaKernel_t* k, cudaLibrary_t lib, const char*) {
+    void* f = dlsym((void*)lib, "hostsim_jit_launch");
+    if (!f) return cudaErrorInvalidValue;
+    *k = (cudaKernel_t)f;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaLaunchKernel(const void* k, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
+    if (!k) return cudaErrorInvalidValue;
+    ((void (*)(unsigned, unsigned, size_t, void**))k)(grid.x, block.x, smem, args);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaKernelSetAttributeForDevice(cudaKernel_t, int, int, int) { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 // one process, one address space: an IPC handle is the pointer itself (several "ranks" of a test share a process)

@@ -5,8 +5,8 @@ retries, counters, host / device output paths -- over the kernels on the SIMT st
 The GPU tests run in a child pytest process started with ``--hostsim`` (tests/conftest.py points the ctypes binding
 at the host-compiled library before it is first loaded), so no handle ever crosses from one library to the other.
 What runs here also runs, identically, on the B200 in the `-m gpu` tier; what cannot run here: anything that needs
-torch.cuda, run-time compiled kernels (the library falls back to its interpreter kernels when a cubin cannot be
-loaded), CUDA graphs (it falls back to plain launches), and the sizes that only make sense on a GPU.
+torch.cuda, CUDA graphs (the library falls back to plain launches), and the sizes that only make sense on a GPU.
+Run-time specialised kernels DO run: the source the library generates is compiled for the host by a stand-in NVRTC.
 """
 import os
 import subprocess
@@ -23,6 +23,11 @@ SELECTIONS = {
     'closures_textures_c_client': (['tests/test_gpu_zzz_texture.py', 'tests/test_gpu_closure.py', 'tests/test_gpu_zzz_cabi_client.py'], ''),
     'weld_windows': (['tests/test_gpu_weld.py', 'tests/test_gpu_windows.py'], 'sphere or csg'),
     'guardband': (['tests/test_gpu_guardband.py'], 'twist_fast or scaled_up or square_jump'),
+    # the library's run-time specialisation end to end: jit_source(), the forced thread-run shapes, background compiles,
+    # the kernel cache, cudaLaunchKernel's argument arrays -- its generated source compiled for the host by a stand-in
+    # NVRTC (tests/hostsim/fake_nvrtc.cpp)
+    'specialised_kernels': (['tests/test_gpu_parity.py', 'tests/test_gpu_grouping.py'],
+                            '(jit and generate_matches_oracle and exact and (sphere or csg)) or (sample_grouping and cyl_x)'),
     # paths of sdfb200.cu's orchestration that only sizes beyond any emulation reach on a GPU (tests/hostsim_paths.py)
     'host_cut_rounds_overflow_retry_pipelined_output_slabs': (['tests/hostsim_paths.py'], ''),
 }

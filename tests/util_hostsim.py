@@ -113,10 +113,31 @@ def patched_library_sources(dst):
             text = _sub(text, r'static const size_t kVolBudgetBytes = \(size_t\)24 << 30;',
                         '#define kVolBudgetBytes (getenv("HOSTSIM_VOL_BUDGET") ? (size_t)atoll(getenv("HOSTSIM_VOL_BUDGET")) '
                         ': (size_t)24 << 30)', 1)
+            # $HOSTSIM_NVRTC: the stand-in compiler (tests/hostsim/fake_nvrtc.cpp) instead of libnvrtc
+            text = _sub(text, r'const char\* names\[\] = \{"libnvrtc\.so\.12",',
+                        'const char* names[] = {getenv("HOSTSIM_NVRTC") ? getenv("HOSTSIM_NVRTC") : "libnvrtc.so.12",', 1)
             text = _sub(text, r'std::max<size_t>\(\(size_t\)1 << 20, est_tiles \* 3072\)',
                         'std::max<size_t>(getenv("HOSTSIM_MIN_CUBES") ? (size_t)atoll(getenv("HOSTSIM_MIN_CUBES")) : (size_t)1 << 20, '
                         '(getenv("HOSTSIM_MIN_CUBES") ? (size_t)0 : est_tiles * 3072))', 1)
         open(os.path.join(dst, f.replace('.cu', '.cpp')), 'w').write(text)
+
+
+def build_fake_nvrtc():
+    """tests/hostsim/fake_nvrtc.cpp as a shared library; returns (path, directory of the patched device headers)."""
+    srcs = [os.path.join(CSRC, f) for f in ('sdf_ops.cuh', 'sdf_kernels.cuh', 'sdf_opcodes.h', 'mc_tables.inc', 'sdf_jit_entry.cuh')]
+    srcs += [os.path.join(HS, 'fake_nvrtc.cpp'), os.path.join(HS, 'cuda_runtime.h'), os.path.abspath(__file__)]
+    key = _digest(*srcs)
+    so = os.path.join(BUILD, 'libhostsim_nvrtc_%s.so' % key)
+    inc = os.path.join(BUILD, 'jitinc_%s' % key)
+    if not os.path.exists(so):
+        patched_sources(inc)
+        shutil.copy(os.path.join(CSRC, 'sdf_jit_entry.cuh'), os.path.join(inc, 'sdf_jit_entry.cuh'))
+        tmp = so + '.%d.tmp' % os.getpid()
+        r = subprocess.run(['g++', '-std=c++17', '-O1', '-fPIC', '-shared', os.path.join(HS, 'fake_nvrtc.cpp'), '-o', tmp],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-4000:]
+        os.replace(tmp, so)
+    return so, inc
 
 
 def build_library(sanitize=None):
