@@ -334,8 +334,8 @@ static inline unsigned long long max(unsigned long long a, unsigned long long b)
 // Host API stand-in: what sdfb200.cu / sdfb200_weld.cu call.  Everything executes at call time (a stream is a
 // label), device memory is host memory kept in a registry so that cudaPointerGetAttributes can tell it from
 // the caller's buffers, one fake device with HOSTSIM_SMS "SMs" (default 3: small grids, fast emulation).
-// Stream capture and loading run-time compiled cubins are refused, which sends the library down
-// its documented fallbacks (plain launches instead of a graph; interpreter kernels instead of NVRTC output).
+// A captured stream records closures that a graph launch replays; a real cubin cannot be loaded (the library then
+// runs its interpreter kernels), the "cubin" of the stand-in NVRTC (fake_nvrtc.cpp) is a host shared object.
 #include <dlfcn.h>
 #include <unistd.h>
 #include <chrono>
@@ -348,12 +348,16 @@ enum {
     cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100,
     cudaErrorInvalidDevice = 101, cudaErrorNotReady = 600, cudaErrorNotSupported = 801
 };
-struct hostsim_stream_ { int id; };
+// A stream is a label; while it is being captured its operations are recorded as closures (kernel parameters copied at
+// that moment, as CUDA does) and a graph launch replays them.
+struct hostsim_stream_ { int id; bool capturing = false; std::vector<std::function<void()>> ops; };
 struct hostsim_event_ { std::chrono::steady_clock::time_point t; };
 typedef hostsim_stream_* cudaStream_t;
 typedef hostsim_event_* cudaEvent_t;
-typedef struct hostsim_graph_* cudaGraph_t;
-typedef struct hostsim_graph_exec_* cudaGraphExec_t;
+struct hostsim_graph_ { std::vector<std::function<void()>> ops; };
+struct hostsim_graph_exec_ { std::vector<std::function<void()>> ops; };
+typedef hostsim_graph_* cudaGraph_t;
+typedef hostsim_graph_exec_* cudaGraphExec_t;
 typedef struct hostsim_kernel_* cudaKernel_t;
 typedef struct hostsim_library_* cudaLibrary_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -388,20 +392,25 @@ inline cudaError_t alloc(void** out, size_t bytes, cudaMemoryType type) {
 inline int device_count() { const char* e = getenv("HOSTSIM_DEVICES"); return e ? atoi(e) : 1; }
 inline int sm_count() { const char* e = getenv("HOSTSIM_SMS"); return e && atoi(e) > 0 ? atoi(e) : 3; }
 
+inline bool capturing(cudaStream_t s) { return s != nullptr && s->capturing; }
+
 template <class... KA, class... A>
-inline void launch_kernel(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t, A&&... args) {
+inline void launch_kernel(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, A&&... args) {
     std::tuple<std::decay_t<KA>...> held(std::forward<A>(args)...);       // kernel parameters are copied at launch
+    if (capturing(s)) { s->ops.push_back([=] { launch(grid, block, smem, [&] { std::apply(k, held); }); }); return; }
     launch(grid, block, smem, [&] { std::apply(k, held); });
 }
 // cudaLaunchKernel's `void** args` unpacked with the parameter types of the kernel's own signature
 template <class... KA, size_t... I>
-inline void launch_args_impl(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args, std::index_sequence<I...>) {
+inline void launch_args_impl(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args, cudaStream_t s,
+                             std::index_sequence<I...>) {
     std::tuple<std::decay_t<KA>...> held(*(std::decay_t<KA>*)args[I]...);
+    if (capturing(s)) { s->ops.push_back([=] { launch(grid, block, smem, [&] { std::apply(k, held); }); }); return; }
     launch(grid, block, smem, [&] { std::apply(k, held); });
 }
 template <class... KA>
-inline void launch_args(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args) {
-    launch_args_impl(k, grid, block, smem, args, std::index_sequence_for<KA...>());
+inline void launch_args(void (*k)(KA...), unsigned grid, unsigned block, size_t smem, void** args, cudaStream_t s) {
+    launch_args_impl(k, grid, block, smem, args, s, std::index_sequence_for<KA...>());
 }
 }  // namespace hostsim
 
@@ -446,28 +455,62 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
     return cudaSuccess;
 }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new hostsim_stream_{1}; return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st = nullptr) {
+    if (hostsim::capturing(st)) { st->ops.push_back([=] { if (n) memmove(d, s, n); }); return cudaSuccess; }
+    if (n) memmove(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr) {
+    if (hostsim::capturing(st)) { st->ops.push_back([=] { if (n) memset(d, v, n); }); return cudaSuccess; }
+    if (n) memset(d, v, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new hostsim_stream_(); (*s)->id = 1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new hostsim_event_(); return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new hostsim_event_(); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
-static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t, unsigned) { return cudaEventRecord(e); }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr) {
+    if (hostsim::capturing(st)) { st->ops.push_back([=] { e->t = std::chrono::steady_clock::now(); }); return cudaSuccess; }
+    e->t = std::chrono::steady_clock::now();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t st, unsigned) { return cudaEventRecord(e, st); }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
     return cudaSuccess;
 }
-static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
-static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+// stream capture -> graph: the recorded closures, replayed in order by every launch ($HOSTSIM_NO_CAPTURE refuses the
+// capture, which sends the library down its plain-launch fallback)
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, int) {
+    if (!s || s->capturing || getenv("HOSTSIM_NO_CAPTURE")) return cudaErrorNotSupported;
+    s->capturing = true; s->ops.clear();
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g) {
+    *g = nullptr;
+    if (!s || !s->capturing) return cudaErrorInvalidValue;
+    s->capturing = false;
+    *g = new hostsim_graph_();
+    (*g)->ops.swap(s->ops);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) {
+    if (!g) return cudaErrorInvalidValue;
+    *e = new hostsim_graph_exec_();
+    (*e)->ops = g->ops;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+    if (!e) return cudaErrorInvalidValue;
+    for (auto& op : e->ops) op();
+    return cudaSuccess;
+}
 // Run-time compiled kernels: a real cubin (NVRTC output) cannot be loaded -- the library then runs its interpreter
 // kernels; the "cubin" of tests/hostsim/fake_nvrtc.cpp is a host shared object and is dlopen'ed.
 static inline cudaError_t cudaLibraryLoadData(cudaLibrary_t* lib, const void* image, void*, void*, unsigned, void*, void*, unsigned) {
@@ -495,9 +538,9 @@ static inline cudaError_t cudaLibraryGetKernel(cudaKernel_t* k, cudaLibrary_t li
     *k = (cudaKernel_t)f;
     return cudaSuccess;
 }
-static inline cudaError_t cudaLaunchKernel(const void* k, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
+static inline cudaError_t cudaLaunchKernel(const void* k, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t s) {
     if (!k) return cudaErrorInvalidValue;
-    ((void (*)(unsigned, unsigned, size_t, void**))k)(grid.x, block.x, smem, args);
+    ((void (*)(unsigned, unsigned, size_t, void**, cudaStream_t))k)(grid.x, block.x, smem, args, s);
     return cudaSuccess;
 }
 static inline cudaError_t cudaKernelSetAttributeForDevice(cudaKernel_t, int, int, int) { return cudaSuccess; }

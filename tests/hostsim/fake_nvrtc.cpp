@@ -26,8 +26,8 @@ std::atomic<int> g_serial{0};
 
 const char* kEpilogue =
     "\n// ---- appended by tests/hostsim/fake_nvrtc.cpp\n"
-    "extern \"C\" void hostsim_jit_launch(unsigned grid, unsigned block, size_t smem, void** args) {\n"
-    "    hostsim::launch_args(jit_kernel, grid, block, smem, args);\n"
+    "extern \"C\" void hostsim_jit_launch(unsigned grid, unsigned block, size_t smem, void** args, cudaStream_t stream) {\n"
+    "    hostsim::launch_args(jit_kernel, grid, block, smem, args, stream);\n"
     "}\n";
 
 std::string read_all(const std::string& path) {

@@ -4,7 +4,9 @@ library (run by tests/test_hostsim_library_cpu.py in a child process started wit
   * rounds cut by the HOST: tile volumes beyond the budget (24 GB on the GPU, a few tiles here)
   * the retry after a work-list overflow (lists start at 1 M entries on the GPU, at 64 here)
   * host output pipelined over device-cut rounds (SDFB200_PIPE): progress words, partial copies
-  * device-resident output, count-only calls, a Z-slab of whole batch layers
+  * device-resident output as ONE captured and replayed graph per parameter set (cache of four), count-only calls,
+    Z-slabs of whole batch layers, the fused root gather played by three in-process ranks
+  * the default specialisation mode: interpreter kernels while the compiler runs in the background
 """
 import os
 
@@ -146,3 +148,83 @@ def test_fused_root_gather_protocol(case, monkeypatch):
         rep = compare_soups(got.reshape(-1, 3), whole.reshape(-1, 3))
         assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], (step, rep)
         root.release(which)
+
+
+class _DeviceBuffer:
+    """"Device" memory under the stand-in runtime: the triangle buffer of a SharedOutput (cudaMalloc'ed by the library)."""
+
+    def __init__(self, triangles):
+        from sdf_b200 import _abi
+        self.shared = _abi.SharedOutput(triangles, 0)
+        self.ptr = self.shared.buffer_ptr(0)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def read(self, n):
+        import ctypes
+        return np.frombuffer((ctypes.c_float * (n * 9)).from_address(self.ptr), np.float32).reshape(-1, 9).copy()
+
+
+def _graphs(capfd):
+    import re
+    return [int(m) for m in re.findall(r'graph=(\d+)', capfd.readouterr().err)]
+
+
+def test_device_resident_step_is_one_replayed_graph(case, monkeypatch, capfd):
+    """Device-resident output: the whole step -- counter reset, pre-pass, A, B, C, counter read-back -- is captured once
+    per set of launch parameters and replayed (the stand-in runtime records the captured operations, kernel parameters
+    copied at capture time as CUDA does, and replays them); a changed parameter captures a new graph, at most four are
+    kept; with capture refused the plain launches give the same triangles."""
+    from sdf_b200 import _abi
+    monkeypatch.setenv('SDFB200_DEBUG', '1')
+    h = _abi.ProgramHandle(case['h'].program)
+    X, Y, Z, tau = case['X'], case['Y'], case['Z'], case['tau']
+    n, stats, _ = h.generate(X, Y, Z, 32, True, 'exact', tau, None, 0)
+    dev = _DeviceBuffer(n + 16)
+    _graphs(capfd)
+    for _ in range(3):
+        dev.read(n)[:] = 0
+        n2, stats2, _ = h.generate(X, Y, Z, 32, True, 'exact', tau, dev, n + 16)
+        assert n2 == n
+        _same_as_oracle(case, dev.read(n), stats2)
+    assert _graphs(capfd) == [2, 2, 2]                      # the count-only call's graph + this one, replayed
+    seen = []
+    for k in range(6):                                      # six more parameter sets: the cache holds four graphs
+        n3, stats3, _ = h.generate(X, Y, Z, 32, True, 'exact', tau * (1.0 + 0.01 * (k + 1)), dev, n + 16)
+        assert n3 == n
+        _same_as_oracle(case, dev.read(n), stats3)
+        seen += _graphs(capfd)
+    assert seen == [3, 4, 4, 4, 4, 4], seen
+    monkeypatch.setenv('HOSTSIM_NO_CAPTURE', '1')
+    h2 = _abi.ProgramHandle(case['h'].program)
+    n4, stats4, _ = h2.generate(X, Y, Z, 32, True, 'exact', tau, dev, n + 16)
+    assert n4 == n and _graphs(capfd) == [0]
+    _same_as_oracle(case, dev.read(n), stats4)
+
+
+def test_default_mode_runs_on_the_interpreter_until_the_compiler_is_done(monkeypatch):
+    """SDFB200_JIT=1 (the default): a big enough call starts the compiles in the background and runs on the interpreter
+    kernels; once the specialised kernels are there later calls use them -- same triangles either way."""
+    import time
+    import sdf_b200 as S
+    from oracle import sdf_ref
+    from sdf_b200 import core
+    monkeypatch.setenv('SDFB200_JIT', '1')
+    f = S.sphere(1.1) - S.box(1.3).k(0.07)                   # a tree no other test compiles: nothing in the kernel cache
+    L, n = 1.25, 128                                         # 2^21 samples: "big enough to repay the compile"
+    kw = dict(step=2 * L / n, bounds=((-L,) * 3, (L,) * 3))
+    rpts, _ = sdf_ref.generate(f, **kw)
+    first = S.generate(f, verbose=False, **kw)
+    h, _ = core.program_handle(f)
+    deadline = time.time() + 120
+    share = None
+    while time.time() < deadline and share is None:
+        try:
+            share = h.jit_plan()[0]                          # waits for (and loads) the specialised tile kernel
+        except Exception:
+            time.sleep(0.5)
+    later = S.generate(f, verbose=False, **kw)
+    for pts in (first, later):
+        rep = compare_soups(pts, rpts)
+        assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'] and rep['n_ref'] > 20000, rep

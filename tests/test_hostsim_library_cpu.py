@@ -5,8 +5,9 @@ retries, counters, host / device output paths -- over the kernels on the SIMT st
 The GPU tests run in a child pytest process started with ``--hostsim`` (tests/conftest.py points the ctypes binding
 at the host-compiled library before it is first loaded), so no handle ever crosses from one library to the other.
 What runs here also runs, identically, on the B200 in the `-m gpu` tier; what cannot run here: anything that needs
-torch.cuda, CUDA graphs (the library falls back to plain launches), and the sizes that only make sense on a GPU.
-Run-time specialised kernels DO run: the source the library generates is compiled for the host by a stand-in NVRTC.
+torch.cuda and the sizes that only make sense on a GPU.  Run-time specialised kernels DO run (the source the library
+generates is compiled for the host by a stand-in NVRTC) and so does the one-graph step (a captured stream records
+closures, a graph launch replays them).
 """
 import os
 import subprocess
