@@ -74,6 +74,10 @@ struct State {
     // FAST-policy error injection: relative perturbation of approximate div / sqrt / sin / cos results, in units
     // of 2^-23 (0 = none); a deterministic hash of the operands picks the sign and magnitude
     double fast_ulps = 0.0;
+    // thread scheduling order (see launch): 0 ascending, 1 descending, >= 2 random permutation per pass, seeded by it
+    int schedule = 0;
+    unsigned long long rng = 1;
+    std::vector<unsigned> order;
 };
 
 inline State S;
@@ -181,7 +185,22 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
         for (;;) {
             const unsigned long before = S.progress;
             bool any = false;
-            for (unsigned t = 0; t < block; ++t) {
+            for (unsigned slot = 0; slot < block; ++slot) {
+                // the order in which ready threads get the host thread: ascending, descending, or a fresh pseudo-random
+                // permutation every pass -- a result that depends on it is a missing barrier (tests: racecheck)
+                unsigned t = slot;
+                if (S.schedule == 1) t = block - 1 - slot;
+                else if (S.schedule >= 2) {
+                    if (slot == 0) {
+                        S.order.resize(block);
+                        for (unsigned i = 0; i < block; ++i) S.order[i] = i;
+                        for (unsigned i = block - 1; i > 0; --i) {
+                            S.rng = S.rng * 6364136223846793005ull + 1442695040888963407ull;
+                            std::swap(S.order[i], S.order[(unsigned)((S.rng >> 33) % (i + 1))]);
+                        }
+                    }
+                    t = S.order[slot];
+                }
                 Fiber& f = S.fibers[t];
                 if (f.done) continue;
                 any = true;

@@ -78,6 +78,7 @@ void run_tile_eval(unsigned grid, const ProgramImage& img, const GridDesc& g, fl
 extern "C" {
 
 void hs_set_fast_ulps(double ulps) { hostsim::S.fast_ulps = ulps; }
+void hs_set_schedule(int mode) { hostsim::S.schedule = mode; hostsim::S.rng = 0x9e3779b97f4a7c15ull * (unsigned long long)(mode + 1); }
 unsigned long hs_switches(void) { return hostsim::S.switches; }
 int hs_spec_shape(int* kn, int* kshare) { *kn = EV::kN; *kshare = EV::kShare;
 #ifdef HOSTSIM_SPEC

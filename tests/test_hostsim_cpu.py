@@ -232,6 +232,43 @@ def test_result_does_not_depend_on_the_launch_shape(S, sims):
         assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'], (grids, rep)
 
 
+def test_result_does_not_depend_on_the_thread_schedule(S, sims, ref):
+    """The stand-in's racecheck: the threads of a CTA are run in ascending order, in descending order and in a fresh
+    random permutation after every rendezvous.  Between two barriers each thread runs to completion, so a read that
+    is not ordered after its write by a barrier / warp collective sees the old value under one of the schedules -- and
+    the triangles or the statistics change.  All kernels of the step, both tile kernels, the stream evaluator's ring."""
+    f = models.cfg_csg(S)
+    hs = sims(f)
+    _, _, (X, Y, Z), tau = _lattice(S, f, 'csg', 64)
+    P = models.random_points(5000, seed=2).astype(np.float32)
+    base = {}
+    try:
+        for mode in (0, 1, 2, 7):
+            hs.set_schedule(mode)
+            for prec in ('exact', 'mixed'):
+                t, st = hs.generate(X, Y, Z, 32, True, prec, tau, grids=(3, 2, 2, 3))
+                key = canonical(t)
+                if mode == 0:
+                    base[prec] = (key, st)
+                else:
+                    assert st == base[prec][1] and np.array_equal(key, base[prec][0]), (mode, prec)
+            d = hs.eval_f32(P, fast=True, grid=1)
+            if mode == 0:
+                base['eval'] = d
+            else:
+                assert np.array_equal(d, base['eval']), mode
+            fl = hs.skip_flags(X, Y, Z, 32)
+            base.setdefault('flags', fl)
+            assert np.array_equal(fl, base['flags']), mode
+    finally:
+        hs.set_schedule(0)
+
+
+def canonical(tris):
+    from util_cmp import canonical_triangles
+    return canonical_triangles(tris.reshape(-1, 3))
+
+
 def test_ragged_lattices_batch_sizes_and_empty_results(S, sims, ref):
     """Tail batches of 1..3 planes, lattices smaller than a batch, batch sizes that are not the tile size
     (sub-tiles: 40, 64), sparse off, nothing to mesh, a result buffer that is too small."""

@@ -269,6 +269,10 @@ class HostSim:
     def set_fast_ulps(self, ulps):
         self.lib.hs_set_fast_ulps(float(ulps))
 
+    def set_schedule(self, mode):
+        """Order in which the fibers of a CTA run: 0 ascending, 1 descending, >= 2 a seeded random permutation per pass."""
+        self.lib.hs_set_schedule(int(mode))
+
     def eval_f64(self, P, grid=3):
         P = np.ascontiguousarray(P, np.float64)
         out = np.empty(len(P), np.float64)
