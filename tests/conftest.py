@@ -27,7 +27,6 @@ def pytest_configure(config):
         nvrtc, inc = util_hostsim.build_fake_nvrtc()
         os.environ['HOSTSIM_NVRTC'] = nvrtc
         os.environ['HOSTSIM_JIT_INCLUDE'] = inc
-        os.environ['HOSTSIM_DIR'] = util_hostsim.HS
         # the library's kernel cache holds HOST objects here: one directory per version of the stand-in
         os.environ.setdefault('SDFB200_JIT_CACHE', inc.replace('jitinc_', 'jitcache_'))
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')

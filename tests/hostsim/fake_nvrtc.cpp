@@ -6,8 +6,8 @@
 // path runs on the host: source generation, candidate shapes, background compiles, the disk cache, argument
 // marshalling, the share axis handed to the classification kernel.
 //
-//   $HOSTSIM_JIT_INCLUDE   directory of the patched device headers (tests/util_hostsim.py)
-//   $HOSTSIM_DIR           tests/hostsim (cuda_runtime.h)
+//   $HOSTSIM_JIT_INCLUDE   directory of the patched device headers and the stand-in cuda_runtime.h the library
+//                          was built with (tests/util_hostsim.py build_fake_nvrtc)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,8 +62,7 @@ int nvrtcDestroyProgram(void** prog) {
 int nvrtcCompileProgram(void* prog, int, const char* const*) {
     Program* p = (Program*)prog;
     const char* inc = getenv("HOSTSIM_JIT_INCLUDE");
-    const char* hs = getenv("HOSTSIM_DIR");
-    if (!inc || !hs) { p->log = "fake nvrtc: HOSTSIM_JIT_INCLUDE / HOSTSIM_DIR not set"; return 1; }
+    if (!inc) { p->log = "fake nvrtc: HOSTSIM_JIT_INCLUDE not set"; return 1; }
     const char* tmp = getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp";
     const std::string base = std::string(tmp) + "/hostsim_jit_" + std::to_string((long long)getpid()) + "_" +
                              std::to_string(g_serial.fetch_add(1));
@@ -71,7 +70,7 @@ int nvrtcCompileProgram(void* prog, int, const char* const*) {
     if (FILE* f = fopen(cpp.c_str(), "w")) { fputs(p->src.c_str(), f); fputs(kEpilogue, f); fclose(f); }
     else { p->log = "fake nvrtc: cannot write " + cpp; return 1; }
     const std::string cmd = std::string("g++ -std=c++17 -O1 -fPIC -shared -ffp-contract=off -fno-strict-aliasing -Wno-unknown-pragmas "
-                                        "-Wl,-Bsymbolic-functions -I") + inc + " -I" + hs + " " + cpp + " -o " + so + " 2> " + err;
+                                        "-Wl,-Bsymbolic-functions -I") + inc + " " + cpp + " -o " + so + " 2> " + err;
     const int rc = system(cmd.c_str());
     p->log = read_all(err);
     if (rc == 0) {

@@ -132,7 +132,8 @@ def build_fake_nvrtc():
     if not os.path.exists(so):
         patched_sources(inc)
         shutil.copy(os.path.join(CSRC, 'sdf_jit_entry.cuh'), os.path.join(inc, 'sdf_jit_entry.cuh'))
-        tmp = so + '.%d.tmp' % os.getpid()
+        shutil.copy(os.path.join(HS, 'cuda_runtime.h'), os.path.join(inc, 'cuda_runtime.h'))      # a snapshot: units compiled
+        tmp = so + '.%d.tmp' % os.getpid()                                                         # later must match this library
         r = subprocess.run(['g++', '-std=c++17', '-O1', '-fPIC', '-shared', os.path.join(HS, 'fake_nvrtc.cpp'), '-o', tmp],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-4000:]
