@@ -1026,7 +1026,8 @@ __device__ __forceinline__ int mc_select_tiling_s(const McTablesSmem* t, int ind
 // Vertex on edge e (12 = centre) of the cube whose corner values are cvp[k * EXTRACT_THREADS], Lewiner
 // cube-local coordinates added to (x,y,z).  With w = 1/(eps+|v|) per corner the coordinate along an edge
 // is x + w_far/(w0+w1); across the edge both corners share the coordinate c, where the generic form
-// (c*w0 + c*w1)/(w0+w1) gives 0 or exactly 1.  1/x is the correctly rounded reciprocal (== 1.0/x).
+// (c*w0 + c*w1)/(w0+w1) gives 0 or exactly 1 whenever w0 + w1 is a positive number -- the remaining inputs (a NaN corner,
+// two infinite corners) are handled below.  1/x is the correctly rounded reciprocal (== 1.0/x).
 __device__ __forceinline__ void mc_vertex_s(const float* cvp, int e, int x, int y, int z, float* out) {
     const double eps = (double)FLT_EPSILON;
     double fx, fy, fz;
@@ -1041,6 +1042,9 @@ __device__ __forceinline__ void mc_vertex_s(const float* cvp, int e, int x, int 
         fx = dx ? q : (double)corner_x(k0);
         fy = dx ? (double)corner_y(k0) : (dy ? q : (double)corner_y(k0));
         fz = (dx | dy) ? (double)corner_z(k0) : q;
+        // a NaN corner (w = NaN) or two infinite ones (w0 + w1 = 0): the generic form is NaN in EVERY coordinate
+        // (0 * NaN, 0 / 0), and so is q
+        if (!(ff > 0.0)) { fx = q; fy = q; fz = q; }
     } else {
         double sx = 0, sy = 0, sz = 0, ff = 0;
 #pragma unroll

@@ -394,6 +394,14 @@ def test_extraction_kernel_equals_the_c_restatement_on_every_configuration(S, si
         want = ref.marching_cubes_soup(vol, 0.0).astype(np.float64) * 0.25 - 1.0
         r = compare_soups(got.reshape(-1, 3), want)
         assert r['count_equal'] and r['exact_triangles'] == r['n_ref'] and r['n_ref'] > 0, (shape, r)
+    # NaN, infinite, zero, denormal samples (a user's SDF can produce them: ellipsoid's centre is 0/0): the same bits as
+    # the C restatement -- a vertex next to a NaN corner is NaN in all three coordinates, as skimage's generic form gives
+    from util_cmp import soup_multiset_bits, special_value_volumes
+    ax12 = np.arange(12.0)
+    for vol in special_value_volumes():
+        got = hs.mc_volume(vol, ax12, ax12, ax12, grid=2)
+        want = ref.marching_cubes_soup(vol, 0.0)
+        assert soup_multiset_bits(got) == soup_multiset_bits(want) and len(got) > 3000
     # degenerate inputs the reference maps to an empty batch (core.py:53-56)
     assert len(hs.mc_volume(np.ones((5, 5, 5), np.float32), *[np.arange(5.0)] * 3)) == 0
     assert len(hs.mc_volume(np.ones((1, 5, 5), np.float32), np.arange(1.0), np.arange(5.0), np.arange(5.0))) == 0

@@ -78,3 +78,30 @@ def mesh_topology(points, decimals=None):
     return dict(V=len(uniq), E=len(ue), F=len(f), boundary=int((counts == 1).sum()),
                 nonmanifold=int((counts > 2).sum()), repeated_directed=int((dcounts > 1).sum()),
                 unbalanced=int(unbalanced))
+
+
+def soup_multiset_bits(points):
+    """The soup as a multiset of triangles compared by BIT PATTERN (NaN-aware, -0.0 != 0.0): Counter of 9-tuples of
+    uint32, each triangle rotated to its smallest representation, every NaN mapped to one pattern.  For volumes with
+    NaN / infinite samples, where the float comparisons of compare_soups are meaningless."""
+    from collections import Counter
+    t = np.array(points, dtype=np.float32).reshape(-1, 3, 3)
+    t[np.isnan(t)] = np.float32(np.nan)
+    u = t.view(np.uint32)
+    return Counter(min(tuple(int(x) for x in np.roll(tri, -k, axis=0).reshape(-1)) for k in range(3)) for tri in u)
+
+
+def special_value_volumes(count=6, n=12, seed=5, denormals=True):
+    """Noise volumes with 15 % of the samples replaced by NaN, +-inf, +-0, +-FLT_EPSILON, +-3e38 (and denormals)."""
+    rng = np.random.default_rng(seed)
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 3e38, -3e38, 1.1920929e-07, -1.1920929e-07]
+    if denormals:
+        specials += [1e-45, -1e-45, 1e-38]
+    specials = np.array(specials, np.float32)
+    out = []
+    for _ in range(count):
+        vol = rng.normal(size=(n, n, n)).astype(np.float32)
+        m = rng.random(vol.shape) < 0.15
+        vol[m] = rng.choice(specials, int(m.sum()))
+        out.append(vol)
+    return out
