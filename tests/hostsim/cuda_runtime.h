@@ -53,15 +53,35 @@ struct Warp {
     uint32_t part[2] = {0, 0};          // lanes that took part in the collective of buffer 0 / 1
 };
 
+// Context switch between fibers: a dozen instructions on x86-64 (glibc's swapcontext makes a signal-mask system call
+// per switch, a third of the suite's run time); ucontext elsewhere and under AddressSanitizer, which knows swapcontext.
+#if defined(__x86_64__) && !defined(__SANITIZE_ADDRESS__) && !defined(HOSTSIM_UCONTEXT)
+#define HOSTSIM_ASM_SWITCH 1
+extern "C" void hostsim_switch(void** save_sp, void* load_sp);
+__asm__(".text\n"
+        ".weak hostsim_switch\n"
+        ".type hostsim_switch,@function\n"
+        "hostsim_switch:\n"
+        "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+        "  movq %rsp, (%rdi)\n"
+        "  movq %rsi, %rsp\n"
+        "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+        "  ret\n"
+        ".size hostsim_switch,.-hostsim_switch\n");
+struct Context { void* sp = nullptr; };
+#else
+struct Context { ucontext_t uc; };
+#endif
+
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
     bool done = false;
 };
 
 struct State {
     uint3 thread_idx{0, 0, 0}, block_idx{0, 0, 0}, block_dim{1, 1, 1}, grid_dim{1, 1, 1};
     int cur = -1;
-    ucontext_t sched;
+    Context sched;
     std::vector<Fiber> fibers;
     std::vector<char*> stacks;
     unsigned alive = 0, bar_arrived = 0, bar_gen = 0;
@@ -88,10 +108,18 @@ inline void die(const char* what) {
     abort();
 }
 
+inline void switch_to(Context& from, Context& to) {
+#ifdef HOSTSIM_ASM_SWITCH
+    hostsim_switch(&from.sp, to.sp);
+#else
+    swapcontext(&from.uc, &to.uc);
+#endif
+}
+
 inline void yield() {
     ++S.switches;
     Fiber& f = S.fibers[(size_t)S.cur];
-    swapcontext(&f.ctx, &S.sched);
+    switch_to(f.ctx, S.sched);
 }
 
 inline void release_block_barrier() { S.bar_arrived = 0; ++S.bar_gen; ++S.progress; }
@@ -134,7 +162,7 @@ inline void fiber_exit() {
     // an exited thread no longer takes part: barriers the others wait at may now be complete
     if (w.arrived != 0 && w.arrived == (uint32_t)__builtin_popcount(w.alive)) release_warp(w);
     if (S.bar_arrived != 0 && S.bar_arrived == S.alive) release_block_barrier();
-    swapcontext(&f.ctx, &S.sched);
+    switch_to(f.ctx, S.sched);
     die("resumed a finished fiber");
 }
 
@@ -176,11 +204,20 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
         for (unsigned t = 0; t < block; ++t) {
             Fiber& f = S.fibers[t];
             f.done = false;
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = S.stacks[t];
-            f.ctx.uc_stack.ss_size = kStackBytes;
-            f.ctx.uc_link = nullptr;
-            makecontext(&f.ctx, (void (*)())trampoline, 0);
+#ifdef HOSTSIM_ASM_SWITCH
+            // a fresh stack that hostsim_switch "returns" into trampoline() from: six callee-saved registers, then the
+            // return address in a 16-byte aligned slot (so that the stack is aligned as after a call)
+            void** slot = (void**)(S.stacks[t] + kStackBytes - 16);
+            slot[0] = (void*)trampoline;
+            for (int r = 1; r <= 6; ++r) slot[-r] = nullptr;
+            f.ctx.sp = (void*)(slot - 6);
+#else
+            getcontext(&f.ctx.uc);
+            f.ctx.uc.uc_stack.ss_sp = S.stacks[t];
+            f.ctx.uc.uc_stack.ss_size = kStackBytes;
+            f.ctx.uc.uc_link = nullptr;
+            makecontext(&f.ctx.uc, (void (*)())trampoline, 0);
+#endif
         }
         for (;;) {
             const unsigned long before = S.progress;
@@ -206,7 +243,7 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
                 any = true;
                 S.cur = (int)t;
                 S.thread_idx = uint3{t, 0, 0};
-                swapcontext(&S.sched, &f.ctx);
+                switch_to(S.sched, f.ctx);
             }
             if (!any) break;
             if (S.progress == before) die("deadlock: a full pass over the CTA's threads changed nothing");
