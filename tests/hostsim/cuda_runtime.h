@@ -116,10 +116,45 @@ inline void switch_to(Context& from, Context& to) {
 #endif
 }
 
+// AddressSanitizer tracks one stack per thread: every fiber switch is announced (sanitizer/common_interface_defs.h), or
+// its stack bookkeeping -- and the reports that rest on it -- would be guesses
+#ifdef __SANITIZE_ADDRESS__
+extern "C" void __sanitizer_start_switch_fiber(void** fake_stack_save, const void* bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void* fake_stack_save, const void** bottom_old, size_t* size_old);
+inline const void* g_sched_stack = nullptr;
+inline size_t g_sched_stack_size = 0;
+inline void* g_sched_fake = nullptr;
+inline std::vector<void*> g_fiber_fake;
+#endif
+
+// scheduler -> fiber t
+inline void enter_fiber(unsigned t) {
+#ifdef __SANITIZE_ADDRESS__
+    __sanitizer_start_switch_fiber(&g_sched_fake, S.stacks[t], kStackBytes);
+    switch_to(S.sched, S.fibers[t].ctx);
+    __sanitizer_finish_switch_fiber(g_sched_fake, nullptr, nullptr);
+#else
+    switch_to(S.sched, S.fibers[t].ctx);
+#endif
+}
+
+// fiber -> scheduler (`dying`: the fiber never runs again)
+inline void leave_fiber(bool dying) {
+    Fiber& f = S.fibers[(size_t)S.cur];
+#ifdef __SANITIZE_ADDRESS__
+    const size_t me = (size_t)S.cur;
+    __sanitizer_start_switch_fiber(dying ? nullptr : &g_fiber_fake[me], g_sched_stack, g_sched_stack_size);
+    switch_to(f.ctx, S.sched);
+    __sanitizer_finish_switch_fiber(g_fiber_fake[me], &g_sched_stack, &g_sched_stack_size);
+#else
+    (void)dying;
+    switch_to(f.ctx, S.sched);
+#endif
+}
+
 inline void yield() {
     ++S.switches;
-    Fiber& f = S.fibers[(size_t)S.cur];
-    switch_to(f.ctx, S.sched);
+    leave_fiber(false);
 }
 
 inline void release_block_barrier() { S.bar_arrived = 0; ++S.bar_gen; ++S.progress; }
@@ -162,11 +197,14 @@ inline void fiber_exit() {
     // an exited thread no longer takes part: barriers the others wait at may now be complete
     if (w.arrived != 0 && w.arrived == (uint32_t)__builtin_popcount(w.alive)) release_warp(w);
     if (S.bar_arrived != 0 && S.bar_arrived == S.alive) release_block_barrier();
-    switch_to(f.ctx, S.sched);
+    leave_fiber(true);
     die("resumed a finished fiber");
 }
 
 inline void trampoline() {
+#ifdef __SANITIZE_ADDRESS__
+    __sanitizer_finish_switch_fiber(nullptr, &g_sched_stack, &g_sched_stack_size);        // first time on this stack
+#endif
     S.body();
     fiber_exit();
 }
@@ -187,6 +225,9 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
         S.stacks.push_back((char*)p);
     }
     ++S.launches;
+#ifdef __SANITIZE_ADDRESS__
+    if (g_fiber_fake.size() < block) g_fiber_fake.resize(block, nullptr);
+#endif
     S.body = std::move(body);
     S.grid_dim = uint3{grid, 1, 1};
     S.block_dim = uint3{block, 1, 1};
@@ -243,7 +284,7 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
                 any = true;
                 S.cur = (int)t;
                 S.thread_idx = uint3{t, 0, 0};
-                switch_to(S.sched, f.ctx);
+                enter_fiber(t);
             }
             if (!any) break;
             if (S.progress == before) die("deadlock: a full pass over the CTA's threads changed nothing");
