@@ -345,6 +345,17 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle|oracle/|oracle\.|libmc_oracle|sdf_ref', src, re.M), fn
 
 
+def test_product_knows_nothing_of_the_host_execution():
+    """tests/hostsim/ (the device code and the library executed on the host) is test infrastructure: no file of the
+    product, the bench or the driver entry points mentions it -- there is no route from the product to a CPU path."""
+    files = [os.path.join(ROOT, 'bench.py'), os.path.join(ROOT, '__graft_entry__.py'), os.path.join(ROOT, 'include', 'sdfb200.h')]
+    for base in ('sdf_b200', 'sdf'):
+        for dirpath, _, names in os.walk(os.path.join(ROOT, base)):
+            files += [os.path.join(dirpath, fn) for fn in names if fn.endswith(('.py', '.cu', '.cuh', '.h', '.inc'))]
+    for path in files:
+        assert not re.search(r'hostsim|HOSTSIM', open(path).read()), path
+
+
 def test_integration_md_stub_binds_the_library():
     """The minimal ctypes stub printed in INTEGRATION.md is executed as written: it loads the library,
     creates a program and reaches sdfb200_generate (which, without a GPU, reports "no CPU fallback")."""
