@@ -3,14 +3,14 @@
 // The device code of this repository (sdf_b200/csrc/sdf_ops.cuh, sdf_kernels.cuh) is written as
 // templated `__device__` bodies.  tests/util_hostsim.py compiles those very files with g++ against
 // this header, so that the CPU test suite (no GPU in the build container) executes the kernels' own
-// source: CUDA threads become fibers (ucontext) of one host thread, a CTA is a set of fibers run
-// round-robin, `__syncthreads` / warp collectives are rendezvous points between fibers, atomics are
+// source: CUDA threads become fibers of one host thread, a CTA is a set of fibers run round-robin
+// (ascending, descending or randomly permuted: State::schedule), `__syncthreads` / warp collectives are rendezvous points between fibers, atomics are
 // plain read-modify-writes (one host thread), `__shared__` is function-static storage (CTAs run one
 // after another), a TMA bulk copy is a memcpy that completes its mbarrier at once.
 //
 // What this does NOT model: memory ordering, bank conflicts, MUFU approximation error (the FAST math
 // policy runs its own formulas -- Cody-Waite reduction, polynomial atan2, the rotation form of the
-// circular array -- on correctly rounded host functions, optionally perturbed: HOSTSIM_FAST_ULPS),
+// circular array -- on correctly rounded host functions, optionally perturbed: State::fast_ulps),
 // timing.  It checks the LOGIC of the kernels: index arithmetic, masks, compaction, list protocols,
 // table look-ups, the marching-cubes arithmetic.
 #pragma once
