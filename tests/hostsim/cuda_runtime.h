@@ -5,8 +5,8 @@
 // this header, so that the CPU test suite (no GPU in the build container) executes the kernels' own
 // source: CUDA threads become fibers of one host thread, a CTA is a set of fibers run round-robin
 // (ascending, descending or randomly permuted: State::schedule), `__syncthreads` / warp collectives are rendezvous points between fibers, atomics are
-// plain read-modify-writes (one host thread), `__shared__` is function-static storage (CTAs run one
-// after another), a TMA bulk copy is a memcpy that completes its mbarrier at once.
+// plain read-modify-writes (one host thread), `__shared__` is function-static storage that every CTA
+// finds filled with garbage (CTAs run one after another), a TMA bulk copy is a memcpy that completes its mbarrier at once.
 //
 // What this does NOT model: memory ordering, bank conflicts, MUFU approximation error (the FAST math
 // policy runs its own formulas -- Cody-Waite reduction, polynomial atan2, the rotation form of the
@@ -211,6 +211,23 @@ inline void trampoline() {
 
 inline unsigned char* dyn_smem() { return S.dyn; }
 
+// Shared memory is neither zero nor the previous CTA's on arrival: the patched sources call note_shared() right after
+// every `__shared__` declaration (tests/util_hostsim.py); the first thread of a CTA to get there fills the variable
+// with garbage.  Dynamic shared memory is filled by launch().
+struct SharedSeen { unsigned long launch; unsigned block; };
+inline std::vector<std::pair<void*, SharedSeen>>& shared_seen() { static std::vector<std::pair<void*, SharedSeen>> v; return v; }
+inline void note_shared(void* p, size_t bytes) {
+    for (auto& e : shared_seen())
+        if (e.first == p) {
+            if (e.second.launch == S.launches && e.second.block == S.block_idx.x) return;
+            e.second = SharedSeen{S.launches, S.block_idx.x};
+            memset(p, 0xcd, bytes);
+            return;
+        }
+    shared_seen().push_back({p, SharedSeen{S.launches, S.block_idx.x}});
+    memset(p, 0xcd, bytes);
+}
+
 // Run `body` as a grid of `grid` CTAs of `block` threads (1-D), CTA after CTA.
 inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::function<void()> body) {
     if (block == 0 || block > 1024) die("bad block size");
@@ -235,6 +252,7 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
     for (unsigned b = 0; b < grid; ++b) {
         S.block_idx = uint3{b, 0, 0};
         S.alive = block; S.bar_arrived = 0;
+        if (S.dyn && dyn_bytes) memset(S.dyn, 0xcd, dyn_bytes);
         for (unsigned wi = 0; wi < 32; ++wi) {
             Warp& w = S.warps[wi];
             const unsigned lo = wi * 32;

@@ -57,6 +57,8 @@ def patched_sources(dst):
     k = _sub(k, r'extern __shared__ __align__\(16\) unsigned char smem_raw\[\];',
              'unsigned char* const smem_raw = hostsim::dyn_smem();', 1)
     assert 'asm' not in re.sub(r'//[^\n]*', '', k), 'unpatched inline assembly in sdf_kernels.cuh'
+    # every __shared__ variable is announced, so that each CTA finds garbage in it instead of its predecessor's data
+    k = _sub(k, r'(\n[ \t]+__shared__ [^;\n]*?\b(\w+)(?:\[[^;\n]*\])?;)', r'\1 hostsim::note_shared(&\2, sizeof(\2));', 6)
     open(os.path.join(dst, 'sdf_kernels.cuh'), 'w').write(k)
 
 
