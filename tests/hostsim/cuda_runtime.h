@@ -249,7 +249,16 @@ inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::functio
     S.grid_dim = uint3{grid, 1, 1};
     S.block_dim = uint3{block, 1, 1};
     S.fibers.resize(block);
-    for (unsigned b = 0; b < grid; ++b) {
+    // CTAs run one after another, in the order the schedule names (which CTA claims which work item, which one finishes last)
+    std::vector<unsigned> cta_order(grid);
+    for (unsigned i = 0; i < grid; ++i) cta_order[i] = S.schedule == 1 ? grid - 1 - i : i;
+    if (S.schedule >= 2)
+        for (unsigned i = grid; i > 1; --i) {
+            S.rng = S.rng * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(cta_order[i - 1], cta_order[(unsigned)((S.rng >> 33) % i)]);
+        }
+    for (unsigned bi = 0; bi < grid; ++bi) {
+        const unsigned b = cta_order[bi];
         S.block_idx = uint3{b, 0, 0};
         S.alive = block; S.bar_arrived = 0;
         if (S.dyn && dyn_bytes) memset(S.dyn, 0xcd, dyn_bytes);

@@ -260,8 +260,8 @@ def test_result_does_not_depend_on_the_launch_shape(S, sims):
 
 
 def test_result_does_not_depend_on_the_thread_schedule(S, sims, ref):
-    """The stand-in's racecheck: the threads of a CTA are run in ascending order, in descending order and in a fresh
-    random permutation after every rendezvous.  Between two barriers each thread runs to completion, so a read that
+    """The stand-in's racecheck: the threads of a CTA (and the CTAs of a launch) are run in ascending order, in descending
+    order and in a fresh random permutation after every rendezvous.  Between two barriers each thread runs to completion, so a read that
     is not ordered after its write by a barrier / warp collective sees the old value under one of the schedules -- and
     the triangles or the statistics change.  All kernels of the step, both tile kernels, the stream evaluator's ring."""
     f = models.cfg_csg(S)
