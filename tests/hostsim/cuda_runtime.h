@@ -231,6 +231,11 @@ inline void note_shared(void* p, size_t bytes) {
 // Run `body` as a grid of `grid` CTAs of `block` threads (1-D), CTA after CTA.
 inline void launch(unsigned grid, unsigned block, size_t dyn_bytes, std::function<void()> body) {
     if (block == 0 || block > 1024) die("bad block size");
+    static const bool env_read = [] {              // $HOSTSIM_SCHEDULE: the schedule for a whole process (pytest --hostsim)
+        if (const char* e = getenv("HOSTSIM_SCHEDULE")) { S.schedule = atoi(e); S.rng = 0x9e3779b97f4a7c15ull * (unsigned long long)(S.schedule + 1); }
+        return true;
+    }();
+    (void)env_read;
     if (dyn_bytes > S.dyn_cap) {
         free(S.dyn);
         S.dyn = (unsigned char*)aligned_alloc(128, (dyn_bytes + 127) & ~(size_t)127);
