@@ -228,3 +228,35 @@ def test_default_mode_runs_on_the_interpreter_until_the_compiler_is_done(monkeyp
     for pts in (first, later):
         rep = compare_soups(pts, rpts)
         assert rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'] and rep['n_ref'] > 20000, rep
+
+
+@pytest.mark.parametrize('jit', ['0', '2'])
+def test_streamed_float32_evaluator_through_the_abi(case, monkeypatch, jit):
+    """sdfb200_eval_f32 / _fast with host buffers (staged through the library) and with "device" buffers, interpreter
+    and run-time specialised stream kernels (on the GPU these entry points are driven with torch tensors)."""
+    import ctypes
+    from oracle import sdf_ref
+    from sdf_b200 import _abi
+    monkeypatch.setenv('SDFB200_JIT', jit)
+    h = _abi.ProgramHandle(case['h'].program)
+    n = 5000
+    P = models.random_points(n, seed=4).astype(np.float32)
+    r = sdf_ref.evaluate(case['f'], P.astype(np.float64)).reshape(-1)
+    out = np.empty(n, np.float32)
+    h.eval_f32(P, out, n)
+    assert np.max(np.abs(out - r)) < 1e-5
+    h.eval_f32_fast(P, out, n)
+    assert np.max(np.abs(out - r)) < 1e-4
+    dev_in, dev_out = _DeviceBuffer((n * 3 + 8) // 9 + 1), _DeviceBuffer(n // 9 + 1)
+    ctypes.memmove(dev_in.ptr, P.ctypes.data, P.nbytes)
+    h.eval_f32(dev_in, dev_out, n)
+    got = np.frombuffer((ctypes.c_float * n).from_address(dev_out.ptr), np.float32)
+    assert np.max(np.abs(got - r)) < 1e-5
+    # page-locking a caller's buffer and the plain device -> host copy (the multi-GPU host gather's two calls)
+    buf = np.zeros(n, np.float32)
+    _abi.host_register(buf.ctypes.data, buf.nbytes)
+    try:
+        rc = _abi.lib().sdfb200_copy_to_host(buf.ctypes.data, dev_out.ptr, buf.nbytes, 0, None)
+        assert rc == 0 and np.array_equal(buf, got)
+    finally:
+        _abi.host_unregister(buf.ctypes.data)

@@ -156,7 +156,8 @@ def build_library(sanitize=None):
              os.path.abspath(__file__)]
     if sanitize is None:
         sanitize = bool(os.environ.get('HOSTSIM_SANITIZE'))
-    key = _digest(*srcs, extra='asan' if sanitize else '')
+    coverage = bool(os.environ.get('HOSTSIM_COVERAGE'))         # gcov instrumentation (tools/hostsim_coverage.py --library)
+    key = _digest(*srcs, extra=('asan' if sanitize else '') + ('gcov' if coverage else ''))
     so = os.path.join(BUILD, 'libsdfb200_hostsim_%s.so' % key)
     if os.path.exists(so):
         return so
@@ -166,9 +167,11 @@ def build_library(sanitize=None):
              '-I', work, '-I', HS]
     if sanitize:
         flags += ['-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-fno-omit-frame-pointer']
+    if coverage:
+        flags = [f for f in flags if f != '-O1'] + ['-O0', '-g', '--coverage']
     tmp = so + '.%d.tmp' % os.getpid()
     r = subprocess.run(['g++'] + flags + [os.path.join(work, 'sdfb200.cpp'), os.path.join(work, 'sdfb200_weld.cpp'), '-o', tmp,
-                                          '-ldl', '-lpthread'], capture_output=True, text=True)
+                                          '-ldl', '-lpthread'], capture_output=True, text=True, cwd=work)
     assert r.returncode == 0, 'hostsim library build failed:\n' + r.stderr[-8000:]
     os.replace(tmp, so)
     return so
