@@ -5,6 +5,8 @@ runs DESIGN.md section 2.1 cites.  No GPU involved; minutes each.
   python tools/hostsim_sweeps.py odd-lattices       the host-compiled LIBRARY on 412 odd lattices (batch sizes 1..200, one-sample axes)
   python tools/hostsim_sweeps.py guard-band         `exact` (4 ulp injected into the FAST pass) == `f64` on all 234 trees, 40^3
   python tools/hostsim_sweeps.py special-volumes    extraction kernel vs the C restatement on NaN / inf / denormal volumes
+  python tools/hostsim_sweeps.py magnitudes         the host-compiled LIBRARY on anisotropic steps, lattices 10 .. 3e6 away from the
+                                                    origin, models scaled by 1e-4 .. 1e6, auto bounds (the guard band scales with |coords|)
 """
 import itertools
 import os
@@ -141,8 +143,43 @@ def special_volumes():
     return bad
 
 
+def magnitudes():
+    import util_hostsim as U
+    from sdf_b200 import _abi
+    _abi.LIB_PATH = U.build_library()
+    os.environ['SDFB200_JIT'] = '0'
+    import models
+    import sdf_b200 as S
+    from oracle import sdf_ref
+    from util_cmp import compare_soups
+    state = dict(bad=0, cases=0)
+
+    def check(f, label, **kw):
+        pts, info = S.generate(f, verbose=False, return_info=True, **kw)
+        rpts, rst = sdf_ref.generate(f, **kw)
+        rep = compare_soups(pts, rpts)
+        state['cases'] += 1
+        if not (rep['count_equal'] and rep['exact_triangles'] == rep['n_ref'] and rep['n_ref'] > 0 and
+                (info['skipped'], info['empty'], info['nonempty']) == (rst['skipped'], rst['empty'], rst['nonempty'])):
+            state['bad'] += 1
+            print('DIFF', label, rep, info, rst)
+    g = models.cfg_gearlike(S)
+    for step in ((0.05, 0.07, 0.031), (0.11, 0.04, 0.04), (0.033, 0.033, 0.2)):
+        check(g, 'anisotropic %r' % (step,), step=step, bounds=((-2.2, -2.3, -0.9), (2.25, 2.2, 0.95)))
+    for off in (10.0, 1e3, 1e5, -3e6):
+        f = S.sphere(1).translate((off, 0.5 * off, 0)) - S.box(0.8).translate((off + 0.6, 0.5 * off, 0.2)).k(0.05)
+        check(f, 'offset %g' % off, step=2.6 / 48, bounds=((off - 1.3, 0.5 * off - 1.3, -1.3), (off + 1.3, 0.5 * off + 1.3, 1.3)))
+    for sc in (1e-4, 1e-2, 1e3, 1e6):
+        f = (S.sphere(1) & S.box(1.5)).scale(sc) | S.capsule((-sc, 0, 0), (sc, 0, 0), 0.3 * sc).k(0.1 * sc)
+        check(f, 'scale %g' % sc, step=2.6 * sc / 48, bounds=((-1.3 * sc,) * 3, (1.3 * sc,) * 3))
+    for name in ('sphere', 'csg'):
+        check(models.CONFIGS[name](S), 'samples %s' % name, samples=40 ** 3)
+    print('magnitudes: %d cases, %d differences' % (state['cases'], state['bad']))
+    return state['bad']
+
+
 if __name__ == '__main__':
-    sweeps = {'special-points': special_points, 'odd-lattices': odd_lattices, 'guard-band': guard_band,
+    sweeps = {'magnitudes': magnitudes, 'special-points': special_points, 'odd-lattices': odd_lattices, 'guard-band': guard_band,
               'special-volumes': special_volumes}
     if len(sys.argv) != 2 or sys.argv[1] not in sweeps:
         sys.exit(__doc__)
