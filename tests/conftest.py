@@ -28,7 +28,7 @@ def pytest_configure(config):
         os.environ['HOSTSIM_NVRTC'] = nvrtc
         os.environ['HOSTSIM_JIT_INCLUDE'] = inc
         # the library's kernel cache holds HOST objects here: one directory per version of the stand-in
-        os.environ.setdefault('SDFB200_JIT_CACHE', inc.replace('jitinc_', 'jitcache_'))
+        os.environ.setdefault('SDFB200_JIT_CACHE', inc.replace('jitinc_', 'jitcache_') + ('_asan' if os.environ.get('HOSTSIM_SANITIZE') else ''))
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
     config.addinivalue_line('markers', 'fullsize: GPU parity at the sizes BASELINE.json states (minutes of CPU oracle time; also marked gpu)')
 

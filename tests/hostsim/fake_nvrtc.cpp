@@ -69,8 +69,10 @@ int nvrtcCompileProgram(void* prog, int, const char* const*) {
     const std::string cpp = base + ".cpp", so = base + ".so", err = base + ".log";
     if (FILE* f = fopen(cpp.c_str(), "w")) { fputs(p->src.c_str(), f); fputs(kEpilogue, f); fclose(f); }
     else { p->log = "fake nvrtc: cannot write " + cpp; return 1; }
-    const std::string cmd = std::string("g++ -std=c++17 -O1 -fPIC -shared -ffp-contract=off -fno-strict-aliasing -Wno-unknown-pragmas "
-                                        "-Wl,-Bsymbolic-functions -I") + inc + " " + cpp + " -o " + so + " 2> " + err;
+    // the unit shares hostsim::S with the library: it must be built like it (the sanitized build switches fibers differently)
+    const char* san = getenv("HOSTSIM_SANITIZE") ? "-g -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer " : "";
+    const std::string cmd = std::string("g++ -std=c++17 -O1 -fPIC -shared -ffp-contract=off -fno-strict-aliasing -Wno-unknown-pragmas ") + san +
+                            "-Wl,-Bsymbolic-functions -I" + inc + " " + cpp + " -o " + so + " 2> " + err;
     const int rc = system(cmd.c_str());
     p->log = read_all(err);
     if (rc == 0) {
